@@ -1,0 +1,173 @@
+/*
+ * nmi_b200.h -- C ABI of the B200-native NMI pose search.
+ *
+ * This is the drop-in boundary for orbslam2_NMI's localization hot path
+ * (Thirdparty/Localization + Thirdparty/CUDA_Functions).  Plain pointers and
+ * sizes only; no torch / OpenCV / GL types.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repo).
+ * The reference-named C++ drop-ins (CUDAF::NMIWithCuda_noMask, NmiObjects,
+ * Image, Rendering<>, NmiSearchKernel, helperFunctions::find_max_elements,
+ * setupCam) live in include/compat/ and are thin wrappers over this ABI.
+ *
+ * Conventions
+ *   - images: row-major u8, top-down rows, stride == W;
+ *   - Twc: row-major 4x4 fp32 camera->world, CV axes (x right, y down, z fwd);
+ *   - grid arrays are ordered {x, y, z};
+ *   - scores / rating order: linear index
+ *       l = ((((wz*nWy + wy)*nWx + wx)*nSz + sz)*nSy + sy)*nSx + sx
+ *     == the reference's rating[wz][wy][wx][sz][sy][sx] (localization.hpp:36);
+ *   - all functions return NMI_OK (0) or an error code; nmi_last_error() gives
+ *     the message (the reference prints and exit()s instead, kernel.cu:53).
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     NMI_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef NMI_B200_H
+#define NMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMI_OK 0
+#define NMI_ERR_INVALID 1   /* bad argument                                  */
+#define NMI_ERR_CUDA 2      /* CUDA runtime error / no usable device         */
+#define NMI_ERR_STATE 3     /* camera / model / frame not set yet            */
+#define NMI_ERR_NO_WINNER 4 /* every score < 0: the reference's max-vector   */
+                            /* is empty (helperFunctions.cpp:50-103)         */
+
+#define NMI_SCORE_ENMI 0 /* kernel.cuh:22  (H(A)+H(B))/H(A,B)                */
+#define NMI_SCORE_SUC 1  /* kernel.cuh:23  2(1-H(A,B)/(H(A)+H(B))) (default) */
+
+#define NMI_EMPTY 0xFFFFFFFFu /* z-buffer winner for "no primitive"          */
+
+typedef struct nmi_ctx nmi_ctx;
+
+/* YAML Camera.* and NMI.Render.* (localization.cpp:131-181) */
+typedef struct {
+  int W, H;
+  double fx, fy, cx, cy;
+  double zn, zf;    /* NMI.Render.NearPlane / FarPlane */
+  float point_size; /* NMI.Render.PointSize            */
+} nmi_camera;
+
+/* NmiSearchKernel's grid part (nmiSearchKernel.hpp:29-30) */
+typedef struct {
+  int nS[3];      /* numSynth{X,Y,Z} */
+  int nW[3];      /* numWarp{X,Y,Z}  */
+  float stepT[3]; /* step{X,Y,Z}     metres  */
+  float stepR[3]; /* stepRad{X,Y,Z}  radians */
+} nmi_grid;
+
+/* compile-time knobs of the reference made run-time */
+typedef struct {
+  int bins;       /* 256 (NMI.cuh:39) or 64                                   */
+  int score_mode; /* NMI_SCORE_SUC / NMI_SCORE_ENMI (kernel.cuh:22-23)        */
+  int bg;         /* nmi_prop_BG (allProperties.hpp:39); 0 skips value-0 px   */
+  int variant;    /* histogram kernel variant, 0 = default    */
+} nmi_flags;
+
+typedef struct {
+  int32_t best_s[3]; /* bestSynth{X,Y,Z} */
+  int32_t best_w[3]; /* bestWarp{X,Y,Z}  */
+  int64_t best_index; /* linear index l, -1 when there is no winner           */
+  float best_score;   /* NmiSearchKernel::NMI                                 */
+  uint64_t key;       /* (bits(max(score,0)) << 32) | (0xFFFFFFFF - l)        */
+  float gpu_ms;       /* device time of the search (CUDA events)              */
+} nmi_result;
+
+/* ---- context ----------------------------------------------------------- */
+/* Replaces Rendering::initGL / CreateFrameBuffers (rendering.hpp:239,332) and
+ * initHistogram256all / closeHistogram256all (NMI.cu:171-186): all scratch is
+ * owned by the context and reused; nothing is allocated per evaluation.      */
+int nmi_ctx_create(int device, nmi_ctx **out);
+void nmi_ctx_destroy(nmi_ctx *ctx);
+const char *nmi_last_error(void);
+/* CUDA stream (cudaStream_t) every kernel of this context is enqueued on.    */
+void *nmi_ctx_stream(nmi_ctx *ctx);
+int nmi_ctx_sync(nmi_ctx *ctx);
+
+/* ---- model / camera / frame -------------------------------------------- */
+/* Rendering ctor + initVBO projection (rendering.hpp:167-236, 196-202).      */
+int nmi_set_camera(nmi_ctx *ctx, const nmi_camera *cam);
+/* loadXYZ -> VBO upload (objloader.cpp:225-264, rendering.hpp:205-217).
+ * xyzi: n x {x, y, z, I}, I = red/256 as the reference stores it.            */
+int nmi_set_points(nmi_ctx *ctx, const float *xyzi_host, size_t n);
+int nmi_set_points_device(nmi_ctx *ctx, const void *xyzi_dev, size_t n);
+/* Image::loadOriginal (image.cpp:130-135): H2D upload of the grey frame.     */
+int nmi_set_frame(nmi_ctx *ctx, const uint8_t *gray_host, int W, int H);
+int nmi_set_frame_device(nmi_ctx *ctx, const void *gray_dev, int W, int H);
+
+/* ---- the batched search (one call per grid) ----------------------------- */
+/* Replaces the six-nested loop of Tracking::RelocalizeWithNMI
+ * (src/Tracking.cc:1871-1905): Image::calculateWarping, nS x
+ * renderToTextureOnGPU, nS*nW x CUDAF::NMIWithCuda_noMask and
+ * helperFunctions::find_max_elements.  scores_host (optional, nP floats)
+ * receives the rating array.  Synchronous.                                   */
+int nmi_search(nmi_ctx *ctx, const float Twc[16], const nmi_grid *grid,
+               const nmi_flags *flags, nmi_result *out, float *scores_host);
+
+/* Multi-GPU form.  Scores only this rank's slice of the grid (see
+ * nmi_partition) and writes the packed local winner key to key_dev (device
+ * u64, e.g. the send buffer of an NCCL max-allreduce).  Asynchronous on
+ * nmi_ctx_stream(); scores_dev (optional, nP floats, device) receives this
+ * rank's scores, others untouched.                                           */
+int nmi_search_enqueue(nmi_ctx *ctx, const float Twc[16], const nmi_grid *grid,
+                       const nmi_flags *flags, int rank, int world,
+                       void *key_dev, void *scores_dev);
+/* Pose-grid partitioner: axis 0 = synthetic views, 1 = warps.    */
+int nmi_partition(const nmi_grid *grid, int rank, int world, int *axis,
+                  int *begin, int *end);
+/* find_max_elements' answer from a (reduced) key.                            */
+int nmi_decode_key(const nmi_grid *grid, uint64_t key, nmi_result *out);
+
+/* ---- stage-level entry points (the reference's own call granularity) ---- */
+/* Rendering::renderToTextureOnGPU(calculateTranslation(sx,sy,sz))
+ * (rendering.hpp:530-630, 644-665).  Returns an opaque render handle in
+ * *handle -- the GL-free stand-in for getrenderedTexture() (rendering.hpp:749).*/
+int nmi_render_cell(nmi_ctx *ctx, const float Twc[16], const nmi_grid *grid,
+                    int sx, int sy, int sz, unsigned int *handle);
+/* Image::calculateWarping (image.cpp:115-128): all nW warps of the frame.    */
+int nmi_warp_cells(nmi_ctx *ctx, const nmi_grid *grid);
+/* Image::getImageGPU(z,y,x).data (image.cpp:142): device pointer, W*H u8.    */
+int nmi_warp_ptr(nmi_ctx *ctx, const nmi_grid *grid, int wx, int wy, int wz,
+                 void **dev_ptr);
+/* CUDAF::NMIWithCuda_noMask (kernel.cuh:37, kernel.cu:49-114): one evaluation
+ * of a device-resident warped image against a render handle.                 */
+int nmi_eval_pair(nmi_ctx *ctx, const void *warped_dev, unsigned int handle,
+                  int W, int H, const nmi_flags *flags, float *score_host);
+
+/* ---- host-side helpers of the search driver ----------------------------- */
+/* Rendering::calculateTranslation (rendering.hpp:644-665)                    */
+void nmi_cell_translation(const float Twc[16], const nmi_grid *grid, int sx,
+                          int sy, int sz, float t[3]);
+/* Image ctor warp matrices (image.cpp:76-108) -> inverse map used by warp.   */
+void nmi_cell_homography_inv(const nmi_camera *cam, const nmi_grid *grid,
+                             int wx, int wy, int wz, float minv[9]);
+/* Tracking::CalculateNMIRelocalization (src/Tracking.cc:2374-2419)           */
+void nmi_apply_winner(const float Twc[16], const nmi_grid *grid,
+                      const int32_t s[3], const int32_t w[3],
+                      float Twc_new[16]);
+/* NmiSearchKernel::isMiddle / resizeKernel (nmiSearchKernel.cpp:99-141)      */
+int nmi_grid_is_middle(const nmi_grid *grid, const int32_t s[3],
+                       const int32_t w[3]);
+void nmi_grid_resize(nmi_grid *grid, const int32_t s[3], const int32_t w[3]);
+
+/* ---- parity / debug read-backs (results of the LAST search or stage) ---- */
+int nmi_get_render(nmi_ctx *ctx, int s, uint8_t *host);    /* W*H u8         */
+int nmi_get_winners(nmi_ctx *ctx, int s, uint32_t *host);  /* W*H u32        */
+int nmi_get_warp(nmi_ctx *ctx, int w, uint8_t *host);      /* W*H u8         */
+/* integer histograms of pair (s, w): J bins*bins, HA/HB bins (u32)           */
+int nmi_get_hist(nmi_ctx *ctx, int s, int w, const nmi_flags *flags,
+                 uint32_t *J, uint32_t *HA, uint32_t *HB, float *score);
+/* per-stage device times of the last search, ms:
+ * [0] params+cull [1] project [2] resolve [3] warp [4] hist+score [5] argmax
+ * [6] total.  launches = kernels launched by the last search.                */
+int nmi_get_timings(nmi_ctx *ctx, float ms[8], int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,712 @@
+// capi.cu -- the C ABI (include/nmi_b200.h) over the sm_100a kernels.
+//
+// One nmi_ctx owns a device, a stream and every scratch buffer; nothing is
+// allocated per evaluation (the reference allocates/frees 10 buffers and
+// registers a GL texture per evaluation, kernel.cu:52-113).  A grid search is
+// params-upload + 6 kernels on one stream, whatever the grid size:
+//   cull_compact -> project_splat -> resolve -> warp -> joint_hist_score -> argmax
+// No CPU fallback exists: without a usable CUDA device every entry point fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nmi_internal.h"
+
+namespace nmi {
+
+// project.cu (not in the header: only capi uses them)
+void launch_cull_compact(const float4* pts, uint32_t n, const ViewConst& vc, const float c0[3],
+                         const float margin[3], float4* out_pts, uint32_t* out_idx,
+                         uint32_t* counter, cudaStream_t st);
+void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32_t* counter,
+                          const float4* centres, int nviews, const ViewConst& vc,
+                          unsigned long long* zbuf, size_t P, cudaStream_t st);
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+}  // namespace nmi
+
+using namespace nmi;
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      char buf__[512];                                                                   \
+      snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+               __FILE__, __LINE__);                                                      \
+      set_error(buf__);                                                                  \
+      return NMI_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define REQUIRE(cond, code, msg) \
+  do {                           \
+    if (!(cond)) {               \
+      set_error(msg);            \
+      return code;               \
+    }                            \
+  } while (0)
+
+namespace {
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+}  // namespace
+
+struct nmi_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  bool timed = false;
+
+  bool has_cam = false, has_frame = false;
+  nmi_camera cam{};
+  size_t P = 0, pitch = 0;
+
+  DevBuf<float4> pts;
+  DevBuf<uint8_t> val;
+  size_t n_pts = 0;
+  DevBuf<float4> cpts;    // compacted survivors of the cull
+  DevBuf<uint32_t> cidx;  // their original indices
+  DevBuf<uint32_t> counter;
+
+  DevBuf<uint8_t> frame;
+  uint8_t* h_frame = nullptr;  // pinned staging for host frames
+  size_t h_frame_cap = 0;
+
+  DevBuf<unsigned long long> zbuf;
+  size_t zbuf_clean = 0;  // elements known to hold ~0
+  DevBuf<uint8_t> renders, warps;
+  DevBuf<float> scores;
+  DevBuf<unsigned long long> key;
+  DevBuf<unsigned char> params;  // device copy of the per-search parameter block
+  unsigned char* h_params = nullptr;
+  size_t h_params_cap = 0;
+
+  // single-evaluation (stage API) + parity scratch
+  DevBuf<uint8_t> one_render, one_warp;
+  DevBuf<uint32_t> winners, dumpJ, dumpH;
+  DevBuf<float> one_score;
+  DevBuf<int2> zero_pair;  // device int2 {0,0}: the pair list of a single evaluation
+
+  // last search
+  bool has_search = false;
+  nmi_grid grid{};
+  float Twc[16] = {};
+  int nvl = 0, nwl = 0;  // local views / warps held in renders / warps
+  int v_begin = 0, w_begin = 0;
+  size_t off_centres = 0;
+  int launches = 0;
+};
+
+namespace {
+
+int ensure_pinned(unsigned char** p, size_t* cap, size_t n) {
+  if (n <= *cap) return NMI_OK;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = 0;
+  CK(cudaMallocHost(p, n));
+  *cap = n;
+  return NMI_OK;
+}
+
+int ensure_zbuf(nmi_ctx* c, size_t elems) {
+  if (elems > c->zbuf.cap) {
+    CK(c->zbuf.reserve(elems));
+    c->zbuf_clean = 0;
+  }
+  if (c->zbuf_clean < elems) {
+    launch_fill_u64(c->zbuf.p, c->zbuf.cap, ~0ull, c->stream);
+    CK(cudaGetLastError());
+    c->zbuf_clean = c->zbuf.cap;
+  }
+  return NMI_OK;
+}
+
+bool valid_grid(const nmi_grid* g) {
+  if (!g) return false;
+  long np = 1;
+  for (int k = 0; k < 3; k++) {
+    if (g->nS[k] < 1 || g->nW[k] < 1 || g->nS[k] > 4096 || g->nW[k] > 4096) return false;
+    np *= (long)g->nS[k] * g->nW[k];
+    if (np > (1l << 26)) return false;
+  }
+  return true;
+}
+
+bool valid_flags(const nmi_flags* f) {
+  return f && (f->bins == 256 || f->bins == 64) &&
+         (f->score_mode == NMI_SCORE_SUC || f->score_mode == NMI_SCORE_ENMI) && f->variant >= 0 &&
+         f->variant <= 3;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Render `nviews` cells whose centres sit at d_centres into images[0..nviews).
+int render_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nviews,
+                 const float margin[3], bool recull, uint8_t* images, uint32_t* winners) {
+  if (recull) {
+    CK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
+    const float c0[3] = {c->Twc[3], c->Twc[7], c->Twc[11]};
+    launch_cull_compact(c->pts.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
+                        c->counter.p, c->stream);
+    c->launches++;
+  }
+  if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
+  launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->zbuf.p, c->P,
+                       c->stream);
+  c->launches++;
+  if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
+  launch_resolve(c->zbuf.p, c->val.p, nviews, c->P, images, c->pitch, winners, c->stream);
+  c->launches++;
+  CK(cudaGetLastError());
+  return NMI_OK;
+}
+
+int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_flags* f, int rank,
+                int world, unsigned long long* key_dev, float* scores_dev) {
+  REQUIRE(c && Twc, NMI_ERR_INVALID, "null ctx / Twc");
+  REQUIRE(valid_grid(g), NMI_ERR_INVALID, "invalid grid (counts must be 1..4096, nP <= 2^26)");
+  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags (bins 256|64, score 0|1, variant 0..3)");
+  REQUIRE(c->has_cam && c->n_pts > 0 && c->has_frame, NMI_ERR_STATE,
+          "camera, model and frame must be set before a search");
+  CK(cudaSetDevice(c->device));
+
+  const int nS = g->nS[0] * g->nS[1] * g->nS[2], nW = g->nW[0] * g->nW[1] * g->nW[2];
+  const size_t nP = (size_t)nS * nW;
+  int axis = 0, b = 0, e = 0;
+  if (nmi_partition(g, rank, world, &axis, &b, &e) != NMI_OK) {
+    set_error("invalid rank / world");
+    return NMI_ERR_INVALID;
+  }
+  const int vb = axis == 0 ? b : 0, ve = axis == 0 ? e : nS;
+  const int wb = axis == 1 ? b : 0, we = axis == 1 ? e : nW;
+  const int nvl = ve - vb, nwl = we - wb;
+  const size_t npl = (size_t)nvl * nwl;
+  REQUIRE(nvl <= kMaxViewsPerLaunch * 64, NMI_ERR_INVALID, "too many synthetic views");
+  REQUIRE(c->P / 16384 + 2 < 1024, NMI_ERR_INVALID, "image too large for the histogram kernel");
+
+  // ---- host parameter block: centres | minv | pairs | out_index ----
+  const size_t off_c = 0;
+  const size_t off_m = align_up(off_c + sizeof(float4) * (size_t)nvl, 256);
+  const size_t off_p = align_up(off_m + sizeof(float) * 9 * (size_t)nwl, 256);
+  const size_t off_i = align_up(off_p + sizeof(int2) * npl, 256);
+  const size_t bytes = align_up(off_i + sizeof(uint32_t) * npl, 256);
+  if (int rc = ensure_pinned(&c->h_params, &c->h_params_cap, bytes)) return rc;
+  CK(c->params.reserve(bytes));
+
+  ViewConst vc;
+  make_view_const(c->cam, Twc, &vc);
+  float margin[3] = {0, 0, 0};
+  float4* hc = reinterpret_cast<float4*>(c->h_params + off_c);
+  for (int s = vb; s < ve; s++) {
+    const int sx = s % g->nS[0], sy = (s / g->nS[0]) % g->nS[1], sz = s / (g->nS[0] * g->nS[1]);
+    float t[3];
+    nmi_cell_translation(Twc, g, sx, sy, sz, t);
+    hc[s - vb] = make_float4(Twc[3] + t[0], Twc[7] + t[1], Twc[11] + t[2], 0.0f);
+    // camera-frame offset of this view (exact per-view shift of Pc), for the cull margin
+    const double ox = (double)vc.r0[0] * t[0] + (double)vc.r0[1] * t[1] + (double)vc.r0[2] * t[2];
+    const double oy = (double)vc.r1[0] * t[0] + (double)vc.r1[1] * t[1] + (double)vc.r1[2] * t[2];
+    const double oz = (double)vc.r2[0] * t[0] + (double)vc.r2[1] * t[1] + (double)vc.r2[2] * t[2];
+    margin[0] = fmaxf(margin[0], (float)fabs(ox));
+    margin[1] = fmaxf(margin[1], (float)fabs(oy));
+    margin[2] = fmaxf(margin[2], (float)fabs(oz));
+  }
+  float* hm = reinterpret_cast<float*>(c->h_params + off_m);
+  for (int w = wb; w < we; w++) {
+    const int wx = w % g->nW[0], wy = (w / g->nW[0]) % g->nW[1], wz = w / (g->nW[0] * g->nW[1]);
+    nmi_cell_homography_inv(&c->cam, g, wx, wy, wz, hm + 9 * (size_t)(w - wb));
+  }
+  // schedule order: tiles of 8 renders x 16 warps, so the ~148 CTAs in flight share
+  // ~24 images (48 MB at 1080p) and the histogram inputs are served from L2
+  int2* hp = reinterpret_cast<int2*>(c->h_params + off_p);
+  uint32_t* hi = reinterpret_cast<uint32_t*>(c->h_params + off_i);
+  {
+    const int TS = 8, TW = 16;
+    size_t k = 0;
+    for (int s0 = 0; s0 < nvl; s0 += TS)
+      for (int w0 = 0; w0 < nwl; w0 += TW)
+        for (int w = w0; w < w0 + TW && w < nwl; w++)
+          for (int s = s0; s < s0 + TS && s < nvl; s++) {
+            hp[k] = make_int2(s, w);
+            hi[k] = (uint32_t)((size_t)(w + wb) * nS + (s + vb));
+            k++;
+          }
+  }
+
+  // ---- buffers ----
+  CK(c->renders.reserve((size_t)nvl * c->pitch));
+  CK(c->warps.reserve((size_t)nwl * c->pitch));
+  CK(c->scores.reserve(nP));
+  CK(c->key.reserve(1));
+  if (int rc = ensure_zbuf(c, (size_t)nvl * c->P)) return rc;
+
+  c->launches = 0;
+  if (c->timed) CK(cudaEventRecord(c->ev[0], c->stream));
+  CK(cudaMemcpyAsync(c->params.p, c->h_params, bytes, cudaMemcpyHostToDevice, c->stream));
+  const float4* d_centres = reinterpret_cast<const float4*>(c->params.p + off_c);
+  const float* d_minv = reinterpret_cast<const float*>(c->params.p + off_m);
+  const int2* d_pairs = reinterpret_cast<const int2*>(c->params.p + off_p);
+  const uint32_t* d_index = reinterpret_cast<const uint32_t*>(c->params.p + off_i);
+
+  memcpy(c->Twc, Twc, sizeof(float) * 16);
+  // project in batches of <= kMaxViewsPerLaunch views (centres live in shared memory)
+  for (int v0 = 0; v0 < nvl; v0 += kMaxViewsPerLaunch) {
+    const int nv = nvl - v0 < kMaxViewsPerLaunch ? nvl - v0 : kMaxViewsPerLaunch;
+    if (v0 == 0) {
+      CK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
+      const float c0[3] = {Twc[3], Twc[7], Twc[11]};
+      launch_cull_compact(c->pts.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
+                          c->counter.p, c->stream);
+      c->launches++;
+      if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
+    }
+    launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres + v0, nv, vc,
+                         c->zbuf.p + (size_t)v0 * c->P, c->P, c->stream);
+    c->launches++;
+  }
+  if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
+  launch_resolve(c->zbuf.p, c->val.p, nvl, c->P, c->renders.p, c->pitch, nullptr, c->stream);
+  c->launches++;
+  if (c->timed) CK(cudaEventRecord(c->ev[3], c->stream));
+  launch_warp(c->frame.p, c->cam.W, c->cam.H, d_minv, nwl, c->warps.p, c->pitch, c->stream);
+  c->launches++;
+  if (c->timed) CK(cudaEventRecord(c->ev[4], c->stream));
+
+  HistArgs a{};
+  a.renders = c->renders.p;
+  a.warps = c->warps.p;
+  a.render_pitch = a.warp_pitch = c->pitch;
+  a.pairs = d_pairs;
+  a.out_index = d_index;
+  a.npairs = (int)npl;
+  a.npix = (uint32_t)c->P;
+  a.length = (uint32_t)c->P;
+  a.bins = f->bins;
+  a.bg = f->bg;
+  a.mode = f->score_mode;
+  a.variant = f->variant;
+  a.scores = scores_dev ? scores_dev : c->scores.p;
+  const int nl = launch_joint_hist_score(a, c->stream);
+  REQUIRE(nl >= 0, NMI_ERR_CUDA, "histogram kernel configuration failed");
+  c->launches += nl;
+  if (c->timed) CK(cudaEventRecord(c->ev[5], c->stream));
+  launch_argmax(a.scores, d_index, (int)npl, (uint32_t)nP, key_dev ? key_dev : c->key.p, c->stream);
+  c->launches++;
+  if (c->timed) CK(cudaEventRecord(c->ev[6], c->stream));
+  CK(cudaGetLastError());
+
+  c->has_search = true;
+  c->grid = *g;
+  c->nvl = nvl;
+  c->nwl = nwl;
+  c->v_begin = vb;
+  c->w_begin = wb;
+  c->off_centres = off_c;
+  return NMI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nmi_last_error(void) { return g_err.c_str(); }
+
+int nmi_ctx_create(int device, nmi_ctx** out) {
+  REQUIRE(out, NMI_ERR_INVALID, "null out");
+  *out = nullptr;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, NMI_ERR_CUDA, "no such CUDA device");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  REQUIRE(prop.major == 10, NMI_ERR_CUDA,
+          "this library is built for sm_100a (B200) only; no fallback path exists");
+  CK(cudaSetDevice(device));
+  nmi_ctx* c = new nmi_ctx();
+  c->device = device;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& e : c->ev) CK(cudaEventCreate(&e));
+  CK(c->counter.reserve(1));
+  CK(c->key.reserve(1));
+  CK(c->one_score.reserve(1));
+  CK(c->zero_pair.reserve(1));
+  CK(cudaMemset(c->zero_pair.p, 0, sizeof(int2)));
+  c->timed = true;
+  *out = c;
+  return NMI_OK;
+}
+
+void nmi_ctx_destroy(nmi_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->pts.release(); c->val.release(); c->cpts.release(); c->cidx.release(); c->counter.release();
+  c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
+  c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
+  c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
+  c->one_score.release(); c->zero_pair.release();
+  if (c->h_frame) cudaFreeHost(c->h_frame);
+  if (c->h_params) cudaFreeHost(c->h_params);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void* nmi_ctx_stream(nmi_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int nmi_ctx_sync(nmi_ctx* c) {
+  REQUIRE(c, NMI_ERR_INVALID, "null ctx");
+  CK(cudaStreamSynchronize(c->stream));
+  return NMI_OK;
+}
+
+int nmi_set_camera(nmi_ctx* c, const nmi_camera* cam) {
+  REQUIRE(c && cam, NMI_ERR_INVALID, "null ctx / camera");
+  REQUIRE(cam->W > 0 && cam->H > 0 && (size_t)cam->W * cam->H < (1ull << 31), NMI_ERR_INVALID,
+          "bad image size");
+  REQUIRE(cam->cx != 0 && cam->cy != 0 && cam->fx != 0 && cam->fy != 0, NMI_ERR_INVALID,
+          "bad intrinsics");
+  REQUIRE(cam->zn > 0 && cam->zf > cam->zn, NMI_ERR_INVALID, "bad near/far planes");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->has_cam && (cam->W != c->cam.W || cam->H != c->cam.H)) {
+    c->has_frame = false;
+    c->has_search = false;
+  }
+  c->cam = *cam;
+  c->P = (size_t)cam->W * cam->H;
+  c->pitch = img_pitch(c->P);
+  c->has_cam = true;
+  return NMI_OK;
+}
+
+static int finish_points(nmi_ctx* c, size_t n) {
+  CK(c->val.reserve(n));
+  CK(c->cpts.reserve(n));
+  CK(c->cidx.reserve(n));
+  launch_intensity_u8(c->pts.p, c->val.p, n, c->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  c->n_pts = n;
+  c->has_search = false;
+  return NMI_OK;
+}
+
+int nmi_set_points(nmi_ctx* c, const float* xyzi, size_t n) {
+  REQUIRE(c && xyzi && n > 0 && n < 0xFFFFFFFFull, NMI_ERR_INVALID, "bad point cloud");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(c->pts.reserve(n));
+  CK(cudaMemcpyAsync(c->pts.p, xyzi, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  return finish_points(c, n);
+}
+
+int nmi_set_points_device(nmi_ctx* c, const void* xyzi_dev, size_t n) {
+  REQUIRE(c && xyzi_dev && n > 0 && n < 0xFFFFFFFFull, NMI_ERR_INVALID, "bad point cloud");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(c->pts.reserve(n));
+  CK(cudaMemcpyAsync(c->pts.p, xyzi_dev, n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+  return finish_points(c, n);
+}
+
+int nmi_set_frame(nmi_ctx* c, const uint8_t* gray, int W, int H) {
+  REQUIRE(c && gray, NMI_ERR_INVALID, "null ctx / frame");
+  REQUIRE(c->has_cam, NMI_ERR_STATE, "set the camera first");
+  REQUIRE(W == c->cam.W && H == c->cam.H, NMI_ERR_INVALID, "frame size != camera size");
+  CK(cudaSetDevice(c->device));
+  CK(c->frame.reserve(c->pitch));
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, gray) == cudaSuccess &&
+                      attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // pageable pointers may leave a sticky-free error behind
+  if (pinned) {
+    // caller's buffer is page-locked: DMA straight from it (caller keeps it alive until sync)
+    CK(cudaMemcpyAsync(c->frame.p, gray, c->P, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    // pageable -> pinned staging so the H2D copy is a true async DMA on our stream
+    unsigned char* stage = c->h_frame;
+    if (int rc = ensure_pinned(&stage, &c->h_frame_cap, c->P)) return rc;
+    c->h_frame = stage;
+    CK(cudaStreamSynchronize(c->stream));  // previous upload of the staging buffer is done
+    memcpy(c->h_frame, gray, c->P);
+    CK(cudaMemcpyAsync(c->frame.p, c->h_frame, c->P, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->has_frame = true;
+  return NMI_OK;
+}
+
+int nmi_set_frame_device(nmi_ctx* c, const void* gray_dev, int W, int H) {
+  REQUIRE(c && gray_dev, NMI_ERR_INVALID, "null ctx / frame");
+  REQUIRE(c->has_cam, NMI_ERR_STATE, "set the camera first");
+  REQUIRE(W == c->cam.W && H == c->cam.H, NMI_ERR_INVALID, "frame size != camera size");
+  CK(cudaSetDevice(c->device));
+  CK(c->frame.reserve(c->pitch));
+  CK(cudaMemcpyAsync(c->frame.p, gray_dev, c->P, cudaMemcpyDeviceToDevice, c->stream));
+  c->has_frame = true;
+  return NMI_OK;
+}
+
+int nmi_search(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_flags* f,
+               nmi_result* out, float* scores_host) {
+  REQUIRE(out, NMI_ERR_INVALID, "null result");
+  if (int rc = search_impl(c, Twc, g, f, 0, 1, nullptr, nullptr)) return rc;
+  unsigned long long key = 0;
+  CK(cudaMemcpyAsync(&key, c->key.p, sizeof key, cudaMemcpyDeviceToHost, c->stream));
+  if (scores_host) {
+    const size_t nP = (size_t)c->nvl * c->nwl;
+    CK(cudaMemcpyAsync(scores_host, c->scores.p, nP * sizeof(float), cudaMemcpyDeviceToHost,
+                       c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  if (c->timed) cudaEventElapsedTime(&ms, c->ev[0], c->ev[6]);
+  const int rc = nmi_decode_key(g, key, out);
+  out->gpu_ms = ms;
+  if (rc == NMI_ERR_NO_WINNER) set_error("every score is negative: no winner");
+  return rc;
+}
+
+int nmi_search_enqueue(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_flags* f,
+                       int rank, int world, void* key_dev, void* scores_dev) {
+  REQUIRE(key_dev, NMI_ERR_INVALID, "null key_dev");
+  return search_impl(c, Twc, g, f, rank, world, static_cast<unsigned long long*>(key_dev),
+                     static_cast<float*>(scores_dev));
+}
+
+// ---- stage-level API ------------------------------------------------------
+
+int nmi_render_cell(nmi_ctx* c, const float Twc[16], const nmi_grid* g, int sx, int sy, int sz,
+                    unsigned int* handle) {
+  REQUIRE(c && Twc && handle, NMI_ERR_INVALID, "null argument");
+  REQUIRE(valid_grid(g), NMI_ERR_INVALID, "invalid grid");
+  REQUIRE(c->has_cam && c->n_pts > 0, NMI_ERR_STATE, "camera and model must be set");
+  REQUIRE(sx >= 0 && sx < g->nS[0] && sy >= 0 && sy < g->nS[1] && sz >= 0 && sz < g->nS[2],
+          NMI_ERR_INVALID, "cell out of range");
+  CK(cudaSetDevice(c->device));
+  ViewConst vc;
+  make_view_const(c->cam, Twc, &vc);
+  float t[3];
+  nmi_cell_translation(Twc, g, sx, sy, sz, t);
+  if (int rc = ensure_pinned(&c->h_params, &c->h_params_cap, 4096)) return rc;
+  CK(c->params.reserve(4096));
+  CK(c->one_render.reserve(c->pitch));
+  if (int rc = ensure_zbuf(c, c->P)) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  float4 centre = make_float4(Twc[3] + t[0], Twc[7] + t[1], Twc[11] + t[2], 0.0f);
+  memcpy(c->h_params, &centre, sizeof centre);
+  CK(cudaMemcpyAsync(c->params.p, c->h_params, sizeof centre, cudaMemcpyHostToDevice, c->stream));
+  float margin[3];
+  margin[0] = (float)fabs((double)vc.r0[0] * t[0] + (double)vc.r0[1] * t[1] + (double)vc.r0[2] * t[2]);
+  margin[1] = (float)fabs((double)vc.r1[0] * t[0] + (double)vc.r1[1] * t[1] + (double)vc.r1[2] * t[2]);
+  margin[2] = (float)fabs((double)vc.r2[0] * t[0] + (double)vc.r2[1] * t[1] + (double)vc.r2[2] * t[2]);
+  memcpy(c->Twc, Twc, sizeof(float) * 16);
+  c->has_search = false;  // the cull list no longer matches the last search
+  const bool timed = c->timed;
+  c->timed = false;
+  const int rc = render_views(c, vc, reinterpret_cast<const float4*>(c->params.p), 1, margin, true,
+                              c->one_render.p, nullptr);
+  c->timed = timed;
+  if (rc) return rc;
+  *handle = 1;  // the one "rendered texture" (rendering.hpp:341 creates exactly one)
+  return NMI_OK;
+}
+
+int nmi_warp_cells(nmi_ctx* c, const nmi_grid* g) {
+  REQUIRE(c, NMI_ERR_INVALID, "null ctx");
+  REQUIRE(valid_grid(g), NMI_ERR_INVALID, "invalid grid");
+  REQUIRE(c->has_cam && c->has_frame, NMI_ERR_STATE, "camera and frame must be set");
+  CK(cudaSetDevice(c->device));
+  const int nW = g->nW[0] * g->nW[1] * g->nW[2];
+  const size_t bytes = sizeof(float) * 9 * (size_t)nW;
+  if (int rc = ensure_pinned(&c->h_params, &c->h_params_cap, bytes)) return rc;
+  CK(c->params.reserve(bytes));
+  CK(c->warps.reserve((size_t)nW * c->pitch));
+  CK(cudaStreamSynchronize(c->stream));
+  float* hm = reinterpret_cast<float*>(c->h_params);
+  for (int w = 0; w < nW; w++) {
+    const int wx = w % g->nW[0], wy = (w / g->nW[0]) % g->nW[1], wz = w / (g->nW[0] * g->nW[1]);
+    nmi_cell_homography_inv(&c->cam, g, wx, wy, wz, hm + 9 * (size_t)w);
+  }
+  CK(cudaMemcpyAsync(c->params.p, c->h_params, bytes, cudaMemcpyHostToDevice, c->stream));
+  launch_warp(c->frame.p, c->cam.W, c->cam.H, reinterpret_cast<const float*>(c->params.p), nW,
+              c->warps.p, c->pitch, c->stream);
+  CK(cudaGetLastError());
+  c->has_search = false;
+  c->nwl = nW;
+  c->w_begin = 0;
+  c->grid = *g;
+  return NMI_OK;
+}
+
+int nmi_warp_ptr(nmi_ctx* c, const nmi_grid* g, int wx, int wy, int wz, void** dev_ptr) {
+  REQUIRE(c && dev_ptr && valid_grid(g), NMI_ERR_INVALID, "bad argument");
+  REQUIRE(wx >= 0 && wx < g->nW[0] && wy >= 0 && wy < g->nW[1] && wz >= 0 && wz < g->nW[2],
+          NMI_ERR_INVALID, "cell out of range");
+  const int w = (wz * g->nW[1] + wy) * g->nW[0] + wx;
+  REQUIRE(c->warps.p && w - c->w_begin >= 0 && w - c->w_begin < c->nwl, NMI_ERR_STATE,
+          "warps not computed for this cell");
+  *dev_ptr = c->warps.p + (size_t)(w - c->w_begin) * c->pitch;
+  return NMI_OK;
+}
+
+static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped, uint32_t npix,
+                       const nmi_flags* f, bool dump, float* score_host) {
+  HistArgs a{};
+  a.renders = render;
+  a.warps = warped;
+  a.render_pitch = a.warp_pitch = 0;
+  a.pairs = c->zero_pair.p;
+  a.out_index = nullptr;
+  a.npairs = 1;
+  a.npix = npix;
+  a.length = npix;
+  a.bins = f->bins;
+  a.bg = f->bg;
+  a.mode = f->score_mode;
+  a.variant = f->variant;
+  a.scores = c->one_score.p;
+  if (dump) {
+    CK(c->dumpJ.reserve(65536));
+    CK(c->dumpH.reserve(512));
+    a.dumpJ = c->dumpJ.p;
+    a.dumpHA = c->dumpH.p;
+    a.dumpHB = c->dumpH.p + 256;
+  }
+  REQUIRE(launch_joint_hist_score(a, c->stream) >= 0, NMI_ERR_CUDA,
+          "histogram kernel configuration failed");
+  CK(cudaGetLastError());
+  if (score_host)
+    CK(cudaMemcpyAsync(score_host, c->one_score.p, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return NMI_OK;
+}
+
+int nmi_eval_pair(nmi_ctx* c, const void* warped_dev, unsigned int handle, int W, int H,
+                  const nmi_flags* f, float* score_host) {
+  REQUIRE(c && warped_dev && score_host, NMI_ERR_INVALID, "null argument");
+  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags");
+  REQUIRE(c->has_cam && W == c->cam.W && H == c->cam.H, NMI_ERR_INVALID, "size != camera size");
+  REQUIRE(handle == 1 && c->one_render.p, NMI_ERR_STATE, "unknown render handle");
+  REQUIRE(c->P / 16384 + 2 < 1024, NMI_ERR_INVALID, "image too large for the histogram kernel");
+  CK(cudaSetDevice(c->device));
+  const uint8_t* wp = static_cast<const uint8_t*>(warped_dev);
+  const bool ours = c->warps.p && wp >= c->warps.p && wp < c->warps.p + c->warps.cap &&
+                    ((size_t)(wp - c->warps.p) % c->pitch) == 0;
+  if (!ours) {
+    // borrowed buffer (e.g. a GpuMat): copy into a padded, 128 B aligned slot so the
+    // TMA loads of the last chunk stay inside memory we own
+    CK(c->one_warp.reserve(c->pitch));
+    CK(cudaMemcpyAsync(c->one_warp.p, wp, c->P, cudaMemcpyDeviceToDevice, c->stream));
+    wp = c->one_warp.p;
+  }
+  return eval_images(c, c->one_render.p, wp, (uint32_t)c->P, f, false, score_host);
+}
+
+// ---- parity read-backs ------------------------------------------------------
+
+int nmi_get_render(nmi_ctx* c, int s, uint8_t* host) {
+  REQUIRE(c && host, NMI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  const uint8_t* src = nullptr;
+  if (c->has_search) {
+    REQUIRE(s - c->v_begin >= 0 && s - c->v_begin < c->nvl, NMI_ERR_INVALID, "view not on this rank");
+    src = c->renders.p + (size_t)(s - c->v_begin) * c->pitch;
+  } else {
+    REQUIRE(c->one_render.p && s == 0, NMI_ERR_STATE, "no render available");
+    src = c->one_render.p;
+  }
+  CK(cudaMemcpyAsync(host, src, c->P, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return NMI_OK;
+}
+
+int nmi_get_winners(nmi_ctx* c, int s, uint32_t* host) {
+  REQUIRE(c && host, NMI_ERR_INVALID, "null argument");
+  REQUIRE(c->has_search, NMI_ERR_STATE, "no search has run");
+  REQUIRE(s - c->v_begin >= 0 && s - c->v_begin < c->nvl, NMI_ERR_INVALID, "view not on this rank");
+  CK(cudaSetDevice(c->device));
+  // re-project this one view from the survivors of the last cull, keeping the indices
+  ViewConst vc;
+  make_view_const(c->cam, c->Twc, &vc);
+  CK(c->winners.reserve(c->P));
+  CK(c->one_render.reserve(c->pitch));
+  const float4* d_centres = reinterpret_cast<const float4*>(c->params.p + c->off_centres);
+  const float margin[3] = {0, 0, 0};
+  const bool timed = c->timed;
+  c->timed = false;
+  const int rc = render_views(c, vc, d_centres + (s - c->v_begin), 1, margin, false,
+                              c->one_render.p, c->winners.p);
+  c->timed = timed;
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(host, c->winners.p, c->P * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return NMI_OK;
+}
+
+int nmi_get_warp(nmi_ctx* c, int w, uint8_t* host) {
+  REQUIRE(c && host, NMI_ERR_INVALID, "null argument");
+  REQUIRE(c->warps.p && w - c->w_begin >= 0 && w - c->w_begin < c->nwl, NMI_ERR_STATE,
+          "warp not available on this rank");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(host, c->warps.p + (size_t)(w - c->w_begin) * c->pitch, c->P,
+                     cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return NMI_OK;
+}
+
+int nmi_get_hist(nmi_ctx* c, int s, int w, const nmi_flags* f, uint32_t* J, uint32_t* HA,
+                 uint32_t* HB, float* score) {
+  REQUIRE(c && J && HA && HB, NMI_ERR_INVALID, "null argument");
+  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags");
+  REQUIRE(c->has_search, NMI_ERR_STATE, "no search has run");
+  REQUIRE(s - c->v_begin >= 0 && s - c->v_begin < c->nvl && w - c->w_begin >= 0 &&
+              w - c->w_begin < c->nwl,
+          NMI_ERR_INVALID, "pair not on this rank");
+  CK(cudaSetDevice(c->device));
+  const int rc = eval_images(c, c->renders.p + (size_t)(s - c->v_begin) * c->pitch,
+                             c->warps.p + (size_t)(w - c->w_begin) * c->pitch, (uint32_t)c->P, f,
+                             true, score);
+  if (rc) return rc;
+  const size_t nb = (size_t)f->bins;
+  CK(cudaMemcpy(J, c->dumpJ.p, nb * nb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(HA, c->dumpH.p, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(HB, c->dumpH.p + 256, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return NMI_OK;
+}
+
+int nmi_get_timings(nmi_ctx* c, float ms[8], int* launches) {
+  REQUIRE(c && ms, NMI_ERR_INVALID, "null argument");
+  REQUIRE(c->has_search && c->timed, NMI_ERR_STATE, "no timed search has run");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(c->ev[6]));
+  for (int i = 0; i < 6; i++) CK(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+  CK(cudaEventElapsedTime(&ms[6], c->ev[0], c->ev[6]));
+  ms[7] = 0;
+  if (launches) *launches = c->launches;
+  return NMI_OK;
+}
+
+}  // extern "C"

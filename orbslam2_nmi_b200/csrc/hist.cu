@@ -1,0 +1,456 @@
+// hist.cu -- fused joint histogram + entropy + NMI score, one CTA per evaluation.
+//
+// Replaces, per (render, warped frame) pair, the reference's six launches
+//   histogram256Kernel + mergeHistogram256Kernel + mergeJointHistogram256Kernel
+//   (Thirdparty/CUDA_Functions/NMI.cu:52-161, driver :188-226),
+//   ComputeEntropyKernel (:230-267), AddvectorParwiseMidKernel (:270-287),
+//   AddVectorPairwiseKernel (:290-363)
+// and the 4 MiB cudaMemset + 10 cudaMalloc/cudaFree + blocking D2H around them
+// (kernel.cu:49-114).  Semantics follow SURVEY.md Appendix A.6/A.7:
+//   J[a*B+b]++ for a = render[p], b = warped[p]  (BG rule NMI.cu:85),
+//   e(c) = (c/L) log2f(c/L), L = W*H always (kernel.cu:85),
+//   fp32 pairwise trees in the reference's order (strides B/2..1 per row, then
+//   over the row sums), SUC / ENMI with the all-zero guard (NMI.cu:342-362).
+//
+// B200 design: the whole 256x256 joint histogram of one evaluation lives in the
+// CTA's shared memory and never touches HBM; the marginals are its row / column
+// sums (integers, exact); only one float leaves the SM.  Both images are streamed
+// through a 3-stage shared-memory ring filled by the TMA engine
+// (cp.async.bulk + mbarrier complete_tx), issued by a dedicated producer warp,
+// so the 16 consumer warps spend their issue slots on shared-memory atomics.
+//
+// Histogram storage policies (template POLICY):
+//   P_U16G  256 bins, single pass. 65 536 counters, two 16-bit fields per 32-bit
+//           word (128 KiB).  Whenever an increment wraps the low 14 bits of its
+//           field (the running count crosses a multiple of 16 384) the thread
+//           that did it subtracts 16 384 again and logs a (bin, +16384) event;
+//           the epilogue adds the events back.  All updates are commutative
+//           adds, so the result is exact as long as a field never carries out,
+//           i.e. fewer than 3*16384 increments land between a thread's wrap and
+//           its fix-up.  The TMA ring bounds that: while one thread sits in chunk
+//           k every other warp stays within chunks k-2..k+2, <= 5*8192 = 40 960
+//           pixels (the LDG variant re-synchronises every two chunks instead).
+//   P_U32X2 256 bins, two passes over the pixels, 128 render rows x 256 u32 per
+//           pass (128 KiB); no overflow logic, twice the L2->SM traffic.
+//   P_B64   64 bins (value >> 2), 8 replicated 64x64 u32 sub-histograms.
+#include "nmi_internal.h"
+
+namespace nmi {
+namespace {
+
+constexpr int kConsumerWarps = 16;
+constexpr int kConsumers = kConsumerWarps * 32;  // 512
+constexpr int kThreads = kConsumers + 32;        // + 1 producer warp
+constexpr int kChunk = kConsumers * 16;          // 8192 pixels per stage and image
+constexpr int kStages = 3;
+constexpr int kEvCap = 1024;
+constexpr int kHistWords = 32768;  // 128 KiB
+constexpr int kB64Copies = 8;
+
+enum Policy { P_U16G = 0, P_U32X2 = 2, P_B64 = 3 };
+
+struct __align__(16) Smem {
+  uint32_t hist[kHistWords];
+  uint8_t rbuf[kStages][kChunk];
+  uint8_t wbuf[kStages][kChunk];
+  unsigned long long full[kStages];
+  unsigned long long empty[kStages];
+  float rowE[256];
+  uint32_t HA[256];
+  uint32_t HB[256];
+  float sums[4];
+  uint32_t ev_count;
+  uint16_t ev_list[kEvCap];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 26)) __trap();  // never hang the GPU on a logic error
+  } while (!done);
+}
+// TMA engine 1-D bulk copy global -> shared, completion counted on an mbarrier.
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- entropy pieces (NMI.cu:240-266) ---------------------------------------
+__device__ __forceinline__ float term(uint32_t c, float L) {
+  if (c == 0) return 0.0f;
+  const float p = __fdiv_rn((float)c, L);
+  return __fmul_rn(p, log2f(p));
+}
+// Pairwise tree of NMI.cu:270-287 / :295-338 for n = 32*K values, lane l holding
+// x[l + 32k]: strides 16K..32 fold k, strides 16..1 are shuffles. Result in lane 0.
+template <int K>
+__device__ __forceinline__ float tree_lanes(float (&v)[K]) {
+#pragma unroll
+  for (int h = K / 2; h >= 1; h /= 2)
+#pragma unroll
+    for (int k = 0; k < h; k++) v[k] = __fadd_rn(v[k], v[k + h]);
+  float x = v[0];
+#pragma unroll
+  for (int d = 16; d >= 1; d /= 2) x = __fadd_rn(x, __shfl_down_sync(0xffffffffu, x, d));
+  return x;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t x) {
+#pragma unroll
+  for (int d = 16; d >= 1; d /= 2) x += __shfl_xor_sync(0xffffffffu, x, d);
+  return x;
+}
+__device__ __forceinline__ float finish_score(float sa, float sb, float sab, int mode) {
+  if (sa == 0.0f && sb == 0.0f && sab == 0.0f) return 0.0f;  // NMI.cu:344,353
+  if (mode == NMI_SCORE_ENMI) return __fdiv_rn(__fadd_rn(-sa, -sb), -sab);  // NMI.cu:348
+  // NMI.cu:357  2*(1-((-Hab)/((-Ha)+(-Hb))))
+  return __fmul_rn(2.0f, __fsub_rn(1.0f, __fdiv_rn(-sab, __fadd_rn(-sa, -sb))));
+}
+
+// ---- per-pixel accumulation --------------------------------------------------
+template <int POLICY>
+__device__ __forceinline__ void accum(Smem& sm, uint32_t t, int pass, int warp) {
+  // t = (a << 8) | b, 16 bits
+  if (POLICY == P_U16G) {
+    const uint32_t sh = (t & 1u) << 4;
+    uint32_t* wp = sm.hist + (t >> 1);
+    const uint32_t old = atomicAdd(wp, 1u << sh);
+    if (((old >> sh) & 0x3FFFu) == 0x3FFFu) {  // count crossed a multiple of 16384
+      atomicSub(wp, 0x4000u << sh);
+      const uint32_t e = atomicAdd(&sm.ev_count, 1u);
+      if (e < kEvCap) sm.ev_list[e] = (uint16_t)t;
+    }
+  } else if (POLICY == P_U32X2) {
+    if ((int)(t >> 15) == pass) atomicAdd(sm.hist + (t & 0x7FFFu), 1u);
+  } else {
+    const uint32_t idx = ((t >> 4) & 0xFC0u) | ((t >> 2) & 0x3Fu);
+    atomicAdd(sm.hist + (warp & (kB64Copies - 1)) * 4096 + idx, 1u);
+  }
+}
+
+template <int POLICY>
+__device__ __forceinline__ void accum_words(Smem& sm, uint32_t rw, uint32_t ww, int nvalid, int bg,
+                                            int pass, int warp) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (k < nvalid) {
+      const uint32_t t = __byte_perm(ww, rw, 0x4440 + k * 0x11) & 0xFFFFu;
+      if (bg || ((t & 0xFF00u) != 0 && (t & 0xFFu) != 0)) accum<POLICY>(sm, t, pass, warp);
+    }
+  }
+}
+
+template <int POLICY>
+__device__ __forceinline__ void accum16(Smem& sm, const uint4& r, const uint4& w, int nvalid,
+                                        int bg, int pass, int warp) {
+  accum_words<POLICY>(sm, r.x, w.x, nvalid, bg, pass, warp);
+  accum_words<POLICY>(sm, r.y, w.y, nvalid - 4, bg, pass, warp);
+  accum_words<POLICY>(sm, r.z, w.z, nvalid - 8, bg, pass, warp);
+  accum_words<POLICY>(sm, r.w, w.w, nvalid - 12, bg, pass, warp);
+}
+
+// ---- epilogue over the rows of one pass --------------------------------------
+// U16G: one pass, 256 rows of 128 packed words.  U32X2: 128 rows of 256 words per
+// pass.  B64: 64 rows of 64 words after folding the copies.
+template <int POLICY>
+__device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const HistArgs& a,
+                                              bool dump, int warp, int lane) {
+  if (POLICY == P_U16G) {
+    const uint32_t nev = min(sm.ev_count, (uint32_t)kEvCap);
+    uint32_t col[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) col[i] = 0;
+    for (int row = warp; row < 256; row += kConsumerWarps) {
+      uint32_t c[8];  // c[2k+h] = J[row][2(lane+32k)+h]
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t wv = sm.hist[row * 128 + lane + 32 * k];
+        c[2 * k] = wv & 0xFFFFu;
+        c[2 * k + 1] = wv >> 16;
+      }
+      for (uint32_t e = 0; e < nev; e++) {  // logged +16384 events of this row
+        const uint32_t t = sm.ev_list[e];
+        if ((int)(t >> 8) == row) {
+          const uint32_t b = t & 0xFFu;
+          if (((b >> 1) & 31u) == (uint32_t)lane) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              if ((uint32_t)i == (((b >> 6) << 1) | (b & 1u))) c[i] += 16384u;
+          }
+        }
+      }
+      uint32_t rs = 0;
+      float vl[4], vh[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        rs += c[2 * k] + c[2 * k + 1];
+        col[2 * k] += c[2 * k];
+        col[2 * k + 1] += c[2 * k + 1];
+        vl[k] = term(c[2 * k], L);
+        vh[k] = term(c[2 * k + 1], L);
+        if (dump) {
+          a.dumpJ[row * 256 + 2 * (lane + 32 * k)] = c[2 * k];
+          a.dumpJ[row * 256 + 2 * (lane + 32 * k) + 1] = c[2 * k + 1];
+        }
+      }
+      rs = warp_sum(rs);
+      // tree over b: strides 128,64 fold k; 32..2 are lane shuffles (b = 2(lane+32k)+h);
+      // stride 1 folds h.
+      const float tl = tree_lanes<4>(vl);
+      const float th = tree_lanes<4>(vh);
+      if (lane == 0) {
+        sm.rowE[row] = __fadd_rn(tl, th);
+        sm.HA[row] = rs;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      atomicAdd(&sm.HB[2 * (lane + 32 * k)], col[2 * k]);
+      atomicAdd(&sm.HB[2 * (lane + 32 * k) + 1], col[2 * k + 1]);
+    }
+  } else if (POLICY == P_U32X2) {
+    uint32_t col[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) col[i] = 0;
+    for (int lr = warp; lr < 128; lr += kConsumerWarps) {
+      const int row = pass * 128 + lr;
+      float v[8];
+      uint32_t rs = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t c = sm.hist[lr * 256 + lane + 32 * k];
+        rs += c;
+        col[k] += c;
+        v[k] = term(c, L);
+        if (dump) a.dumpJ[row * 256 + lane + 32 * k] = c;
+      }
+      rs = warp_sum(rs);
+      const float tr = tree_lanes<8>(v);
+      if (lane == 0) {
+        sm.rowE[row] = tr;
+        sm.HA[row] = rs;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) atomicAdd(&sm.HB[lane + 32 * k], col[k]);
+  } else {
+    // fold the replicated sub-histograms into copy 0 (all 512 consumers)
+    const int tid = warp * 32 + lane;
+    for (int i = tid; i < 4096; i += kConsumers) {
+      uint32_t s = 0;
+#pragma unroll
+      for (int r = 0; r < kB64Copies; r++) s += sm.hist[r * 4096 + i];
+      sm.hist[i] = s;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+    uint32_t col[2] = {0, 0};
+    for (int row = warp; row < 64; row += kConsumerWarps) {
+      float v[2];
+      uint32_t rs = 0;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const uint32_t c = sm.hist[row * 64 + lane + 32 * k];
+        rs += c;
+        col[k] += c;
+        v[k] = term(c, L);
+        if (dump) a.dumpJ[row * 64 + lane + 32 * k] = c;
+      }
+      rs = warp_sum(rs);
+      const float tr = tree_lanes<2>(v);
+      if (lane == 0) {
+        sm.rowE[row] = tr;
+        sm.HA[row] = rs;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) atomicAdd(&sm.HB[lane + 32 * k], col[k]);
+  }
+}
+
+template <int POLICY, bool USE_TMA>
+__global__ void __launch_bounds__(kThreads, 1) joint_hist_score_kernel(const HistArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr int BINS = POLICY == P_B64 ? 64 : 256;
+  constexpr int NPASS = POLICY == P_U32X2 ? 2 : 1;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int2 pr = a.pairs[blockIdx.x];
+  const uint8_t* __restrict__ rimg = a.renders + (size_t)pr.x * a.render_pitch;
+  const uint8_t* __restrict__ wimg = a.warps + (size_t)pr.y * a.warp_pitch;
+  const uint32_t npix = a.npix;
+  const int nchunks = (int)((npix + kChunk - 1) / kChunk);
+  const int total = nchunks * NPASS;
+  const float L = (float)a.length;
+  const bool dump = a.dumpJ != nullptr && blockIdx.x == 0;
+
+  // ---- init ----
+  {
+    uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+    for (int i = tid; i < kHistWords / 4; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 256) sm.HB[tid] = 0;
+    if (tid == 0) {
+      sm.ev_count = 0;
+      for (int s = 0; s < kStages; s++) {
+        mbar_init(&sm.full[s], 1);
+        mbar_init(&sm.empty[s], kConsumerWarps);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    // ===== producer warp: TMA ring =====
+    if (USE_TMA && lane == 0) {
+      for (int k = 0; k < total; k++) {
+        const int st = k % kStages;
+        if (k >= kStages) mbar_wait(&sm.empty[st], ((k / kStages) - 1) & 1);
+        const int ck = k % nchunks;
+        const uint32_t off = (uint32_t)ck * kChunk;
+        uint32_t bytes = npix - off;
+        bytes = bytes > (uint32_t)kChunk ? (uint32_t)kChunk : ((bytes + 15u) & ~15u);
+        mbar_expect_tx(&sm.full[st], 2 * bytes);
+        tma_load_1d(sm.rbuf[st], rimg + off, bytes, &sm.full[st]);
+        tma_load_1d(sm.wbuf[st], wimg + off, bytes, &sm.full[st]);
+      }
+    }
+  } else {
+    // ===== consumers =====
+    uint4 nr = make_uint4(0, 0, 0, 0), nw = nr;
+    if (!USE_TMA) {
+      const uint32_t off = (uint32_t)tid * 16;
+      if (off < npix) {
+        nr = __ldg(reinterpret_cast<const uint4*>(rimg + off));
+        nw = __ldg(reinterpret_cast<const uint4*>(wimg + off));
+      }
+    }
+    for (int k = 0; k < total; k++) {
+      const int pass = k / nchunks;
+      const int ck = k - pass * nchunks;
+      const uint32_t off = (uint32_t)ck * kChunk + (uint32_t)tid * 16;
+      uint4 r, w;
+      if (USE_TMA) {
+        const int st = k % kStages;
+        mbar_wait(&sm.full[st], (k / kStages) & 1);
+        r = *reinterpret_cast<const uint4*>(sm.rbuf[st] + tid * 16);
+        w = *reinterpret_cast<const uint4*>(sm.wbuf[st] + tid * 16);
+      } else {
+        r = nr;
+        w = nw;
+        if (k + 1 < total) {  // register prefetch of the next chunk
+          const int ck2 = (k + 1) % nchunks;
+          const uint32_t off2 = (uint32_t)ck2 * kChunk + (uint32_t)tid * 16;
+          if (off2 < npix) {
+            nr = __ldg(reinterpret_cast<const uint4*>(rimg + off2));
+            nw = __ldg(reinterpret_cast<const uint4*>(wimg + off2));
+          }
+        }
+      }
+      const int nvalid = off >= npix ? 0 : (int)min(16u, npix - off);
+      if (nvalid == 16)
+        accum16<POLICY>(sm, r, w, 16, a.bg, pass, warp);
+      else if (nvalid > 0)
+        accum16<POLICY>(sm, r, w, nvalid, a.bg, pass, warp);
+      if (USE_TMA) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[k % kStages]);
+      } else if (POLICY == P_U16G && (k & 1)) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // bound the in-flight pixels
+      }
+      if (NPASS == 2 && ck == nchunks - 1) {
+        // end of a pass: rows of this half are final
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+        rows_epilogue<POLICY>(sm, pass, L, a, dump, warp, lane);
+        if (pass == 0) {
+          asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+          uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+          for (int i = tid; i < kHistWords / 4; i += kConsumers) h4[i] = make_uint4(0, 0, 0, 0);
+          asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+        }
+      }
+    }
+    if (NPASS == 1) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+      rows_epilogue<POLICY>(sm, 0, L, a, dump, warp, lane);
+    }
+  }
+  __syncthreads();
+
+  // ---- final trees: SAB over row sums, SA over HA terms, SB over HB terms ----
+  if (warp < 3) {
+    constexpr int K = BINS / 32;
+    float v[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int i = lane + 32 * k;
+      v[k] = warp == 0 ? sm.rowE[i] : term(warp == 1 ? sm.HA[i] : sm.HB[i], L);
+    }
+    const float s = tree_lanes<K>(v);
+    if (lane == 0) sm.sums[warp] = s;
+  }
+  if (dump && tid < BINS) {
+    a.dumpHA[tid] = sm.HA[tid];
+    a.dumpHB[tid] = sm.HB[tid];
+  }
+  __syncthreads();
+  if (tid == 0)
+    a.scores[a.out_index ? a.out_index[blockIdx.x] : blockIdx.x] =
+        finish_score(sm.sums[1], sm.sums[2], sm.sums[0], a.mode);
+}
+
+template <int POLICY, bool USE_TMA>
+int launch_t(const HistArgs& a, cudaStream_t st) {
+  auto kern = joint_hist_score_kernel<POLICY, USE_TMA>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(Smem)) != cudaSuccess)
+      return -1;
+    configured = true;
+  }
+  kern<<<a.npairs, kThreads, sizeof(Smem), st>>>(a);
+  return 1;
+}
+
+}  // namespace
+
+int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
+  if (a.npairs <= 0) return 0;
+  if (a.bins == 64) return a.variant == 1 ? launch_t<P_B64, false>(a, st) : launch_t<P_B64, true>(a, st);
+  switch (a.variant) {
+    case 1: return launch_t<P_U16G, false>(a, st);
+    case 2: return launch_t<P_U32X2, true>(a, st);
+    case 3: return launch_t<P_U32X2, false>(a, st);
+    default: return launch_t<P_U16G, true>(a, st);
+  }
+}
+
+}  // namespace nmi

@@ -1,0 +1,68 @@
+// nmi_internal.h -- shared declarations of the sm_100a NMI pose-search library.
+// Host-side context + the launch wrappers each .cu file exports.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/nmi_b200.h"
+
+namespace nmi {
+
+// Per synthetic-view camera, consumed by the projection kernel.
+// Layout of A.2: Rwc columns + view centre + projection scales.
+struct ViewConst {
+  float r0[3], r1[3], r2[3];  // columns of Rwc (Twc[:3,0], [:3,1], [:3,2])
+  float kx, ky, hw, hh, zn, zf;
+  int W, H, s;  // image size, integer point size
+};
+
+constexpr int kMaxViewsPerLaunch = 512;
+constexpr size_t kImgAlign = 128;  // every render / warp image starts 128 B aligned
+
+inline size_t img_pitch(size_t P) { return (P + kImgAlign - 1) / kImgAlign * kImgAlign; }
+
+// --- project.cu ------------------------------------------------------------
+void launch_fill_u64(unsigned long long* p, size_t n, unsigned long long v, cudaStream_t st);
+void launch_intensity_u8(const float4* pts, uint8_t* val, size_t n, cudaStream_t st);
+// z-buffer -> u8 image (+ optional winner indices); resets the z-buffer to ~0
+void launch_resolve(unsigned long long* zbuf, const uint8_t* val, int nviews, size_t P,
+                    uint8_t* images, size_t pitch, uint32_t* winners, cudaStream_t st);
+
+// --- warp.cu ---------------------------------------------------------------
+void launch_warp(const uint8_t* src, int W, int H, const float* minv /*nW x 9, device*/,
+                 int nW, uint8_t* dst, size_t pitch, cudaStream_t st);
+
+// --- hist.cu ---------------------------------------------------------------
+struct HistArgs {
+  const uint8_t* renders;  // render images, pitch bytes apart
+  const uint8_t* warps;    // warped images, pitch bytes apart
+  size_t render_pitch, warp_pitch;
+  const int2* pairs;  // (render slot, warp slot) per evaluation, schedule order
+  const uint32_t* out_index;  // score slot per evaluation (rating linear index)
+  int npairs;
+  uint32_t npix;    // W*H
+  uint32_t length;  // kernel.cu:85: always W*H
+  int bins, bg, mode, variant;
+  float* scores;
+  // optional dumps (parity): when non-null, pair 0 of the launch writes them
+  uint32_t* dumpJ;
+  uint32_t* dumpHA;
+  uint32_t* dumpHB;
+};
+int launch_joint_hist_score(const HistArgs& a, cudaStream_t st);  // returns launches, <0 on error
+int hist_configure();  // cudaFuncSetAttribute for the big-smem kernels; 0 on success
+
+// --- argmax.cu -------------------------------------------------------------
+// key = (bits(max(0, scores)) << 32) | (0xFFFFFFFF - lowest index with score == max)
+void launch_argmax(const float* scores, const uint32_t* index_list, int n_list, uint32_t n_total,
+                   unsigned long long* key, cudaStream_t st);
+
+// --- host_math.cpp ----------------------------------------------------------
+void make_view_const(const nmi_camera& cam, const float Twc[16], ViewConst* vc);
+uint64_t pack_key(float max_score, int64_t index);
+
+void set_error(const std::string& msg);
+
+}  // namespace nmi

@@ -1,0 +1,216 @@
+"""Thin Python host over the C ABI -- used by tests/, bench.py and the multi-GPU launcher.
+
+Mirrors the reference's host objects only as far as the harness needs them:
+`NmiSearcher` ~ NmiObjects (localization.hpp:31) + the grid loop of
+Tracking::RelocalizeWithNMI (src/Tracking.cc:1851-1985).  The production host side is
+the C++ drop-in layer in include/compat/ + libnmi_b200.so; this module adds nothing
+numerical -- every number comes from the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import Camera, Flags, Grid, Result, check, ptr
+
+
+@dataclass
+class SearchResult:
+    best_s: tuple
+    best_w: tuple
+    best_index: int
+    best_score: float
+    key: int
+    gpu_ms: float
+    scores: np.ndarray | None = None
+
+
+def _result(r: Result, scores=None) -> SearchResult:
+    return SearchResult(tuple(r.best_s), tuple(r.best_w), int(r.best_index), float(r.best_score),
+                        int(r.key), float(r.gpu_ms), scores)
+
+
+class NmiSearcher:
+    """One context on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        check(self.lib.nmi_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+        self.cam: Camera | None = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nmi_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- model / camera / frame ------------------------------------------------
+    def set_camera(self, W, H, fx, fy, cx, cy, zn, zf, point_size=3.0):
+        self.cam = Camera(int(W), int(H), fx, fy, cx, cy, zn, zf, point_size)
+        check(self.lib.nmi_set_camera(self.h, C.byref(self.cam)))
+
+    def set_scene(self, scene):
+        self.set_camera(scene.W, scene.H, scene.fx, scene.fy, scene.cx, scene.cy, scene.zn, scene.zf,
+                        scene.point_size)
+        self.set_points(scene.xyzi)
+
+    def set_points(self, xyzi: np.ndarray):
+        xyzi = np.ascontiguousarray(xyzi, dtype=np.float32)
+        assert xyzi.ndim == 2 and xyzi.shape[1] == 4
+        check(self.lib.nmi_set_points(self.h, ptr(xyzi), xyzi.shape[0]))
+
+    def set_frame(self, gray: np.ndarray):
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        check(self.lib.nmi_set_frame(self.h, ptr(gray), gray.shape[1], gray.shape[0]))
+
+    def set_frame_device(self, dev_ptr: int, W: int, H: int):
+        check(self.lib.nmi_set_frame_device(self.h, dev_ptr, W, H))
+
+    # -- search -----------------------------------------------------------------
+    @staticmethod
+    def flags(bins=256, score=capi.SCORE_SUC, bg=True, variant=0) -> Flags:
+        return Flags(bins, score, 1 if bg else 0, variant)
+
+    def search(self, Twc, grid: Grid, flags: Flags | None = None, want_scores=False) -> SearchResult:
+        Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
+        flags = flags or self.flags()
+        r = Result()
+        scores = np.empty(grid.n_pose, dtype=np.float32) if want_scores else None
+        code = self.lib.nmi_search(self.h, ptr(Twc), C.byref(grid), C.byref(flags), C.byref(r),
+                                   ptr(scores) if want_scores else None)
+        if code not in (capi.NMI_OK, capi.NMI_ERR_NO_WINNER):
+            check(code)
+        return _result(r, scores)
+
+    def search_enqueue(self, Twc, grid: Grid, flags: Flags, rank: int, world: int, key_dev: int,
+                       scores_dev: int | None = None):
+        Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
+        check(self.lib.nmi_search_enqueue(self.h, ptr(Twc), C.byref(grid), C.byref(flags), rank,
+                                          world, key_dev, scores_dev))
+
+    def stream(self) -> int:
+        return int(self.lib.nmi_ctx_stream(self.h) or 0)
+
+    def sync(self):
+        check(self.lib.nmi_ctx_sync(self.h))
+
+    def decode(self, grid: Grid, key: int) -> SearchResult:
+        r = Result()
+        self.lib.nmi_decode_key(C.byref(grid), C.c_uint64(key), C.byref(r))
+        return _result(r)
+
+    # -- stage-level API (reference call granularity) ------------------------------
+    def render_cell(self, Twc, grid: Grid, sx, sy, sz) -> int:
+        Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
+        h = C.c_uint(0)
+        check(self.lib.nmi_render_cell(self.h, ptr(Twc), C.byref(grid), sx, sy, sz, C.byref(h)))
+        return h.value
+
+    def warp_cells(self, grid: Grid):
+        check(self.lib.nmi_warp_cells(self.h, C.byref(grid)))
+
+    def warp_ptr(self, grid: Grid, wx, wy, wz) -> int:
+        p = C.c_void_p()
+        check(self.lib.nmi_warp_ptr(self.h, C.byref(grid), wx, wy, wz, C.byref(p)))
+        return int(p.value)
+
+    def eval_pair(self, warped_dev: int, handle: int, flags: Flags | None = None) -> float:
+        flags = flags or self.flags()
+        s = np.zeros(1, dtype=np.float32)
+        check(self.lib.nmi_eval_pair(self.h, warped_dev, handle, self.cam.W, self.cam.H,
+                                     C.byref(flags), ptr(s)))
+        return float(s[0])
+
+    # -- parity read-backs -------------------------------------------------------
+    def get_render(self, s: int) -> np.ndarray:
+        out = np.empty((self.cam.H, self.cam.W), dtype=np.uint8)
+        check(self.lib.nmi_get_render(self.h, s, ptr(out)))
+        return out
+
+    def get_winners(self, s: int) -> np.ndarray:
+        out = np.empty((self.cam.H, self.cam.W), dtype=np.uint32)
+        check(self.lib.nmi_get_winners(self.h, s, ptr(out)))
+        return out
+
+    def get_warp(self, w: int) -> np.ndarray:
+        out = np.empty((self.cam.H, self.cam.W), dtype=np.uint8)
+        check(self.lib.nmi_get_warp(self.h, w, ptr(out)))
+        return out
+
+    def get_hist(self, s: int, w: int, flags: Flags | None = None):
+        flags = flags or self.flags()
+        b = flags.bins
+        J = np.zeros((b, b), dtype=np.uint32)
+        HA = np.zeros(b, dtype=np.uint32)
+        HB = np.zeros(b, dtype=np.uint32)
+        sc = np.zeros(1, dtype=np.float32)
+        check(self.lib.nmi_get_hist(self.h, s, w, C.byref(flags), ptr(J), ptr(HA), ptr(HB), ptr(sc)))
+        return J, HA, HB, float(sc[0])
+
+    def timings(self):
+        ms = np.zeros(8, dtype=np.float32)
+        n = C.c_int(0)
+        check(self.lib.nmi_get_timings(self.h, ptr(ms), C.byref(n)))
+        names = ["params_cull", "project", "resolve", "warp", "hist_score", "argmax", "total"]
+        return {k: float(ms[i]) for i, k in enumerate(names)}, n.value
+
+
+# -- host helpers that need no GPU (bound straight to the library's host code) ------
+def partition(grid: Grid, rank: int, world: int):
+    lib = capi.load()
+    ax, b, e = C.c_int(), C.c_int(), C.c_int()
+    check(lib.nmi_partition(C.byref(grid), rank, world, C.byref(ax), C.byref(b), C.byref(e)))
+    return ax.value, b.value, e.value
+
+
+def cell_translation(Twc, grid: Grid, sx, sy, sz) -> np.ndarray:
+    Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
+    t = np.zeros(3, dtype=np.float32)
+    capi.load().nmi_cell_translation(ptr(Twc), C.byref(grid), sx, sy, sz, ptr(t))
+    return t
+
+
+def cell_homography_inv(cam: Camera, grid: Grid, wx, wy, wz) -> np.ndarray:
+    m = np.zeros(9, dtype=np.float32)
+    capi.load().nmi_cell_homography_inv(C.byref(cam), C.byref(grid), wx, wy, wz, ptr(m))
+    return m
+
+
+def apply_winner(Twc, grid: Grid, s, w) -> np.ndarray:
+    Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
+    s = np.asarray(s, dtype=np.int32)
+    w = np.asarray(w, dtype=np.int32)
+    out = np.zeros(16, dtype=np.float32)
+    capi.load().nmi_apply_winner(ptr(Twc), C.byref(grid), ptr(s), ptr(w), ptr(out))
+    return out.reshape(4, 4)
+
+
+def grid_is_middle(grid: Grid, s, w) -> bool:
+    s = np.asarray(s, dtype=np.int32)
+    w = np.asarray(w, dtype=np.int32)
+    return bool(capi.load().nmi_grid_is_middle(C.byref(grid), ptr(s), ptr(w)))
+
+
+def grid_resize(grid: Grid, s, w) -> Grid:
+    g = grid.copy()
+    s = np.asarray(s, dtype=np.int32)
+    w = np.asarray(w, dtype=np.int32)
+    capi.load().nmi_grid_resize(C.byref(g), ptr(s), ptr(w))
+    return g
+
+
+def decode_key(grid: Grid, key: int) -> SearchResult:
+    r = Result()
+    capi.load().nmi_decode_key(C.byref(grid), C.c_uint64(key), C.byref(r))
+    return _result(r)
