@@ -109,10 +109,10 @@ def ncu_traffic_bytes():
 
 
 # ------------------------------------------------------------------ CPU baseline ----
-def cpu_baseline_run(scene, frame, threads: int, sample=((2, 2, 2), (2, 2, 2))):
+def cpu_baseline_run(scene, frame, threads: int, sample=((3, 3, 3), (3, 3, 3))):
     """Times the CPU oracle (the `port` of the reference's arithmetic; the reference itself
     has no CPU NMI path and cannot be built here) on a bounded sample of the
-    same workload: full-size frame and cloud, a (2x2x2)x(2x2x2)=64-pose grid."""
+    same workload: full-size frame and cloud, the reference default (3x3x3)x(3x3x3)=729-pose grid (ETH_small.yaml:77-82)."""
     from oracle import oracle_py as oracle  # test infrastructure: cpu_baseline leg only
     from orbslam2_nmi_b200 import synth
 
@@ -146,7 +146,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32+f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "note": "each step is a bounded 64-pose sample of the workload"},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "note": "each step is a bounded 729-pose (3^6) sample of the workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -174,7 +174,8 @@ def run_gpu(args):
     build.build_cuda()
 
     scene = synth.make_scene("C2")  # same seed on every rank: the cloud is replicated
-    frame = synth.frame_textured(scene.W, scene.H)
+    frame = {"textured": synth.frame_textured, "uniform": synth.frame_uniform,
+             "constant": synth.frame_constant}[args.frame](scene.W, scene.H)
     grid = grid_for(world)
     searcher = NmiSearcher(local)
     searcher.set_scene(scene)
@@ -274,7 +275,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "poses_per_step": evals_per_step,
                        "grid": {"nS": list(grid.nS), "nW": list(grid.nW)},
                        "l2": "inputs larger than L2 (160 MB cloud, 1.06 GB z-buffers, 266 MB images per step)",
-                       "hist_variant": args.variant, "frame": "textured synthetic, seed 5",
+                       "hist_variant": args.variant, "frame": args.frame + " synthetic",
                        "winner": {"index": winner.best_index, "score": winner.best_score}},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(P + 256 * 1024), "d2h_bytes_per_step": 8},
@@ -306,6 +307,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="histogram kernel variant (0..3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frame", default="textured", choices=["textured", "uniform", "constant"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
