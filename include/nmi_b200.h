@@ -123,12 +123,55 @@ int nmi_partition(const nmi_grid *grid, int rank, int world, int *axis,
 /* find_max_elements' answer from a (reduced) key.                            */
 int nmi_decode_key(const nmi_grid *grid, uint64_t key, nmi_result *out);
 
+/* ---- the coarse-to-fine driver ------------------------------------------ */
+#define NMI_MAX_PREV_POSES 8
+/* inputs of Tracking::RelocalizeWithNMIStrategy that live in Tracking's state  */
+typedef struct {
+  float threshold;              /* NMI.Treshold -> mfNmiInitTresholf (Tracking.cc:157)   */
+  int max_iterations;           /* nmi_prop_MAX_ITERATION_COUNT (allProperties.hpp:27), 0 = 4 */
+  float distance_since_last[3]; /* mDistanceSinceLastNMI (Tracking.cc:648-652)           */
+  float rotation_since_last[3]; /* mRotationSinceLastNMI (Tracking.cc:654-660)           */
+} nmi_reloc_params;
+
+typedef struct {
+  float Twc[16];     /* pose after accept / restore / reject                             */
+  int relocalized;   /* Frame::SetNMIRelocalized                                          */
+  int failed;        /* Frame::SetNMIFailed                                               */
+  int iterations;    /* grid searches run (<= max_iterations)                             */
+  float nmi;         /* NmiKernel->NMI     of the last search                             */
+  float last_nmi;    /* LastNmiKernel->NMI                                                */
+  float threshold_used;
+  nmi_grid final_grid;       /* NmiKernel after the last resizeKernel                     */
+  nmi_grid last_search_grid; /* grid of the last search that ran                          */
+  int32_t best_s[3], best_w[3];
+  int n_prev;                /* mvPreviousPoses (Tracking.cc:2094-2097)                    */
+  float prev_Twc[NMI_MAX_PREV_POSES][16];
+  int n_evals;               /* total (render, warp) pairs scored                         */
+  float gpu_ms;
+} nmi_reloc_result;
+
+/* Grid choice at the top of RelocalizeWithNMIStrategy (Tracking.cc:2001-2069):
+ * 2 % of the motion since the last fix, axes under 5 mm / 1 mrad collapse to 1;
+ * 5x5x5 translations while NOT_INITIALIZED; else the YAML "Initial" kernel.     */
+void nmi_grid_from_motion(const nmi_grid *initial, const float dist[3],
+                          const float rot[3], int not_initialized,
+                          nmi_grid *out);
+/* Tracking::RelocalizeWithNMIStrategy (src/Tracking.cc:1987-2179): up to
+ * max_iterations batched searches, step halving, stop rules, accept/reject.     */
+int nmi_relocalize(nmi_ctx *ctx, const float Twc[16], const nmi_grid *start_grid,
+                   const nmi_flags *flags, const nmi_reloc_params *params,
+                   nmi_reloc_result *out);
+
 /* ---- stage-level entry points (the reference's own call granularity) ---- */
 /* Rendering::renderToTextureOnGPU(calculateTranslation(sx,sy,sz))
  * (rendering.hpp:530-630, 644-665).  Returns an opaque render handle in
  * *handle -- the GL-free stand-in for getrenderedTexture() (rendering.hpp:749).*/
 int nmi_render_cell(nmi_ctx *ctx, const float Twc[16], const nmi_grid *grid,
                     int sx, int sy, int sz, unsigned int *handle);
+/* Same with an explicit world-frame translation, the argument
+ * renderToTextureOnGPU itself takes (rendering.hpp:530).                      */
+int nmi_render_at(nmi_ctx *ctx, const float Twc[16], const float t[3],
+                  unsigned int *handle);
 /* Image::calculateWarping (image.cpp:115-128): all nW warps of the frame.    */
 int nmi_warp_cells(nmi_ctx *ctx, const nmi_grid *grid);
 /* Image::getImageGPU(z,y,x).data (image.cpp:142): device pointer, W*H u8.    */

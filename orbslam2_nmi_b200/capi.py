@@ -57,6 +57,23 @@ class Flags(C.Structure):
     _fields_ = [("bins", C.c_int), ("score_mode", C.c_int), ("bg", C.c_int), ("variant", C.c_int)]
 
 
+class RelocParams(C.Structure):
+    _fields_ = [("threshold", C.c_float), ("max_iterations", C.c_int),
+                ("distance_since_last", C.c_float * 3), ("rotation_since_last", C.c_float * 3)]
+
+
+MAX_PREV_POSES = 8
+
+
+class RelocResult(C.Structure):
+    _fields_ = [("Twc", C.c_float * 16), ("relocalized", C.c_int), ("failed", C.c_int),
+                ("iterations", C.c_int), ("nmi", C.c_float), ("last_nmi", C.c_float),
+                ("threshold_used", C.c_float), ("final_grid", Grid), ("last_search_grid", Grid),
+                ("best_s", C.c_int32 * 3), ("best_w", C.c_int32 * 3), ("n_prev", C.c_int),
+                ("prev_Twc", (C.c_float * 16) * MAX_PREV_POSES), ("n_evals", C.c_int),
+                ("gpu_ms", C.c_float)]
+
+
 class Result(C.Structure):
     _fields_ = [("best_s", C.c_int32 * 3), ("best_w", C.c_int32 * 3), ("best_index", C.c_int64),
                 ("best_score", C.c_float), ("key", C.c_uint64), ("gpu_ms", C.c_float)]
@@ -81,6 +98,10 @@ SYMBOLS = [
     ("nmi_partition", C.c_int, [C.POINTER(Grid), C.c_int, C.c_int, C.POINTER(C.c_int),
                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("nmi_decode_key", C.c_int, [C.POINTER(Grid), C.c_uint64, C.POINTER(Result)]),
+    ("nmi_grid_from_motion", None, [C.POINTER(Grid), _P, _P, C.c_int, C.POINTER(Grid)]),
+    ("nmi_relocalize", C.c_int, [_P, _P, C.POINTER(Grid), C.POINTER(Flags), C.POINTER(RelocParams),
+                                 C.POINTER(RelocResult)]),
+    ("nmi_render_at", C.c_int, [_P, _P, _P, C.POINTER(C.c_uint)]),
     ("nmi_render_cell", C.c_int, [_P, _P, C.POINTER(Grid), C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_uint)]),
     ("nmi_warp_cells", C.c_int, [_P, C.POINTER(Grid)]),

@@ -6,6 +6,7 @@
 // params-upload + 6 kernels on one stream, whatever the grid size:
 //   cull_compact -> project_splat -> resolve -> warp -> joint_hist_score -> argmax
 // No CPU fallback exists: without a usable CUDA device every entry point fails.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -17,9 +18,9 @@
 namespace nmi {
 
 // project.cu (not in the header: only capi uses them)
-void launch_cull_compact(const float4* pts, uint32_t n, const ViewConst& vc, const float c0[3],
-                         const float margin[3], float4* out_pts, uint32_t* out_idx,
-                         uint32_t* counter, cudaStream_t st);
+void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const ViewConst& vc,
+                         const float c0[3], const float margin[3], float4* out_pts,
+                         uint32_t* out_idx, uint32_t* counter, cudaStream_t st);
 void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32_t* counter,
                           const float4* centres, int nviews, const ViewConst& vc,
                           unsigned long long* zbuf, size_t P, cudaStream_t st);
@@ -77,6 +78,8 @@ struct nmi_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_params = nullptr;  // completion of the last H2D from h_params
+  bool params_in_flight = false;
   bool timed = false;
 
   bool has_cam = false, has_frame = false;
@@ -84,7 +87,8 @@ struct nmi_ctx {
   size_t P = 0, pitch = 0;
 
   DevBuf<float4> pts;
-  DevBuf<uint8_t> val;
+  DevBuf<uint32_t> orig;  // original index of every (Morton-ordered) point
+  DevBuf<uint8_t> val;    // u8 intensity, indexed by ORIGINAL index
   size_t n_pts = 0;
   DevBuf<float4> cpts;    // compacted survivors of the cull
   DevBuf<uint32_t> cidx;  // their original indices
@@ -120,6 +124,20 @@ struct nmi_ctx {
 };
 
 namespace {
+
+// h_params is reused by every call: wait until the previous upload has been consumed
+int params_acquire(nmi_ctx* c) {
+  if (c->params_in_flight) {
+    CK(cudaEventSynchronize(c->ev_params));
+    c->params_in_flight = false;
+  }
+  return NMI_OK;
+}
+int params_uploaded(nmi_ctx* c) {
+  CK(cudaEventRecord(c->ev_params, c->stream));
+  c->params_in_flight = true;
+  return NMI_OK;
+}
 
 int ensure_pinned(unsigned char** p, size_t* cap, size_t n) {
   if (n <= *cap) return NMI_OK;
@@ -158,7 +176,7 @@ bool valid_grid(const nmi_grid* g) {
 bool valid_flags(const nmi_flags* f) {
   return f && (f->bins == 256 || f->bins == 64) &&
          (f->score_mode == NMI_SCORE_SUC || f->score_mode == NMI_SCORE_ENMI) && f->variant >= 0 &&
-         f->variant <= 3;
+         f->variant <= 7;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -169,7 +187,7 @@ int render_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int n
   if (recull) {
     CK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
     const float c0[3] = {c->Twc[3], c->Twc[7], c->Twc[11]};
-    launch_cull_compact(c->pts.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
+    launch_cull_compact(c->pts.p, c->orig.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
                         c->counter.p, c->stream);
     c->launches++;
   }
@@ -188,7 +206,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
                 int world, unsigned long long* key_dev, float* scores_dev) {
   REQUIRE(c && Twc, NMI_ERR_INVALID, "null ctx / Twc");
   REQUIRE(valid_grid(g), NMI_ERR_INVALID, "invalid grid (counts must be 1..4096, nP <= 2^26)");
-  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags (bins 256|64, score 0|1, variant 0..3)");
+  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags (bins 256|64, score 0|1, variant 0..7)");
   REQUIRE(c->has_cam && c->n_pts > 0 && c->has_frame, NMI_ERR_STATE,
           "camera, model and frame must be set before a search");
   CK(cudaSetDevice(c->device));
@@ -213,7 +231,9 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   const size_t off_p = align_up(off_m + sizeof(float) * 9 * (size_t)nwl, 256);
   const size_t off_i = align_up(off_p + sizeof(int2) * npl, 256);
   const size_t bytes = align_up(off_i + sizeof(uint32_t) * npl, 256);
+  if (int rc = params_acquire(c)) return rc;
   if (int rc = ensure_pinned(&c->h_params, &c->h_params_cap, bytes)) return rc;
+  if (bytes > c->params.cap) CK(cudaStreamSynchronize(c->stream));  // old block may be in use
   CK(c->params.reserve(bytes));
 
   ViewConst vc;
@@ -265,6 +285,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   c->launches = 0;
   if (c->timed) CK(cudaEventRecord(c->ev[0], c->stream));
   CK(cudaMemcpyAsync(c->params.p, c->h_params, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (int rc = params_uploaded(c)) return rc;
   const float4* d_centres = reinterpret_cast<const float4*>(c->params.p + off_c);
   const float* d_minv = reinterpret_cast<const float*>(c->params.p + off_m);
   const int2* d_pairs = reinterpret_cast<const int2*>(c->params.p + off_p);
@@ -277,7 +298,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
     if (v0 == 0) {
       CK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
       const float c0[3] = {Twc[3], Twc[7], Twc[11]};
-      launch_cull_compact(c->pts.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
+      launch_cull_compact(c->pts.p, c->orig.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
                           c->counter.p, c->stream);
       c->launches++;
       if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
@@ -348,6 +369,7 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   c->device = device;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& e : c->ev) CK(cudaEventCreate(&e));
+  CK(cudaEventCreateWithFlags(&c->ev_params, cudaEventDisableTiming));
   CK(c->counter.reserve(1));
   CK(c->key.reserve(1));
   CK(c->one_score.reserve(1));
@@ -362,7 +384,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->pts.release(); c->val.release(); c->cpts.release(); c->cidx.release(); c->counter.release();
+  c->pts.release(); c->orig.release(); c->val.release(); c->cpts.release(); c->cidx.release(); c->counter.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
   c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
@@ -370,6 +392,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (c->h_frame) cudaFreeHost(c->h_frame);
   if (c->h_params) cudaFreeHost(c->h_params);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->ev_params) cudaEventDestroy(c->ev_params);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -402,11 +425,61 @@ int nmi_set_camera(nmi_ctx* c, const nmi_camera* cam) {
   return NMI_OK;
 }
 
-static int finish_points(nmi_ctx* c, size_t n) {
+// Model upload.  The cloud is stored in 3-D Morton order (a load-time permutation) so that
+// neighbouring threads of the projection kernel splat neighbouring pixels: z-buffer lines
+// are then fetched from HBM about once per search instead of once per fragment.  The
+// ORIGINAL index travels with every point -- it is what the z-buffer key carries, so the
+// GL "earlier primitive wins a depth tie" rule (rendering.hpp:297) is unaffected.
+static inline uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+int nmi_set_points(nmi_ctx* c, const float* xyzi, size_t n) {
+  REQUIRE(c && xyzi && n > 0 && n < 0xFFFFFFFFull, NMI_ERR_INVALID, "bad point cloud");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (size_t i = 0; i < n; i++)
+    for (int k = 0; k < 3; k++) {
+      const float v = xyzi[4 * i + k];
+      if (v < lo[k]) lo[k] = v;
+      if (v > hi[k]) hi[k] = v;
+    }
+  float scale[3];
+  for (int k = 0; k < 3; k++) scale[k] = hi[k] > lo[k] ? 1023.0f / (hi[k] - lo[k]) : 0.0f;
+  std::vector<uint64_t> order(n);
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; i++) {
+    uint32_t q[3];
+    for (int k = 0; k < 3; k++) {
+      const float f = (xyzi[4 * i + k] - lo[k]) * scale[k];
+      q[k] = f >= 0.0f ? (f < 1023.0f ? (uint32_t)f : 1023u) : 0u;  // NaN -> 0
+    }
+    const uint64_t m = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+    order[i] = (m << 32) | (uint64_t)i;
+  }
+  std::sort(order.begin(), order.end());
+  std::vector<float> sorted(4 * n);
+  std::vector<uint32_t> orig(n);
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)n; i++) {
+    const uint32_t src = (uint32_t)(order[i] & 0xFFFFFFFFu);
+    orig[i] = src;
+    memcpy(&sorted[4 * i], &xyzi[4 * (size_t)src], 4 * sizeof(float));
+  }
+  CK(c->pts.reserve(n));
+  CK(c->orig.reserve(n));
   CK(c->val.reserve(n));
   CK(c->cpts.reserve(n));
   CK(c->cidx.reserve(n));
-  launch_intensity_u8(c->pts.p, c->val.p, n, c->stream);
+  CK(cudaMemcpyAsync(c->pts.p, sorted.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->orig.p, orig.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  launch_intensity_u8(c->pts.p, c->orig.p, c->val.p, n, c->stream);  // val[original index]
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   c->n_pts = n;
@@ -414,22 +487,13 @@ static int finish_points(nmi_ctx* c, size_t n) {
   return NMI_OK;
 }
 
-int nmi_set_points(nmi_ctx* c, const float* xyzi, size_t n) {
-  REQUIRE(c && xyzi && n > 0 && n < 0xFFFFFFFFull, NMI_ERR_INVALID, "bad point cloud");
-  CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->stream));
-  CK(c->pts.reserve(n));
-  CK(cudaMemcpyAsync(c->pts.p, xyzi, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-  return finish_points(c, n);
-}
-
 int nmi_set_points_device(nmi_ctx* c, const void* xyzi_dev, size_t n) {
   REQUIRE(c && xyzi_dev && n > 0 && n < 0xFFFFFFFFull, NMI_ERR_INVALID, "bad point cloud");
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->stream));
-  CK(c->pts.reserve(n));
-  CK(cudaMemcpyAsync(c->pts.p, xyzi_dev, n * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
-  return finish_points(c, n);
+  // load-time path: bring the cloud to the host once for the Morton ordering
+  std::vector<float> host(4 * n);
+  CK(cudaMemcpy(host.data(), xyzi_dev, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  return nmi_set_points(c, host.data(), n);
 }
 
 int nmi_set_frame(nmi_ctx* c, const uint8_t* gray, int W, int H) {
@@ -498,18 +562,12 @@ int nmi_search_enqueue(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const
 
 // ---- stage-level API ------------------------------------------------------
 
-int nmi_render_cell(nmi_ctx* c, const float Twc[16], const nmi_grid* g, int sx, int sy, int sz,
-                    unsigned int* handle) {
-  REQUIRE(c && Twc && handle, NMI_ERR_INVALID, "null argument");
-  REQUIRE(valid_grid(g), NMI_ERR_INVALID, "invalid grid");
+int nmi_render_at(nmi_ctx* c, const float Twc[16], const float t[3], unsigned int* handle) {
+  REQUIRE(c && Twc && t && handle, NMI_ERR_INVALID, "null argument");
   REQUIRE(c->has_cam && c->n_pts > 0, NMI_ERR_STATE, "camera and model must be set");
-  REQUIRE(sx >= 0 && sx < g->nS[0] && sy >= 0 && sy < g->nS[1] && sz >= 0 && sz < g->nS[2],
-          NMI_ERR_INVALID, "cell out of range");
   CK(cudaSetDevice(c->device));
   ViewConst vc;
   make_view_const(c->cam, Twc, &vc);
-  float t[3];
-  nmi_cell_translation(Twc, g, sx, sy, sz, t);
   if (int rc = ensure_pinned(&c->h_params, &c->h_params_cap, 4096)) return rc;
   CK(c->params.reserve(4096));
   CK(c->one_render.reserve(c->pitch));
@@ -532,6 +590,17 @@ int nmi_render_cell(nmi_ctx* c, const float Twc[16], const nmi_grid* g, int sx, 
   if (rc) return rc;
   *handle = 1;  // the one "rendered texture" (rendering.hpp:341 creates exactly one)
   return NMI_OK;
+}
+
+int nmi_render_cell(nmi_ctx* c, const float Twc[16], const nmi_grid* g, int sx, int sy, int sz,
+                    unsigned int* handle) {
+  REQUIRE(c && Twc && handle, NMI_ERR_INVALID, "null argument");
+  REQUIRE(valid_grid(g), NMI_ERR_INVALID, "invalid grid");
+  REQUIRE(sx >= 0 && sx < g->nS[0] && sy >= 0 && sy < g->nS[1] && sz >= 0 && sz < g->nS[2],
+          NMI_ERR_INVALID, "cell out of range");
+  float t[3];
+  nmi_cell_translation(Twc, g, sx, sy, sz, t);
+  return nmi_render_at(c, Twc, t, handle);
 }
 
 int nmi_warp_cells(nmi_ctx* c, const nmi_grid* g) {

@@ -1,0 +1,123 @@
+// driver.cpp -- the coarse-to-fine NMI relocalisation driver (host C++, no CUDA).
+//
+// Restates Tracking::RelocalizeWithNMIStrategy (src/Tracking.cc:1987-2179) and the
+// per-level body Tracking::RelocalizeWithNMI (src/Tracking.cc:1851-1985) on a plain
+// pose instead of a Frame/KeyFrame object.  Every level is ONE nmi_search() call
+// (the reference runs nS*nW separate evaluations), re-centred on the previous winner
+// with NmiSearchKernel::resizeKernel's step-halving rule (nmiSearchKernel.cpp:104-141).
+// The accept / reject logic is kept decision for decision.
+#include <cmath>
+#include <cstring>
+
+#include "nmi_internal.h"
+
+extern "C" {
+
+void nmi_grid_from_motion(const nmi_grid* initial, const float dist[3], const float rot[3],
+                          int not_initialized, nmi_grid* out) {
+  // src/Tracking.cc:2001-2069
+  const double min_trans = 0.005, min_rot = 0.001;  // allProperties.hpp:48-49
+  if (dist[0] > 0.0f) {
+    for (int k = 0; k < 3; ++k) {
+      // "ORB-SLAM 2 has a drift about 1% so we conservatively search in the 2% proximity"
+      const float st = static_cast<float>(dist[k] * 0.02);
+      const float sr = static_cast<float>(rot[k] * 0.02);
+      out->stepT[k] = st;
+      out->stepR[k] = sr;
+      out->nS[k] = st < min_trans ? 1 : initial->nS[k];
+      out->nW[k] = sr < min_rot ? 1 : initial->nW[k];
+    }
+  } else if (not_initialized) {
+    *out = *initial;
+    out->nS[0] = out->nS[1] = out->nS[2] = 5;  // Tracking.cc:2057
+  } else {
+    *out = *initial;
+  }
+}
+
+int nmi_relocalize(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid* start_grid,
+                   const nmi_flags* flags, const nmi_reloc_params* prm, nmi_reloc_result* out) {
+  if (!ctx || !Twc_in || !start_grid || !flags || !prm || !out) {
+    nmi::set_error("nmi_relocalize: null argument");
+    return NMI_ERR_INVALID;
+  }
+  std::memset(out, 0, sizeof *out);
+  const int max_it = prm->max_iterations > 0 ? prm->max_iterations : 4;  // allProperties.hpp:27
+
+  nmi_grid kernel = *start_grid;        // MyObjects->NmiKernel (grid part)
+  float kernel_nmi = 0.0f;              //   ->NMI, reset() at Tracking.cc:1997
+  float last_nmi = 0.0f;                // MyObjects->LastNmiKernel->NMI, reset() at :1998
+  float pose[16], save[16], save_last[16];
+  std::memcpy(pose, Twc_in, sizeof pose);
+  std::memcpy(save, Twc_in, sizeof save);            // TcwSave      (:2082-2085)
+  std::memcpy(save_last, Twc_in, sizeof save_last);  // TcwSaveLast  (:2087)
+  int under = 0, i = 0;
+  nmi_result best{};
+  nmi_grid used = kernel;
+
+  for (;;) {
+    ++i;
+    if (i > max_it) break;  // :2091
+    if (out->n_prev < NMI_MAX_PREV_POSES)
+      std::memcpy(out->prev_Twc[out->n_prev++], pose, sizeof pose);  // mvPreviousPoses (:2094-2097)
+
+    // ---- RelocalizeWithNMI: one batched grid search around `pose` ----
+    nmi_result r{};
+    const int rc = nmi_search(ctx, pose, &kernel, flags, &r, nullptr);
+    if (rc != NMI_OK) return rc;  // NMI_ERR_NO_WINNER is the reference's UB case: surface it
+    out->gpu_ms += r.gpu_ms;
+    out->n_evals += kernel.nS[0] * kernel.nS[1] * kernel.nS[2] * kernel.nW[0] * kernel.nW[1] * kernel.nW[2];
+    kernel_nmi = r.best_score;  // NmiKernel->setBest + NMI (:1952-1953)
+    best = r;
+    used = kernel;
+    float moved[16];
+    nmi_apply_winner(pose, &kernel, r.best_s, r.best_w, moved);  // :1956, :1976-1983
+    std::memcpy(pose, moved, sizeof pose);
+    out->relocalized = 1;  // SetNMIRelocalized(true) (:1978,:1982)
+    out->iterations = i;
+
+    if (i > 1 && nmi_grid_is_middle(&kernel, r.best_s, r.best_w)) break;  // :2108-2110
+    if (i > 1) {                                                         // :2112-2121
+      if (static_cast<double>(kernel_nmi / last_nmi) < 1.001) {
+        if (under > 0) break;
+        ++under;
+      } else {
+        under = 0;
+      }
+    }
+    // NMIobjectsReInitialization (:2124): Last <- current, then halve the steps
+    last_nmi = kernel_nmi;
+    nmi_grid_resize(&kernel, r.best_s, r.best_w);
+    std::memcpy(save_last, pose, sizeof pose);  // :2126-2129
+  }
+
+  if (kernel_nmi < last_nmi) std::memcpy(pose, save_last, sizeof pose);  // :2134-2139
+
+  // :2143-2152 threshold relaxed with the distance travelled since the last NMI fix
+  const double base = 5.0;
+  const double d = std::sqrt(std::pow(prm->distance_since_last[0], 2) + std::pow(prm->distance_since_last[1], 2) +
+                             std::pow(prm->distance_since_last[2], 2));
+  double thr = prm->threshold;
+  if (!(d < base)) {
+    thr = prm->threshold * (base / d);
+    if (thr < prm->threshold / 2) thr = prm->threshold / 2;
+  }
+  if (kernel_nmi < thr) {  // :2157-2168
+    std::memcpy(pose, save, sizeof pose);
+    out->relocalized = 0;
+    out->failed = 1;
+  }
+  std::memcpy(out->Twc, pose, sizeof pose);
+  out->nmi = kernel_nmi;
+  out->last_nmi = last_nmi;
+  out->threshold_used = static_cast<float>(thr);
+  out->final_grid = kernel;
+  out->last_search_grid = used;
+  for (int k = 0; k < 3; ++k) {
+    out->best_s[k] = best.best_s[k];
+    out->best_w[k] = best.best_w[k];
+  }
+  return NMI_OK;
+}
+
+}  // extern "C"

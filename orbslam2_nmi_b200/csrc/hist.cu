@@ -17,7 +17,9 @@
 // sums (integers, exact); only one float leaves the SM.  Both images are streamed
 // through a 3-stage shared-memory ring filled by the TMA engine
 // (cp.async.bulk + mbarrier complete_tx), issued by a dedicated producer warp,
-// so the 16 consumer warps spend their issue slots on shared-memory atomics.
+// so the 16 or 32 consumer warps spend their issue slots on shared-memory atomics.
+// The hot loop is branch-free: each thread fires all its atomics of a chunk back to
+// back (independent ATOMS in flight) and only afterwards inspects the returned values.
 //
 // Histogram storage policies (template POLICY):
 //   P_U16G  256 bins, single pass. 65 536 counters, two 16-bit fields per 32-bit
@@ -38,10 +40,7 @@
 namespace nmi {
 namespace {
 
-constexpr int kConsumerWarps = 16;
-constexpr int kConsumers = kConsumerWarps * 32;  // 512
-constexpr int kThreads = kConsumers + 32;        // + 1 producer warp
-constexpr int kChunk = kConsumers * 16;          // 8192 pixels per stage and image
+constexpr int kChunk = 8192;  // pixels per stage and image
 constexpr int kStages = 3;
 constexpr int kEvCap = 1024;
 constexpr int kHistWords = 32768;  // 128 KiB
@@ -132,19 +131,29 @@ __device__ __forceinline__ float finish_score(float sa, float sb, float sab, int
   return __fmul_rn(2.0f, __fsub_rn(1.0f, __fdiv_rn(-sab, __fadd_rn(-sa, -sb))));
 }
 
-// ---- per-pixel accumulation --------------------------------------------------
-template <int POLICY>
-__device__ __forceinline__ void accum(Smem& sm, uint32_t t, int pass, int warp) {
-  // t = (a << 8) | b, 16 bits
+// ---- bin addressing ----------------------------------------------------------
+// t = (a << 8) | b.  U16G: word (t >> 1), 16-bit field (t & 1).  With SWZ the word's low
+// five bits are XORed with a's low five bits: the bank then depends on both images, so a
+// flat region in one of them no longer piles a whole warp onto one bank.
+template <bool SWZ>
+__device__ __forceinline__ uint32_t u16g_word(uint32_t t) {
+  const uint32_t w = (t >> 1) & 0x7FFFu;
+  return SWZ ? (w ^ ((t >> 8) & 31u)) : w;
+}
+template <bool SWZ>
+__device__ __forceinline__ void u16g_fixup(Smem& sm, uint32_t t) {
+  atomicSub(sm.hist + u16g_word<SWZ>(t), 0x4000u << ((t & 1u) << 4));
+  const uint32_t e = atomicAdd(&sm.ev_count, 1u);
+  if (e < kEvCap) sm.ev_list[e] = (uint16_t)t;
+}
+
+// generic (branchy) per-pixel path: partial chunks and BG == false
+template <int POLICY, bool SWZ>
+__device__ __forceinline__ void accum_one(Smem& sm, uint32_t t, int pass, int warp) {
   if (POLICY == P_U16G) {
     const uint32_t sh = (t & 1u) << 4;
-    uint32_t* wp = sm.hist + (t >> 1);
-    const uint32_t old = atomicAdd(wp, 1u << sh);
-    if (((old >> sh) & 0x3FFFu) == 0x3FFFu) {  // count crossed a multiple of 16384
-      atomicSub(wp, 0x4000u << sh);
-      const uint32_t e = atomicAdd(&sm.ev_count, 1u);
-      if (e < kEvCap) sm.ev_list[e] = (uint16_t)t;
-    }
+    const uint32_t old = atomicAdd(sm.hist + u16g_word<SWZ>(t), 1u << sh);
+    if (((old >> sh) & 0x3FFFu) == 0x3FFFu) u16g_fixup<SWZ>(sm, t);  // crossed a multiple of 16384
   } else if (POLICY == P_U32X2) {
     if ((int)(t >> 15) == pass) atomicAdd(sm.hist + (t & 0x7FFFu), 1u);
   } else {
@@ -153,43 +162,80 @@ __device__ __forceinline__ void accum(Smem& sm, uint32_t t, int pass, int warp) 
   }
 }
 
-template <int POLICY>
-__device__ __forceinline__ void accum_words(Smem& sm, uint32_t rw, uint32_t ww, int nvalid, int bg,
-                                            int pass, int warp) {
+template <int POLICY, bool SWZ, int NW>
+__device__ __forceinline__ void accum_slow(Smem& sm, const uint32_t (&rw)[NW], const uint32_t (&ww)[NW],
+                                           int nvalid, int bg, int pass, int warp) {
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    if (k < nvalid) {
-      const uint32_t t = __byte_perm(ww, rw, 0x4440 + k * 0x11) & 0xFFFFu;
-      if (bg || ((t & 0xFF00u) != 0 && (t & 0xFFu) != 0)) accum<POLICY>(sm, t, pass, warp);
-    }
-  }
+  for (int j = 0; j < NW; j++)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (4 * j + k < nvalid) {
+        const uint32_t t = __byte_perm(ww[j], rw[j], 0x4440 + k * 0x11) & 0xFFFFu;
+        if (bg || ((t & 0xFF00u) != 0 && (t & 0xFFu) != 0)) accum_one<POLICY, SWZ>(sm, t, pass, warp);
+      }
 }
 
-template <int POLICY>
-__device__ __forceinline__ void accum16(Smem& sm, const uint4& r, const uint4& w, int nvalid,
-                                        int bg, int pass, int warp) {
-  accum_words<POLICY>(sm, r.x, w.x, nvalid, bg, pass, warp);
-  accum_words<POLICY>(sm, r.y, w.y, nvalid - 4, bg, pass, warp);
-  accum_words<POLICY>(sm, r.z, w.z, nvalid - 8, bg, pass, warp);
-  accum_words<POLICY>(sm, r.w, w.w, nvalid - 12, bg, pass, warp);
+// fast path: full chunk, every pixel counted (nmi_prop_BG == true, the reference default)
+template <int POLICY, bool SWZ, int NW>
+__device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], const uint32_t (&ww)[NW],
+                                           int pass, int warp) {
+  constexpr int N = NW * 4;
+  if (POLICY == P_U16G) {
+    uint32_t t[N], old[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      t[i] = __byte_perm(ww[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);
+      old[i] = atomicAdd(sm.hist + u16g_word<SWZ>(t[i]), 1u << ((t[i] & 1u) << 4));
+    }
+    uint32_t flag = 0xFFFFFFFFu;  // becomes 0 iff some increment wrapped its field's low 14 bits
+#pragma unroll
+    for (int i = 0; i < N; i++) flag = min(flag, ~(old[i] >> ((t[i] & 1u) << 4)) & 0x3FFFu);
+    if (flag == 0) {
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        if ((~(old[i] >> ((t[i] & 1u) << 4)) & 0x3FFFu) == 0) u16g_fixup<SWZ>(sm, t[i] & 0xFFFFu);
+    }
+  } else if (POLICY == P_U32X2) {
+    const uint32_t base = smem_u32(sm.hist);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const uint32_t t = __byte_perm(ww[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);
+      // predicated reduction, no branch: only rows of this pass's half are counted
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.eq.u32 p, %1, %2;\n\t"
+          "@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(base + ((t & 0x7FFFu) << 2)),
+          "r"((t >> 15) & 1u), "r"((uint32_t)pass)
+          : "memory");
+    }
+  } else {
+    uint32_t* h = sm.hist + (warp & (kB64Copies - 1)) * 4096;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const uint32_t t = __byte_perm(ww[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);
+      atomicAdd(h + (((t >> 4) & 0xFC0u) | ((t >> 2) & 0x3Fu)), 1u);
+    }
+  }
 }
 
 // ---- epilogue over the rows of one pass --------------------------------------
 // U16G: one pass, 256 rows of 128 packed words.  U32X2: 128 rows of 256 words per
 // pass.  B64: 64 rows of 64 words after folding the copies.
-template <int POLICY>
+template <int POLICY, bool SWZ, int NWARPS>
 __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const HistArgs& a,
                                               bool dump, int warp, int lane) {
+  constexpr int kConsumers = NWARPS * 32;
   if (POLICY == P_U16G) {
     const uint32_t nev = min(sm.ev_count, (uint32_t)kEvCap);
     uint32_t col[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) col[i] = 0;
-    for (int row = warp; row < 256; row += kConsumerWarps) {
+    for (int row = warp; row < 256; row += NWARPS) {
       uint32_t c[8];  // c[2k+h] = J[row][2(lane+32k)+h]
+      const int src = SWZ ? (lane ^ (row & 31)) : lane;  // undo the bank swizzle
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const uint32_t wv = sm.hist[row * 128 + lane + 32 * k];
+        const uint32_t wv = sm.hist[row * 128 + src + 32 * k];
         c[2 * k] = wv & 0xFFFFu;
         c[2 * k + 1] = wv >> 16;
       }
@@ -237,7 +283,7 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
     uint32_t col[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) col[i] = 0;
-    for (int lr = warp; lr < 128; lr += kConsumerWarps) {
+    for (int lr = warp; lr < 128; lr += NWARPS) {
       const int row = pass * 128 + lr;
       float v[8];
       uint32_t rs = 0;
@@ -259,7 +305,7 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
 #pragma unroll
     for (int k = 0; k < 8; k++) atomicAdd(&sm.HB[lane + 32 * k], col[k]);
   } else {
-    // fold the replicated sub-histograms into copy 0 (all 512 consumers)
+    // fold the replicated sub-histograms into copy 0 (all consumers)
     const int tid = warp * 32 + lane;
     for (int i = tid; i < 4096; i += kConsumers) {
       uint32_t s = 0;
@@ -269,7 +315,7 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
     uint32_t col[2] = {0, 0};
-    for (int row = warp; row < 64; row += kConsumerWarps) {
+    for (int row = warp; row < 64; row += NWARPS) {
       float v[2];
       uint32_t rs = 0;
 #pragma unroll
@@ -292,12 +338,37 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
   }
 }
 
-template <int POLICY, bool USE_TMA>
-__global__ void __launch_bounds__(kThreads, 1) joint_hist_score_kernel(const HistArgs a) {
+template <int NW>
+__device__ __forceinline__ void load_words(uint32_t (&dst)[NW], const uint8_t* p) {
+  if (NW == 4) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[NW - 1] = v.w;
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    dst[0] = v.x; dst[NW - 1] = v.y;
+  }
+}
+template <int NW>
+__device__ __forceinline__ void ldg_words(uint32_t (&dst)[NW], const uint8_t* p) {
+  if (NW == 4) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[NW - 1] = v.w;
+  } else {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    dst[0] = v.x; dst[NW - 1] = v.y;
+  }
+}
+
+template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ>
+__global__ void __launch_bounds__(NWARPS * 32 + 32, 1) joint_hist_score_kernel(const HistArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int BINS = POLICY == P_B64 ? 64 : 256;
   constexpr int NPASS = POLICY == P_U32X2 ? 2 : 1;
+  constexpr int kConsumers = NWARPS * 32;
+  constexpr int kThreads = kConsumers + 32;
+  constexpr int PIX = kChunk / kConsumers;  // pixels per thread and chunk: 16 or 8
+  constexpr int NW = PIX / 4;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -319,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_hist_score_kernel(const His
       sm.ev_count = 0;
       for (int s = 0; s < kStages; s++) {
         mbar_init(&sm.full[s], 1);
-        mbar_init(&sm.empty[s], kConsumerWarps);
+        mbar_init(&sm.empty[s], NWARPS);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -327,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_hist_score_kernel(const His
   }
   __syncthreads();
 
-  if (warp == kConsumerWarps) {
+  if (warp == NWARPS) {
     // ===== producer warp: TMA ring =====
     if (USE_TMA && lane == 0) {
       for (int k = 0; k < total; k++) {
@@ -344,41 +415,43 @@ __global__ void __launch_bounds__(kThreads, 1) joint_hist_score_kernel(const His
     }
   } else {
     // ===== consumers =====
-    uint4 nr = make_uint4(0, 0, 0, 0), nw = nr;
+    uint32_t nr[NW], nw[NW];
+#pragma unroll
+    for (int j = 0; j < NW; j++) nr[j] = nw[j] = 0;
     if (!USE_TMA) {
-      const uint32_t off = (uint32_t)tid * 16;
+      const uint32_t off = (uint32_t)tid * PIX;
       if (off < npix) {
-        nr = __ldg(reinterpret_cast<const uint4*>(rimg + off));
-        nw = __ldg(reinterpret_cast<const uint4*>(wimg + off));
+        ldg_words<NW>(nr, rimg + off);
+        ldg_words<NW>(nw, wimg + off);
       }
     }
     for (int k = 0; k < total; k++) {
       const int pass = k / nchunks;
       const int ck = k - pass * nchunks;
-      const uint32_t off = (uint32_t)ck * kChunk + (uint32_t)tid * 16;
-      uint4 r, w;
+      const uint32_t off = (uint32_t)ck * kChunk + (uint32_t)tid * PIX;
+      uint32_t r[NW], w[NW];
       if (USE_TMA) {
         const int st = k % kStages;
         mbar_wait(&sm.full[st], (k / kStages) & 1);
-        r = *reinterpret_cast<const uint4*>(sm.rbuf[st] + tid * 16);
-        w = *reinterpret_cast<const uint4*>(sm.wbuf[st] + tid * 16);
+        load_words<NW>(r, sm.rbuf[st] + tid * PIX);
+        load_words<NW>(w, sm.wbuf[st] + tid * PIX);
       } else {
-        r = nr;
-        w = nw;
+#pragma unroll
+        for (int j = 0; j < NW; j++) { r[j] = nr[j]; w[j] = nw[j]; }
         if (k + 1 < total) {  // register prefetch of the next chunk
           const int ck2 = (k + 1) % nchunks;
-          const uint32_t off2 = (uint32_t)ck2 * kChunk + (uint32_t)tid * 16;
+          const uint32_t off2 = (uint32_t)ck2 * kChunk + (uint32_t)tid * PIX;
           if (off2 < npix) {
-            nr = __ldg(reinterpret_cast<const uint4*>(rimg + off2));
-            nw = __ldg(reinterpret_cast<const uint4*>(wimg + off2));
+            ldg_words<NW>(nr, rimg + off2);
+            ldg_words<NW>(nw, wimg + off2);
           }
         }
       }
-      const int nvalid = off >= npix ? 0 : (int)min(16u, npix - off);
-      if (nvalid == 16)
-        accum16<POLICY>(sm, r, w, 16, a.bg, pass, warp);
+      const int nvalid = off >= npix ? 0 : (int)min((uint32_t)PIX, npix - off);
+      if (nvalid == PIX && a.bg)
+        accum_fast<POLICY, SWZ, NW>(sm, r, w, pass, warp);
       else if (nvalid > 0)
-        accum16<POLICY>(sm, r, w, nvalid, a.bg, pass, warp);
+        accum_slow<POLICY, SWZ, NW>(sm, r, w, nvalid, a.bg, pass, warp);
       if (USE_TMA) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[k % kStages]);
@@ -388,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_hist_score_kernel(const His
       if (NPASS == 2 && ck == nchunks - 1) {
         // end of a pass: rows of this half are final
         asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
-        rows_epilogue<POLICY>(sm, pass, L, a, dump, warp, lane);
+        rows_epilogue<POLICY, SWZ, NWARPS>(sm, pass, L, a, dump, warp, lane);
         if (pass == 0) {
           asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
           uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
@@ -399,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) joint_hist_score_kernel(const His
     }
     if (NPASS == 1) {
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
-      rows_epilogue<POLICY>(sm, 0, L, a, dump, warp, lane);
+      rows_epilogue<POLICY, SWZ, NWARPS>(sm, 0, L, a, dump, warp, lane);
     }
   }
   __syncthreads();
@@ -426,9 +499,9 @@ __global__ void __launch_bounds__(kThreads, 1) joint_hist_score_kernel(const His
         finish_score(sm.sums[1], sm.sums[2], sm.sums[0], a.mode);
 }
 
-template <int POLICY, bool USE_TMA>
+template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ>
 int launch_t(const HistArgs& a, cudaStream_t st) {
-  auto kern = joint_hist_score_kernel<POLICY, USE_TMA>;
+  auto kern = joint_hist_score_kernel<POLICY, USE_TMA, NWARPS, SWZ>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -436,7 +509,7 @@ int launch_t(const HistArgs& a, cudaStream_t st) {
       return -1;
     configured = true;
   }
-  kern<<<a.npairs, kThreads, sizeof(Smem), st>>>(a);
+  kern<<<a.npairs, NWARPS * 32 + 32, sizeof(Smem), st>>>(a);
   return 1;
 }
 
@@ -444,12 +517,18 @@ int launch_t(const HistArgs& a, cudaStream_t st) {
 
 int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
   if (a.npairs <= 0) return 0;
-  if (a.bins == 64) return a.variant == 1 ? launch_t<P_B64, false>(a, st) : launch_t<P_B64, true>(a, st);
+  if (a.bins == 64)
+    return (a.variant & 1) ? launch_t<P_B64, false, 16, false>(a, st)
+                           : launch_t<P_B64, true, 16, false>(a, st);
   switch (a.variant) {
-    case 1: return launch_t<P_U16G, false>(a, st);
-    case 2: return launch_t<P_U32X2, true>(a, st);
-    case 3: return launch_t<P_U32X2, false>(a, st);
-    default: return launch_t<P_U16G, true>(a, st);
+    case 1: return launch_t<P_U16G, false, 16, false>(a, st);
+    case 2: return launch_t<P_U32X2, true, 16, false>(a, st);
+    case 3: return launch_t<P_U32X2, false, 16, false>(a, st);
+    case 4: return launch_t<P_U16G, true, 32, false>(a, st);
+    case 5: return launch_t<P_U16G, true, 16, true>(a, st);
+    case 6: return launch_t<P_U16G, true, 32, true>(a, st);
+    case 7: return launch_t<P_U32X2, true, 32, false>(a, st);
+    default: return launch_t<P_U16G, true, 16, false>(a, st);
   }
 }
 

@@ -36,14 +36,14 @@ __global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long l
 
 // value = floor(255 I + 0.5) clamped (objloader.cpp:261 stores I = red/256;
 // GL float->unorm8 conversion, tie rule ours)
-__global__ void intensity_u8_kernel(const float4* __restrict__ pts, uint8_t* __restrict__ val,
-                                    size_t n) {
+__global__ void intensity_u8_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ orig,
+                                    uint8_t* __restrict__ val, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float f = floorf(__fadd_rn(__fmul_rn(255.0f, pts[i].w), 0.5f));
   if (!(f >= 0.0f)) f = 0.0f;
   if (f > 255.0f) f = 255.0f;
-  val[i] = (uint8_t)f;
+  val[orig[i]] = (uint8_t)f;  // looked up by the original index the z-buffer key carries
 }
 
 struct CullConst {
@@ -53,9 +53,9 @@ struct CullConst {
 
 // Conservative frustum-union test, then warp-aggregated append.
 __global__ void __launch_bounds__(256)
-cull_compact_kernel(const float4* __restrict__ pts, uint32_t n, ViewConst vc, CullConst cc,
-                    float4* __restrict__ out_pts, uint32_t* __restrict__ out_idx,
-                    uint32_t* __restrict__ counter) {
+cull_compact_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ orig, uint32_t n,
+                    ViewConst vc, CullConst cc, float4* __restrict__ out_pts,
+                    uint32_t* __restrict__ out_idx, uint32_t* __restrict__ counter) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool keep = false;
   float4 p = make_float4(0, 0, 0, 0);
@@ -81,7 +81,7 @@ cull_compact_kernel(const float4* __restrict__ pts, uint32_t n, ViewConst vc, Cu
   if (keep) {
     uint32_t o = base + __popc(m & ((1u << lane) - 1u));
     out_pts[o] = p;
-    out_idx[o] = i;
+    out_idx[o] = orig[i];
   }
 }
 
@@ -131,7 +131,6 @@ project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict
   }
 }
 
-// Fallback without compaction (tiny clouds): identical arithmetic.
 __global__ void __launch_bounds__(256)
 resolve_kernel(unsigned long long* __restrict__ zbuf, const uint8_t* __restrict__ val, size_t P,
                uint8_t* __restrict__ images, size_t pitch, uint32_t* __restrict__ winners) {
@@ -169,21 +168,23 @@ void launch_fill_u64(unsigned long long* p, size_t n, unsigned long long v, cuda
   fill_u64_kernel<<<148 * 8, 256, 0, st>>>(p, n, v);
 }
 
-void launch_intensity_u8(const float4* pts, uint8_t* val, size_t n, cudaStream_t st) {
+void launch_intensity_u8(const float4* pts, const uint32_t* orig, uint8_t* val, size_t n,
+                         cudaStream_t st) {
   if (n == 0) return;
-  intensity_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pts, val, n);
+  intensity_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pts, orig, val, n);
 }
 
-void launch_cull_compact(const float4* pts, uint32_t n, const ViewConst& vc, const float c0[3],
-                         const float margin[3], float4* out_pts, uint32_t* out_idx,
-                         uint32_t* counter, cudaStream_t st) {
+void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const ViewConst& vc,
+                         const float c0[3], const float margin[3], float4* out_pts,
+                         uint32_t* out_idx, uint32_t* counter, cudaStream_t st) {
   if (n == 0) return;
   CullConst cc;
   for (int i = 0; i < 3; i++) cc.c0[i] = c0[i];
   cc.mx = margin[0];
   cc.my = margin[1];
   cc.mz = margin[2];
-  cull_compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, n, vc, cc, out_pts, out_idx, counter);
+  cull_compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, orig, n, vc, cc, out_pts, out_idx,
+                                                       counter);
 }
 
 void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32_t* counter,

@@ -13,7 +13,7 @@ from orbslam2_nmi_b200.capi import Grid
 pytestmark = pytest.mark.gpu
 
 SCORE_RTOL = 1e-5  # north_star: "NMI scores must match within 1e-5 relative"
-HIST_VARIANTS = [0, 1, 2, 3]  # U16G/TMA, U16G/LDG, U32x2/TMA, U32x2/LDG
+HIST_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7]  # storage policy x TMA/LDG x 16/32 warps x swizzle (hist.cu)
 
 
 @pytest.fixture(scope="module")
