@@ -20,7 +20,7 @@ LIBDIR = ROOT / "orbslam2_nmi_b200" / "_lib"
 LIB = LIBDIR / "libnmi_b200.so"
 ORACLE_LIB = ROOT / "oracle" / "_build" / "libnmi_oracle.so"
 
-CU_SOURCES = ["capi.cu", "project.cu", "warp.cu", "hist.cu", "argmax.cu", "host_math.cpp", "driver.cpp"]
+CU_SOURCES = ["capi.cu", "project.cu", "warp.cu", "hist.cu", "argmax.cu", "host_math.cpp", "driver.cpp", "compat.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -53,7 +53,7 @@ def _digest(paths) -> str:
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / s for s in CU_SOURCES]
-    deps = srcs + [CSRC / "nmi_internal.h", ROOT / "include" / "nmi_b200.h"]
+    deps = srcs + [CSRC / "nmi_internal.h", ROOT / "include" / "nmi_b200.h"] + sorted((ROOT / "include" / "compat").glob("*"))
     stamp = LIBDIR / "build.sha256"
     dig = _digest(deps)
     if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:

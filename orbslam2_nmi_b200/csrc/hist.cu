@@ -359,14 +359,19 @@ __device__ __forceinline__ void ldg_words(uint32_t (&dst)[NW], const uint8_t* p)
   }
 }
 
+// NWARPS consumer warps.  With 16 of them a 17th warp is the dedicated TMA producer; with 32
+// (the 1024-thread CTA limit) thread 0 doubles as producer: after releasing chunk k it waits
+// until every warp has released it and refills that stage with chunk k + kStages.
 template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ>
-__global__ void __launch_bounds__(NWARPS * 32 + 32, 1) joint_hist_score_kernel(const HistArgs a) {
+__global__ void __launch_bounds__(NWARPS == 32 ? 1024 : NWARPS * 32 + 32, 1)
+joint_hist_score_kernel(const HistArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int BINS = POLICY == P_B64 ? 64 : 256;
   constexpr int NPASS = POLICY == P_U32X2 ? 2 : 1;
   constexpr int kConsumers = NWARPS * 32;
-  constexpr int kThreads = kConsumers + 32;
+  constexpr bool INLINE_PRODUCER = NWARPS == 32;
+  constexpr int kThreads = INLINE_PRODUCER ? kConsumers : kConsumers + 32;
   constexpr int PIX = kChunk / kConsumers;  // pixels per thread and chunk: 16 or 8
   constexpr int NW = PIX / 4;
 
@@ -398,22 +403,28 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, 1) joint_hist_score_kernel(c
   }
   __syncthreads();
 
-  if (warp == NWARPS) {
+  auto issue_chunk = [&](int k) {  // one elected thread: both images of chunk k -> stage k % kStages
+    const int st = k % kStages;
+    const int ck = k % nchunks;
+    const uint32_t off = (uint32_t)ck * kChunk;
+    uint32_t bytes = npix - off;
+    bytes = bytes > (uint32_t)kChunk ? (uint32_t)kChunk : ((bytes + 15u) & ~15u);
+    mbar_expect_tx(&sm.full[st], 2 * bytes);
+    tma_load_1d(sm.rbuf[st], rimg + off, bytes, &sm.full[st]);
+    tma_load_1d(sm.wbuf[st], wimg + off, bytes, &sm.full[st]);
+  };
+
+  if (!INLINE_PRODUCER && warp == NWARPS) {
     // ===== producer warp: TMA ring =====
     if (USE_TMA && lane == 0) {
       for (int k = 0; k < total; k++) {
-        const int st = k % kStages;
-        if (k >= kStages) mbar_wait(&sm.empty[st], ((k / kStages) - 1) & 1);
-        const int ck = k % nchunks;
-        const uint32_t off = (uint32_t)ck * kChunk;
-        uint32_t bytes = npix - off;
-        bytes = bytes > (uint32_t)kChunk ? (uint32_t)kChunk : ((bytes + 15u) & ~15u);
-        mbar_expect_tx(&sm.full[st], 2 * bytes);
-        tma_load_1d(sm.rbuf[st], rimg + off, bytes, &sm.full[st]);
-        tma_load_1d(sm.wbuf[st], wimg + off, bytes, &sm.full[st]);
+        if (k >= kStages) mbar_wait(&sm.empty[k % kStages], ((k / kStages) - 1) & 1);
+        issue_chunk(k);
       }
     }
   } else {
+    if (INLINE_PRODUCER && USE_TMA && tid == 0)
+      for (int k = 0; k < kStages && k < total; k++) issue_chunk(k);
     // ===== consumers =====
     uint32_t nr[NW], nw[NW];
 #pragma unroll
@@ -455,6 +466,10 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, 1) joint_hist_score_kernel(c
       if (USE_TMA) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[k % kStages]);
+        if (INLINE_PRODUCER && tid == 0 && k + kStages < total) {
+          mbar_wait(&sm.empty[k % kStages], (k / kStages) & 1);
+          issue_chunk(k + kStages);
+        }
       } else if (POLICY == P_U16G && (k & 1)) {
         asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // bound the in-flight pixels
       }
@@ -509,7 +524,7 @@ int launch_t(const HistArgs& a, cudaStream_t st) {
       return -1;
     configured = true;
   }
-  kern<<<a.npairs, NWARPS * 32 + 32, sizeof(Smem), st>>>(a);
+  kern<<<a.npairs, NWARPS == 32 ? 1024 : NWARPS * 32 + 32, sizeof(Smem), st>>>(a);
   return 1;
 }
 

@@ -20,7 +20,7 @@ print("variant $v $f", round(d["value"]), "evals/s", {k: round(x,3) for k,x in d
 PY
  done
 done
-V=${PROF_VARIANT:-4}
+V=${PROF_VARIANT:-0}
 python tools/profile_run.py $V > gpurun_out/prof_plain.log 2>&1 && \
 ncu --set full --import-source on --clock-control none -k regex:"joint_hist|project_splat|resolve" -s 3 -c 3 -f -o gpurun_out/prof_r1_v$V python tools/profile_run.py $V > gpurun_out/prof_ncu.log 2>&1
 tail -3 gpurun_out/prof_plain.log; tail -3 gpurun_out/prof_ncu.log
