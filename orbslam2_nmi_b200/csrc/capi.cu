@@ -223,7 +223,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   const int nvl = ve - vb, nwl = we - wb;
   const size_t npl = (size_t)nvl * nwl;
   REQUIRE(nvl <= kMaxViewsPerLaunch * 64, NMI_ERR_INVALID, "too many synthetic views");
-  REQUIRE(c->P / 16384 + 2 < 1024, NMI_ERR_INVALID, "image too large for the histogram kernel");
+  REQUIRE(c->P / 4096 + 2 < 2048, NMI_ERR_INVALID, "image too large for the histogram kernel");
 
   // ---- host parameter block: centres | minv | pairs | out_index ----
   const size_t off_c = 0;
@@ -679,7 +679,7 @@ int nmi_eval_pair(nmi_ctx* c, const void* warped_dev, unsigned int handle, int W
   REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags");
   REQUIRE(c->has_cam && W == c->cam.W && H == c->cam.H, NMI_ERR_INVALID, "size != camera size");
   REQUIRE(handle == 1 && c->one_render.p, NMI_ERR_STATE, "unknown render handle");
-  REQUIRE(c->P / 16384 + 2 < 1024, NMI_ERR_INVALID, "image too large for the histogram kernel");
+  REQUIRE(c->P / 4096 + 2 < 2048, NMI_ERR_INVALID, "image too large for the histogram kernel");
   CK(cudaSetDevice(c->device));
   const uint8_t* wp = static_cast<const uint8_t*>(warped_dev);
   const bool ours = c->warps.p && wp >= c->warps.p && wp < c->warps.p + c->warps.cap &&

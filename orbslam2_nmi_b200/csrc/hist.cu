@@ -23,15 +23,17 @@
 //
 // Histogram storage policies (template POLICY):
 //   P_U16G  256 bins, single pass. 65 536 counters, two 16-bit fields per 32-bit
-//           word (128 KiB).  Whenever an increment wraps the low 14 bits of its
-//           field (the running count crosses a multiple of 16 384) the thread
-//           that did it subtracts 16 384 again and logs a (bin, +16384) event;
-//           the epilogue adds the events back.  All updates are commutative
-//           adds, so the result is exact as long as a field never carries out,
-//           i.e. fewer than 3*16384 increments land between a thread's wrap and
-//           its fix-up.  The TMA ring bounds that: while one thread sits in chunk
-//           k every other warp stays within chunks k-2..k+2, <= 5*8192 = 40 960
-//           pixels (the LDG variant re-synchronises every two chunks instead).
+//           word (128 KiB).  Fields are plain counts; the top four bits of a field
+//           double as a "needs draining" flag.  Every thread ORs the values its
+//           atomics return (one LOP3 per two pixels) and looks at the flag bits once
+//           per chunk; whoever sees a field >= 4096 drains it with a CAS (subtracts
+//           the multiple of 4096, logs a (bin, multiple) event) and the epilogue adds
+//           the events back.  Exactness needs a field never to reach 2^16: after a
+//           field hits 4096 the next increment of that word observes it and its
+//           thread drains within its current chunk, during which the TMA ring lets
+//           the other warps process at most 2*kStages-1 = 7 chunks = 57 344 pixels:
+//           4096 + 1 + 57 344 < 65 536.  (The LDG variant re-synchronises every two
+//           chunks instead.)
 //   P_U32X2 256 bins, two passes over the pixels, 128 render rows x 256 u32 per
 //           pass (128 KiB); no overflow logic, twice the L2->SM traffic.
 //   P_B64   64 bins (value >> 2), 8 replicated 64x64 u32 sub-histograms.
@@ -41,8 +43,9 @@ namespace nmi {
 namespace {
 
 constexpr int kChunk = 8192;  // pixels per stage and image
-constexpr int kStages = 3;
-constexpr int kEvCap = 1024;
+constexpr int kStages = 4;
+constexpr int kEvCap = 2048;       // >= npix / 4096 drain events (npix <= 8.3M)
+constexpr uint32_t kFlagMask = 0xF000F000u;  // a field >= 4096 has one of these bits set
 constexpr int kHistWords = 32768;  // 128 KiB
 constexpr int kB64Copies = 8;
 
@@ -59,7 +62,7 @@ struct __align__(16) Smem {
   uint32_t HB[256];
   float sums[4];
   uint32_t ev_count;
-  uint16_t ev_list[kEvCap];
+  uint32_t ev_list[kEvCap];  // (bin << 16) | multiple of 4096 drained
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -132,28 +135,53 @@ __device__ __forceinline__ float finish_score(float sa, float sb, float sab, int
 }
 
 // ---- bin addressing ----------------------------------------------------------
-// t = (a << 8) | b.  U16G: word (t >> 1), 16-bit field (t & 1).  With SWZ the word's low
-// five bits are XORed with a's low five bits: the bank then depends on both images, so a
-// flat region in one of them no longer piles a whole warp onto one bank.
+// t = (a << 8) | b (upper bits of t may hold garbage).  U16G: word w = t >> 1 (15 bits),
+// field t & 1.  With SWZ the low 8 bits of w are XORed with a: the bank then depends on
+// both images, so a flat region in one of them no longer piles a warp onto one bank.
+// The map stays a bijection (a's upper 7 bits sit untouched in w's upper bits).
 template <bool SWZ>
 __device__ __forceinline__ uint32_t u16g_word(uint32_t t) {
   const uint32_t w = (t >> 1) & 0x7FFFu;
-  return SWZ ? (w ^ ((t >> 8) & 31u)) : w;
+  return SWZ ? (w ^ ((t >> 8) & 0xFFu)) : w;
 }
 template <bool SWZ>
-__device__ __forceinline__ void u16g_fixup(Smem& sm, uint32_t t) {
-  atomicSub(sm.hist + u16g_word<SWZ>(t), 0x4000u << ((t & 1u) << 4));
-  const uint32_t e = atomicAdd(&sm.ev_count, 1u);
-  if (e < kEvCap) sm.ev_list[e] = (uint16_t)t;
+__device__ __forceinline__ uint32_t u16g_bin_of_word(uint32_t w) {  // inverse, field 0
+  if (SWZ) {
+    const uint32_t a = ((w >> 7) & 0xFEu) | (((w >> 7) ^ (w >> 14)) & 1u);
+    w ^= a;
+  }
+  return w << 1;
+}
+// Drain every field of word w that has reached 4096 (exact, CAS based; rare path).
+template <bool SWZ>
+__device__ __noinline__ void u16g_drain(Smem& sm, uint32_t w) {
+  uint32_t* p = sm.hist + w;
+  for (;;) {
+    const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(p);
+    const uint32_t sub = cur & kFlagMask;  // multiples of 4096 held by the two fields
+    if (sub == 0) return;
+    if (atomicCAS(p, cur, cur - sub) == cur) {
+      const uint32_t bin = u16g_bin_of_word<SWZ>(w);
+      if (sub & 0xFFFFu) {
+        const uint32_t e = atomicAdd(&sm.ev_count, 1u);
+        if (e < kEvCap) sm.ev_list[e] = (bin << 16) | ((sub & 0xFFFFu) >> 12);
+      }
+      if (sub >> 16) {
+        const uint32_t e = atomicAdd(&sm.ev_count, 1u);
+        if (e < kEvCap) sm.ev_list[e] = ((bin | 1u) << 16) | (sub >> 28);
+      }
+      return;
+    }
+  }
 }
 
 // generic (branchy) per-pixel path: partial chunks and BG == false
 template <int POLICY, bool SWZ>
 __device__ __forceinline__ void accum_one(Smem& sm, uint32_t t, int pass, int warp) {
   if (POLICY == P_U16G) {
-    const uint32_t sh = (t & 1u) << 4;
-    const uint32_t old = atomicAdd(sm.hist + u16g_word<SWZ>(t), 1u << sh);
-    if (((old >> sh) & 0x3FFFu) == 0x3FFFu) u16g_fixup<SWZ>(sm, t);  // crossed a multiple of 16384
+    const uint32_t w = u16g_word<SWZ>(t);
+    const uint32_t old = atomicAdd(sm.hist + w, (t & 1u) * 0xFFFFu + 1u);
+    if (old & kFlagMask) u16g_drain<SWZ>(sm, w);
   } else if (POLICY == P_U32X2) {
     if ((int)(t >> 15) == pass) atomicAdd(sm.hist + (t & 0x7FFFu), 1u);
   } else {
@@ -181,19 +209,27 @@ __device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], c
                                            int pass, int warp) {
   constexpr int N = NW * 4;
   if (POLICY == P_U16G) {
-    uint32_t t[N], old[N];
+    // 16 (or 8) independent ATOMS in flight; the returned words are only ORed together.
+    // Integer work is split between the ALU pipe (PRMT, LOP3) and the FMA pipe (IMAD).
+    uint32_t w[N], old[N];
+    const uint32_t base = smem_u32(sm.hist);
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      t[i] = __byte_perm(ww[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);
-      old[i] = atomicAdd(sm.hist + u16g_word<SWZ>(t[i]), 1u << ((t[i] & 1u) << 4));
+      const uint32_t t = __byte_perm(ww[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);
+      uint32_t addr = (t * 2u) & 0x1FFFCu;  // byte offset of word t >> 1
+      if (SWZ) addr ^= __byte_perm(rw[i >> 2], 0u, 0x4440 + (i & 3)) * 4u;  // ^ (a << 2)
+      uint32_t inc;  // 1 or 0x10000; a real IMAD (FMA pipe), not the ISETP+SEL the compiler prefers
+      asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc) : "r"(t & 1u));
+      w[i] = addr;
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[i]) : "r"(base + addr), "r"(inc) : "memory");
     }
-    uint32_t flag = 0xFFFFFFFFu;  // becomes 0 iff some increment wrapped its field's low 14 bits
+    uint32_t acc = 0;
 #pragma unroll
-    for (int i = 0; i < N; i++) flag = min(flag, ~(old[i] >> ((t[i] & 1u) << 4)) & 0x3FFFu);
-    if (flag == 0) {
+    for (int i = 0; i < N; i++) acc |= old[i];
+    if (acc & kFlagMask) {
 #pragma unroll
       for (int i = 0; i < N; i++)
-        if ((~(old[i] >> ((t[i] & 1u) << 4)) & 0x3FFFu) == 0) u16g_fixup<SWZ>(sm, t[i] & 0xFFFFu);
+        if (old[i] & kFlagMask) u16g_drain<SWZ>(sm, w[i] >> 2);
     }
   } else if (POLICY == P_U32X2) {
     const uint32_t base = smem_u32(sm.hist);
@@ -232,21 +268,22 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
     for (int i = 0; i < 8; i++) col[i] = 0;
     for (int row = warp; row < 256; row += NWARPS) {
       uint32_t c[8];  // c[2k+h] = J[row][2(lane+32k)+h]
-      const int src = SWZ ? (lane ^ (row & 31)) : lane;  // undo the bank swizzle
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const uint32_t wv = sm.hist[row * 128 + src + 32 * k];
+        // word of bins (row, 2(lane+32k)) / (row, 2(lane+32k)+1), bank swizzle undone
+        const uint32_t wv = sm.hist[u16g_word<SWZ>(((uint32_t)row << 8) | (2u * (lane + 32 * k)))];
         c[2 * k] = wv & 0xFFFFu;
         c[2 * k + 1] = wv >> 16;
       }
-      for (uint32_t e = 0; e < nev; e++) {  // logged +16384 events of this row
-        const uint32_t t = sm.ev_list[e];
+      for (uint32_t e = 0; e < nev; e++) {  // drained multiples of 4096 of this row
+        const uint32_t ev = sm.ev_list[e];
+        const uint32_t t = ev >> 16;
         if ((int)(t >> 8) == row) {
           const uint32_t b = t & 0xFFu;
           if (((b >> 1) & 31u) == (uint32_t)lane) {
 #pragma unroll
             for (int i = 0; i < 8; i++)
-              if ((uint32_t)i == (((b >> 6) << 1) | (b & 1u))) c[i] += 16384u;
+              if ((uint32_t)i == (((b >> 6) << 1) | (b & 1u))) c[i] += (ev & 0xFFFFu) << 12;
           }
         }
       }

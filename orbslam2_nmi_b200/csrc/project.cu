@@ -85,44 +85,23 @@ cull_compact_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__
   }
 }
 
-// Lane = view, warp = run of consecutive (Morton-ordered) survivors.
-// The 32 lanes of a warp project the SAME point into 32 different views, so one warp-level
-// atomic never carries two fragments for the same cell (different z-buffers), and since
-// consecutive points are spatial neighbours each lane keeps revisiting the same few lines
-// of its own view's z-buffer.
+// One thread per surviving point, looping over the views of the batch.
 __global__ void __launch_bounds__(256)
 project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ cidx,
                      const uint32_t* __restrict__ counter, const float4* __restrict__ centres,
                      int nviews, ViewConst vc, unsigned long long* __restrict__ zbuf, size_t P) {
-  constexpr int kRun = 32;  // points per warp task
+  extern __shared__ float4 s_c[];
+  for (int i = threadIdx.x; i < nviews; i += blockDim.x) s_c[i] = centres[i];
+  __syncthreads();
   const uint32_t count = *counter;
-  const int lane = threadIdx.x & 31;
-  const int ngroups = (nviews + 31) / 32;
-  const uint32_t nruns = (count + kRun - 1) / kRun;
-  const uint32_t ntasks = nruns * (uint32_t)ngroups;
-  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const float half = 0.5f * (float)(vc.s - 1);
-  for (uint32_t task = warp_global; task < ntasks; task += nwarps) {
-    const uint32_t run = task / ngroups;
-    const int v = (int)(task - run * ngroups) * 32 + lane;
-    const bool active = v < nviews;
-    const float4 c = active ? centres[v] : make_float4(0, 0, 0, 0);
-    unsigned long long* zb = zbuf + (size_t)(active ? v : 0) * P;
-    const uint32_t t0 = run * kRun;
-    const uint32_t t1 = min(t0 + kRun, count);
-    // each lane fetches one point of the run (coalesced), then they are broadcast one by one
-    const uint32_t mine = t0 + lane;
-    const float4 pl = mine < t1 ? cpts[mine] : make_float4(0, 0, 0, 0);
-    const uint32_t il = mine < t1 ? cidx[mine] : 0u;
-    for (uint32_t t = t0; t < t1; t++) {
-      const int src = (int)(t - t0);
-      const float px = __shfl_sync(0xffffffffu, pl.x, src);
-      const float py = __shfl_sync(0xffffffffu, pl.y, src);
-      const float pz = __shfl_sync(0xffffffffu, pl.z, src);
-      const unsigned long long lo = __shfl_sync(0xffffffffu, il, src);
-      if (!active) continue;
-      const float dx = __fsub_rn(px, c.x), dy = __fsub_rn(py, c.y), dz = __fsub_rn(pz, c.z);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count;
+       t += gridDim.x * blockDim.x) {
+    const float4 p = cpts[t];
+    const unsigned long long lo = cidx[t];
+    for (int v = 0; v < nviews; v++) {
+      const float4 c = s_c[v];
+      const float dx = __fsub_rn(p.x, c.x), dy = __fsub_rn(p.y, c.y), dz = __fsub_rn(p.z, c.z);
       const float Zc =
           __fmaf_rn(vc.r2[2], dz, __fmaf_rn(vc.r2[1], dy, __fmul_rn(vc.r2[0], dx)));
       if (!(Zc >= vc.zn && Zc <= vc.zf)) continue;
@@ -138,12 +117,13 @@ project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict
       const int i0 = (int)floorf(__fsub_rn(xw, half));
       const int j0 = (int)floorf(__fsub_rn(yr, half));
       const unsigned long long key = ((unsigned long long)__float_as_uint(Zc) << 32) | lo;
+      unsigned long long* zb = zbuf + (size_t)v * P;
       for (int j = j0; j < j0 + vc.s; j++) {
         if (j < 0 || j >= vc.H) continue;
         for (int ii = i0; ii < i0 + vc.s; ii++) {
           if (ii < 0 || ii >= vc.W) continue;
           unsigned long long* cell = zb + (size_t)j * vc.W + ii;
-          // early-z: a cell only ever decreases, so a stale (L1-cached) read is conservative
+          // early-z: the cell only ever decreases, so a stale read is conservative
           if (key < *cell) atomicMin(cell, key);
         }
       }
@@ -211,7 +191,8 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
                           const float4* centres, int nviews, const ViewConst& vc,
                           unsigned long long* zbuf, size_t P, cudaStream_t st) {
   if (nviews == 0) return;
-  project_splat_kernel<<<148 * 16, 256, 0, st>>>(cpts, cidx, counter, centres, nviews, vc, zbuf, P);
+  project_splat_kernel<<<148 * 16, 256, sizeof(float4) * nviews, st>>>(cpts, cidx, counter,
+                                                                      centres, nviews, vc, zbuf, P);
 }
 
 void launch_resolve(unsigned long long* zbuf, const uint8_t* val, int nviews, size_t P,

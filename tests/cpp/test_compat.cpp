@@ -1,0 +1,174 @@
+// test_compat.cpp -- exercises the reference-named C++ drop-ins (include/compat/) the way
+// src/Tracking.cc uses them.  Built and driven by tests/test_compat_cpp.py.
+//   test_compat host <yaml> <xyz> <offset>          host-only checks (no GPU)
+//   test_compat gpu  <yaml> <frame.raw> <twc.txt>    the reference's loop vs the batched call
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+
+#include "compat/helperFunctions.hpp"
+#include "compat/ioData.hpp"
+#include "compat/kernel.cuh"
+#include "compat/localization.hpp"
+
+#define EXPECT(c)                                                     \
+  do {                                                                \
+    if (!(c)) {                                                       \
+      std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c);         \
+      return 1;                                                       \
+    }                                                                 \
+  } while (0)
+
+static int host_checks(const char* yaml, const char* xyz, const char* off) {
+  // NmiSearchKernel (nmiSearchKernel.cpp)
+  NmiSearchKernel k(3, 3, 3, 3, 3, 3, 0.2f, 0.2f, 0.5f, 0.02f, 0.02f, 0.05f);
+  EXPECT(k.getNumSynthX() == 3 && k.getBestWarpZ() == -1 && k.getNmi() == 0);
+  k.setBest(1, 1, 1, 1, 1, 1, 0.5f);
+  EXPECT(k.isMiddle());
+  k.setBest(0, 1, 1, 1, 1, 2, 0.5f);
+  EXPECT(!k.isMiddle());
+  k.resizeKernel();  // sX and wZ on the periphery keep their step, the rest halve
+  EXPECT(k.stepX == 0.2f && k.stepY == 0.1f && k.stepZ == 0.25f);
+  EXPECT(k.stepRadX == 0.01f && k.stepRadY == 0.01f && k.stepRadZ == 0.05f);
+  NmiSearchKernel tiny(3, 3, 3, 3, 3, 3, 0.009f, 0.2f, 0.5f, 0.0019f, 0.02f, 0.05f);
+  tiny.setBest(1, 1, 1, 1, 1, 1, 0.1f);
+  tiny.resizeKernel();
+  EXPECT(tiny.numSynthX == 1 && tiny.numWarpX == 1 && tiny.numSynthY == 3);
+  NmiSearchKernel copy;
+  copy.setTo(&k);
+  EXPECT(copy.stepY == k.stepY && copy.bestWarpZ == 2 && copy.NMI == 0.5f);
+  copy.reset();
+  EXPECT(copy.numSynthX == -1 && copy.bestSynthX == -1 && copy.NMI == 0);
+
+  // find_max_elements (helperFunctions.cpp:50-103) on a 2x1x1 x 1x1x2 rating
+  NmiSearchKernel g(2, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0, 0);
+  float v[4] = {0.25f, 0.75f, 0.75f, 0.5f};
+  float* r0[1] = {&v[0]};
+  float* r1[1] = {&v[2]};
+  float** z0[1] = {r0};
+  float** z1[1] = {r1};
+  float*** x0[1] = {z0};
+  float*** x1[1] = {z1};
+  float**** y0[1] = {x0};
+  float**** y1[1] = {x1};
+  float***** wz[2] = {y0, y1};
+  auto m = helperFunctions::find_max_elements(wz, g);
+  EXPECT(m.size() == 2 && m[0].getBestSynthX() == 1 && m[0].getBestWarpZ() == 0 && m[0].getNmi() == 0.75f);
+  EXPECT(m[1].getBestSynthX() == 0 && m[1].getBestWarpZ() == 1);
+  v[0] = v[1] = v[2] = v[3] = -1.0f;  // nothing reaches 0: the reference's vector is empty
+  EXPECT(helperFunctions::find_max_elements(wz, g).empty());
+
+  // setupCam (ioData.cpp:177-197)
+  cv::Mat T = cv::Mat::eye(4, 4, CV_32F), K = cv::Mat::eye(3, 3, CV_64F);
+  T.at<float>(0, 3) = 1; T.at<float>(1, 3) = 2; T.at<float>(2, 3) = 3;
+  CameraSettings cs = setupCam(T, K);
+  EXPECT(cs.getPosition().x == 1 && cs.getDirection().z == 4 && cs.getUp().y == 1 && cs.getUp().x == 0);
+
+  // YAML reader on the reference-style settings file
+  nmi_compat::Yaml y(yaml);
+  EXPECT(y.ok());
+  EXPECT(y.num("NMI.SynthNumX") == 2 && y.num("NMI.WarpNumY") == 2);
+  EXPECT(std::fabs(y.num("NMI.SynthStepZ") - 0.5) < 1e-12 && std::fabs(y.num("Camera.fx") - 95.0) < 1e-12);
+  EXPECT(y.str("NMI.Render.Cloud") == xyz);
+  int rows = 0, cols = 0;
+  auto init1 = y.mat("NMI.Init1", &rows, &cols);
+  EXPECT(rows == 4 && cols == 4 && init1.size() == 16 && init1[15] == 1.0);
+
+  // loadXYZ (objloader.cpp:225-264): offset subtraction, /256, trailing-newline duplicate
+  std::vector<float> pts;
+  EXPECT(nmi_compat::loadXYZ(xyz, off, pts));
+  std::ifstream f(xyz);
+  size_t lines = 0;
+  std::string line;
+  while (std::getline(f, line))
+    if (!line.empty()) lines++;
+  EXPECT(pts.size() / 4 == lines + 1);  // last point pushed twice
+  const size_t n = pts.size() / 4;
+  EXPECT(pts[4 * (n - 1)] == pts[4 * (n - 2)] && pts[4 * (n - 1) + 3] == pts[4 * (n - 2) + 3]);
+  std::printf("HOST OK %zu points\n", n);
+  return 0;
+}
+
+static int gpu_checks(const char* yaml, const char* frame_raw, const char* twc_txt) {
+  NmiObjects objs(yaml);
+  Image* img = objs.myImage;
+  Rendering<nmi_prop_RENDER>* ren = objs.myRenderer;
+  const int W = ren->getImageWidth(), H = ren->getImageHeight();
+  cv::Mat gray(H, W, CV_8U);
+  {
+    std::ifstream f(frame_raw, std::ios::binary);
+    f.read(reinterpret_cast<char*>(gray.data), (std::streamsize)W * H);
+    if (!f) { std::printf("FAIL cannot read frame\n"); return 1; }
+  }
+  cv::Mat Twc(4, 4, CV_32F);
+  {
+    std::ifstream f(twc_txt);
+    for (int i = 0; i < 16; i++) f >> Twc.at<float>(i);
+  }
+  // ---- the reference's loop, verbatim in structure (src/Tracking.cc:1871-1905) ----
+  img->loadOriginal(gray.clone());
+  img->calculateWarping();
+  cv::Mat K = img->getK();
+  CameraSettings settings = setupCam(Twc, K);
+  ren->setCamera(settings.getPosition(), settings.getDirection(), settings.getUp());
+  for (int sX = 0; sX < ren->getNumSynthX(); sX++)
+    for (int sY = 0; sY < ren->getNumSynthY(); sY++)
+      for (int sZ = 0; sZ < ren->getNumSynthZ(); sZ++) {
+        ren->renderToTextureOnGPU(ren->calculateTranslation(sX, sY, sZ));
+        for (int wX = 0; wX < img->getNumWarpX(); wX++)
+          for (int wY = 0; wY < img->getNumWarpY(); wY++)
+            for (int wZ = 0; wZ < img->getNumWarpZ(); wZ++)
+              CUDAF::NMIWithCuda_noMask(
+                  (cv::cuda::PtrStep<unsigned char>*)img->getImageGPU(wZ, wY, wX).data, SUC, MATCHING_NMI,
+                  ren->getImageWidth(), ren->getImageHeight(), &(objs.rating[wZ][wY][wX][sZ][sY][sX]),
+                  ren->getrenderedTexture());
+      }
+  std::vector<NmiSearchKernel> ext = helperFunctions::find_max_elements(objs.rating, *objs.NmiKernel);
+  if (ext.empty()) { std::printf("FAIL no extreme element\n"); return 1; }
+  std::printf("LOOP");
+  for (int wz = 0; wz < img->getNumWarpZ(); wz++)
+    for (int wy = 0; wy < img->getNumWarpY(); wy++)
+      for (int wx = 0; wx < img->getNumWarpX(); wx++)
+        for (int sz = 0; sz < ren->getNumSynthZ(); sz++)
+          for (int sy = 0; sy < ren->getNumSynthY(); sy++)
+            for (int sx = 0; sx < ren->getNumSynthX(); sx++) std::printf(" %.9g", objs.rating[wz][wy][wx][sz][sy][sx]);
+  std::printf("\nLOOPBEST %d %d %d %d %d %d %.9g\n", ext[0].getBestSynthX(), ext[0].getBestSynthY(),
+              ext[0].getBestSynthZ(), ext[0].getBestWarpX(), ext[0].getBestWarpY(), ext[0].getBestWarpZ(),
+              ext[0].getNmi());
+  // ---- the batched drop-in for the same loop ----
+  cv::Mat newTwc = objs.searchGrid(Twc, gray);
+  std::printf("BATCH");
+  for (int wz = 0; wz < img->getNumWarpZ(); wz++)
+    for (int wy = 0; wy < img->getNumWarpY(); wy++)
+      for (int wx = 0; wx < img->getNumWarpX(); wx++)
+        for (int sz = 0; sz < ren->getNumSynthZ(); sz++)
+          for (int sy = 0; sy < ren->getNumSynthY(); sy++)
+            for (int sx = 0; sx < ren->getNumSynthX(); sx++) std::printf(" %.9g", objs.rating[wz][wy][wx][sz][sy][sx]);
+  NmiSearchKernel* nk = objs.NmiKernel;
+  std::printf("\nBATCHBEST %d %d %d %d %d %d %.9g\n", nk->bestSynthX, nk->bestSynthY, nk->bestSynthZ,
+              nk->bestWarpX, nk->bestWarpY, nk->bestWarpZ, nk->NMI);
+  std::printf("NEWTWC");
+  for (int i = 0; i < 16; i++) std::printf(" %.9g", newTwc.at<float>(i));
+  // ---- the multi-level driver ----
+  nmi_reloc_params prm{};
+  prm.threshold = objs.threshold();
+  prm.max_iterations = nmi_prop_MAX_ITERATION_COUNT;
+  nmi_reloc_result rr = objs.relocalize(Twc, gray, prm);
+  std::printf("\nRELOC %d %d %d %.9g %.9g", rr.relocalized, rr.failed, rr.iterations, rr.nmi, rr.last_nmi);
+  for (int i = 0; i < 16; i++) std::printf(" %.9g", rr.Twc[i]);
+  std::stringstream ss;
+  ss << *objs.NmiKernel;
+  std::printf("\nKERNEL %s\nGPU OK\n", ss.str().c_str());
+  nmi_compat::shutdown();
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc >= 5 && std::string(argv[1]) == "host") return host_checks(argv[2], argv[3], argv[4]);
+  if (argc >= 5 && std::string(argv[1]) == "gpu") return gpu_checks(argv[2], argv[3], argv[4]);
+  std::printf("usage: test_compat host|gpu ...\n");
+  return 2;
+}
