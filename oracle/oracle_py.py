@@ -29,6 +29,18 @@ class OrcGrid(C.Structure):
                 ("stepR", C.c_float * 3)]
 
 
+class OrcRelocParams(C.Structure):
+    _fields_ = [("threshold", C.c_float), ("max_iterations", C.c_int), ("dist", C.c_float * 3),
+                ("rot", C.c_float * 3)]
+
+
+class OrcRelocResult(C.Structure):
+    _fields_ = [("Twc", C.c_float * 16), ("relocalized", C.c_int), ("failed", C.c_int),
+                ("iterations", C.c_int), ("nmi", C.c_float), ("last_nmi", C.c_float),
+                ("final_grid", OrcGrid), ("best_s", C.c_int * 3), ("best_w", C.c_int * 3),
+                ("n_evals", C.c_int)]
+
+
 _lib = None
 
 
@@ -67,6 +79,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.orc_is_middle.argtypes = [C.POINTER(OrcGrid), P, P]
     lib.orc_is_middle.restype = C.c_int
     lib.orc_resize_grid.argtypes = [C.POINTER(OrcGrid), P, P]
+    lib.orc_grid_from_motion.argtypes = [C.POINTER(OrcGrid), P, P, C.c_int, C.POINTER(OrcGrid)]
+    lib.orc_relocalize_points.argtypes = [C.POINTER(OrcCamera), P, C.POINTER(OrcGrid), P, C.c_size_t, P,
+                                          C.c_int, C.c_int, C.c_int, C.POINTER(OrcRelocParams),
+                                          C.POINTER(OrcRelocResult), C.c_int]
+    lib.orc_relocalize_points.restype = C.c_int
     _lib = lib
     return lib
 
@@ -206,3 +223,23 @@ def resize_grid(g, s, w):
     w = np.asarray(w, dtype=np.int32)
     load().orc_resize_grid(C.byref(og), _p(s), _p(w))
     return og
+
+
+def grid_from_motion(initial, dist, rot, not_initialized=False):
+    out = OrcGrid()
+    d = np.asarray(dist, dtype=np.float32)
+    r = np.asarray(rot, dtype=np.float32)
+    load().orc_grid_from_motion(C.byref(grid(initial)), _p(d), _p(r), int(not_initialized), C.byref(out))
+    return out
+
+
+def relocalize_points(cam, Twc, g, xyzi, frame, threshold, max_iterations=4, dist=(0, 0, 0), rot=(0, 0, 0),
+                      bins=256, bg=True, mode=SUC, threads=0):
+    prm = OrcRelocParams(threshold, max_iterations, (C.c_float * 3)(*dist), (C.c_float * 3)(*rot))
+    out = OrcRelocResult()
+    T = _twc(Twc)
+    xyzi = np.ascontiguousarray(xyzi, dtype=np.float32)
+    frame = np.ascontiguousarray(frame, dtype=np.uint8)
+    rc = load().orc_relocalize_points(C.byref(camera(cam)), _p(T), C.byref(grid(g)), _p(xyzi), xyzi.shape[0],
+                                      _p(frame), bins, int(bg), mode, C.byref(prm), C.byref(out), threads)
+    return rc, out

@@ -3,8 +3,9 @@
 // One nmi_ctx owns a device, a stream and every scratch buffer; nothing is
 // allocated per evaluation (the reference allocates/frees 10 buffers and
 // registers a GL texture per evaluation, kernel.cu:52-113).  A grid search is
-// params-upload + 6 kernels on one stream, whatever the grid size:
-//   cull_compact -> project_splat -> resolve -> warp -> joint_hist_score -> argmax
+// params-upload + a handful of kernels on one stream:
+//   cull_compact -> (project_splat -> resolve) per L2-sized view group -> warp ->
+//   joint_hist_score -> argmax
 // No CPU fallback exists: without a usable CUDA device every entry point fails.
 #include <algorithm>
 #include <cmath>
@@ -280,7 +281,15 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   CK(c->warps.reserve((size_t)nwl * c->pitch));
   CK(c->scores.reserve(nP));
   CK(c->key.reserve(1));
-  if (int rc = ensure_zbuf(c, (size_t)nvl * c->P)) return rc;
+  // Views are rendered in groups whose z-buffers (8 B per pixel and view) fit in L2
+  // together (~64 MB of the 126 MB): the z-buffer is written, resolved and reset without
+  // ever being streamed through HBM, and only `group` views of it exist.
+  const size_t zb_view = c->P * sizeof(unsigned long long);
+  int group = (int)((64ull << 20) / (zb_view ? zb_view : 1));
+  if (group < 1) group = 1;
+  if (group > nvl) group = nvl;
+  if (group > kMaxViewsPerLaunch) group = kMaxViewsPerLaunch;
+  if (int rc = ensure_zbuf(c, (size_t)group * c->P)) return rc;
 
   c->launches = 0;
   if (c->timed) CK(cudaEventRecord(c->ev[0], c->stream));
@@ -292,24 +301,24 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   const uint32_t* d_index = reinterpret_cast<const uint32_t*>(c->params.p + off_i);
 
   memcpy(c->Twc, Twc, sizeof(float) * 16);
-  // project in batches of <= kMaxViewsPerLaunch views (centres live in shared memory)
-  for (int v0 = 0; v0 < nvl; v0 += kMaxViewsPerLaunch) {
-    const int nv = nvl - v0 < kMaxViewsPerLaunch ? nvl - v0 : kMaxViewsPerLaunch;
-    if (v0 == 0) {
-      CK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
-      const float c0[3] = {Twc[3], Twc[7], Twc[11]};
-      launch_cull_compact(c->pts.p, c->orig.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
-                          c->counter.p, c->stream);
-      c->launches++;
-      if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
-    }
-    launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres + v0, nv, vc,
-                         c->zbuf.p + (size_t)v0 * c->P, c->P, c->stream);
+  CK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
+  {
+    const float c0[3] = {Twc[3], Twc[7], Twc[11]};
+    launch_cull_compact(c->pts.p, c->orig.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
+                        c->counter.p, c->stream);
     c->launches++;
   }
+  if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
+  for (int v0 = 0; v0 < nvl; v0 += group) {
+    const int nv = nvl - v0 < group ? nvl - v0 : group;
+    launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres + v0, nv, vc, c->zbuf.p, c->P,
+                         c->stream);
+    launch_resolve(c->zbuf.p, c->val.p, nv, c->P, c->renders.p + (size_t)v0 * c->pitch, c->pitch,
+                   nullptr, c->stream);
+    c->launches += 2;
+  }
+  // stage events: [1] = project + resolve of all view groups (interleaved), [2] = 0
   if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
-  launch_resolve(c->zbuf.p, c->val.p, nvl, c->P, c->renders.p, c->pitch, nullptr, c->stream);
-  c->launches++;
   if (c->timed) CK(cudaEventRecord(c->ev[3], c->stream));
   launch_warp(c->frame.p, c->cam.W, c->cam.H, d_minv, nwl, c->warps.p, c->pitch, c->stream);
   c->launches++;

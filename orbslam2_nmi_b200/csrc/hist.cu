@@ -23,17 +23,17 @@
 //
 // Histogram storage policies (template POLICY):
 //   P_U16G  256 bins, single pass. 65 536 counters, two 16-bit fields per 32-bit
-//           word (128 KiB).  Fields are plain counts; the top four bits of a field
-//           double as a "needs draining" flag.  Every thread ORs the values its
-//           atomics return (one LOP3 per two pixels) and looks at the flag bits once
-//           per chunk; whoever sees a field >= 4096 drains it with a CAS (subtracts
-//           the multiple of 4096, logs a (bin, multiple) event) and the epilogue adds
-//           the events back.  Exactness needs a field never to reach 2^16: after a
-//           field hits 4096 the next increment of that word observes it and its
-//           thread drains within its current chunk, during which the TMA ring lets
-//           the other warps process at most 2*kStages-1 = 7 chunks = 57 344 pixels:
-//           4096 + 1 + 57 344 < 65 536.  (The LDG variant re-synchronises every two
-//           chunks instead.)
+//           word (128 KiB).  The increment that takes a field across a multiple of
+//           4096 ("crossing") is unique; its thread subtracts 4096 again and logs a
+//           (bin) event, and the epilogue adds 4096 per event back.  The hot loop
+//           does not test every pixel: it ORs the post-increment words of a chunk
+//           (one LOP3 per two pixels) and only when a bit >= 12 of either field shows
+//           up does it look for its own crossings.  All updates are commutative adds,
+//           so the counts are exact provided a field never reaches 2^16, i.e. at most
+//           15 crossings are pending at once.  A crossing is repaid before its thread
+//           leaves the chunk, and while a thread sits in one chunk the TMA ring lets
+//           the other warps process at most 2*kStages-1 = 7 chunks = 57 344 pixels
+//           < 15*4096.  (The LDG variant re-synchronises every two chunks instead.)
 //   P_U32X2 256 bins, two passes over the pixels, 128 render rows x 256 u32 per
 //           pass (128 KiB); no overflow logic, twice the L2->SM traffic.
 //   P_B64   64 bins (value >> 2), 8 replicated 64x64 u32 sub-histograms.
@@ -46,6 +46,7 @@ constexpr int kChunk = 8192;  // pixels per stage and image
 constexpr int kStages = 4;
 constexpr int kEvCap = 2048;       // >= npix / 4096 drain events (npix <= 8.3M)
 constexpr uint32_t kFlagMask = 0xF000F000u;  // a field >= 4096 has one of these bits set
+constexpr uint32_t kCross = 0x0FFFu;         // low 12 bits of a field: 0 right after a crossing
 constexpr int kHistWords = 32768;  // 128 KiB
 constexpr int kB64Copies = 8;
 
@@ -62,7 +63,7 @@ struct __align__(16) Smem {
   uint32_t HB[256];
   float sums[4];
   uint32_t ev_count;
-  uint32_t ev_list[kEvCap];  // (bin << 16) | multiple of 4096 drained
+  uint16_t ev_list[kEvCap];  // bin of every repaid crossing (+4096 each)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -144,34 +145,15 @@ __device__ __forceinline__ uint32_t u16g_word(uint32_t t) {
   const uint32_t w = (t >> 1) & 0x7FFFu;
   return SWZ ? (w ^ ((t >> 8) & 0xFFu)) : w;
 }
+// The thread whose increment made field (t & 1) of word w cross a multiple of 4096 repays
+// it.  `nw` is the word right after that increment.
 template <bool SWZ>
-__device__ __forceinline__ uint32_t u16g_bin_of_word(uint32_t w) {  // inverse, field 0
-  if (SWZ) {
-    const uint32_t a = ((w >> 7) & 0xFEu) | (((w >> 7) ^ (w >> 14)) & 1u);
-    w ^= a;
-  }
-  return w << 1;
-}
-// Drain every field of word w that has reached 4096 (exact, CAS based; rare path).
-template <bool SWZ>
-__device__ __noinline__ void u16g_drain(Smem& sm, uint32_t w) {
-  uint32_t* p = sm.hist + w;
-  for (;;) {
-    const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(p);
-    const uint32_t sub = cur & kFlagMask;  // multiples of 4096 held by the two fields
-    if (sub == 0) return;
-    if (atomicCAS(p, cur, cur - sub) == cur) {
-      const uint32_t bin = u16g_bin_of_word<SWZ>(w);
-      if (sub & 0xFFFFu) {
-        const uint32_t e = atomicAdd(&sm.ev_count, 1u);
-        if (e < kEvCap) sm.ev_list[e] = (bin << 16) | ((sub & 0xFFFFu) >> 12);
-      }
-      if (sub >> 16) {
-        const uint32_t e = atomicAdd(&sm.ev_count, 1u);
-        if (e < kEvCap) sm.ev_list[e] = ((bin | 1u) << 16) | (sub >> 28);
-      }
-      return;
-    }
+__device__ __forceinline__ void u16g_repay_if_crossed(Smem& sm, uint32_t t, uint32_t nw) {
+  const uint32_t sh = (t & 1u) << 4;
+  if (((nw >> sh) & kCross) == 0) {
+    atomicSub(sm.hist + u16g_word<SWZ>(t), 0x1000u << sh);
+    const uint32_t e = atomicAdd(&sm.ev_count, 1u);
+    if (e < kEvCap) sm.ev_list[e] = (uint16_t)t;
   }
 }
 
@@ -179,9 +161,9 @@ __device__ __noinline__ void u16g_drain(Smem& sm, uint32_t w) {
 template <int POLICY, bool SWZ>
 __device__ __forceinline__ void accum_one(Smem& sm, uint32_t t, int pass, int warp) {
   if (POLICY == P_U16G) {
-    const uint32_t w = u16g_word<SWZ>(t);
-    const uint32_t old = atomicAdd(sm.hist + w, (t & 1u) * 0xFFFFu + 1u);
-    if (old & kFlagMask) u16g_drain<SWZ>(sm, w);
+    const uint32_t inc = (t & 1u) ? 0x10000u : 1u;
+    const uint32_t old = atomicAdd(sm.hist + u16g_word<SWZ>(t), inc);
+    u16g_repay_if_crossed<SWZ>(sm, t, old + inc);
   } else if (POLICY == P_U32X2) {
     if ((int)(t >> 15) == pass) atomicAdd(sm.hist + (t & 0x7FFFu), 1u);
   } else {
@@ -211,7 +193,7 @@ __device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], c
   if (POLICY == P_U16G) {
     // 16 (or 8) independent ATOMS in flight; the returned words are only ORed together.
     // Integer work is split between the ALU pipe (PRMT, LOP3) and the FMA pipe (IMAD).
-    uint32_t w[N], old[N];
+    uint32_t tt[N], nw[N];
     const uint32_t base = smem_u32(sm.hist);
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -220,16 +202,17 @@ __device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], c
       if (SWZ) addr ^= __byte_perm(rw[i >> 2], 0u, 0x4440 + (i & 3)) * 4u;  // ^ (a << 2)
       uint32_t inc;  // 1 or 0x10000; a real IMAD (FMA pipe), not the ISETP+SEL the compiler prefers
       asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc) : "r"(t & 1u));
-      w[i] = addr;
-      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old[i]) : "r"(base + addr), "r"(inc) : "memory");
+      uint32_t old;
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(base + addr), "r"(inc) : "memory");
+      tt[i] = t;
+      nw[i] = old + inc;  // the word right after this thread's increment
     }
     uint32_t acc = 0;
 #pragma unroll
-    for (int i = 0; i < N; i++) acc |= old[i];
-    if (acc & kFlagMask) {
+    for (int i = 0; i < N; i++) acc |= nw[i];
+    if (acc & kFlagMask) {  // rare: some field of a touched word is >= 4096
 #pragma unroll
-      for (int i = 0; i < N; i++)
-        if (old[i] & kFlagMask) u16g_drain<SWZ>(sm, w[i] >> 2);
+      for (int i = 0; i < N; i++) u16g_repay_if_crossed<SWZ>(sm, tt[i] & 0xFFFFu, nw[i]);
     }
   } else if (POLICY == P_U32X2) {
     const uint32_t base = smem_u32(sm.hist);
@@ -275,15 +258,14 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
         c[2 * k] = wv & 0xFFFFu;
         c[2 * k + 1] = wv >> 16;
       }
-      for (uint32_t e = 0; e < nev; e++) {  // drained multiples of 4096 of this row
-        const uint32_t ev = sm.ev_list[e];
-        const uint32_t t = ev >> 16;
+      for (uint32_t e = 0; e < nev; e++) {  // repaid crossings of this row: +4096 each
+        const uint32_t t = sm.ev_list[e];
         if ((int)(t >> 8) == row) {
           const uint32_t b = t & 0xFFu;
           if (((b >> 1) & 31u) == (uint32_t)lane) {
 #pragma unroll
             for (int i = 0; i < 8; i++)
-              if ((uint32_t)i == (((b >> 6) << 1) | (b & 1u))) c[i] += (ev & 0xFFFFu) << 12;
+              if ((uint32_t)i == (((b >> 6) << 1) | (b & 1u))) c[i] += 4096u;
           }
         }
       }
@@ -577,10 +559,10 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
     case 2: return launch_t<P_U32X2, true, 16, false>(a, st);
     case 3: return launch_t<P_U32X2, false, 16, false>(a, st);
     case 4: return launch_t<P_U16G, true, 32, false>(a, st);
-    case 5: return launch_t<P_U16G, true, 16, true>(a, st);
+    case 5: return launch_t<P_U16G, true, 16, false>(a, st);
     case 6: return launch_t<P_U16G, true, 32, true>(a, st);
     case 7: return launch_t<P_U32X2, true, 32, false>(a, st);
-    default: return launch_t<P_U16G, true, 16, false>(a, st);
+    default: return launch_t<P_U16G, true, 16, true>(a, st);  // variant 0: TMA ring, bank swizzle
   }
 }
 

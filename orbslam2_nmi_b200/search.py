@@ -110,6 +110,17 @@ class NmiSearcher:
         self.lib.nmi_decode_key(C.byref(grid), C.c_uint64(key), C.byref(r))
         return _result(r)
 
+    def relocalize(self, Twc, grid: Grid, flags: Flags | None = None, threshold=0.1, max_iterations=4,
+                   dist=(0.0, 0.0, 0.0), rot=(0.0, 0.0, 0.0)):
+        """Tracking::RelocalizeWithNMIStrategy on a pose (csrc/driver.cpp)."""
+        Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
+        flags = flags or self.flags()
+        prm = capi.RelocParams(threshold, max_iterations, (C.c_float * 3)(*dist), (C.c_float * 3)(*rot))
+        out = capi.RelocResult()
+        check(self.lib.nmi_relocalize(self.h, ptr(Twc), C.byref(grid), C.byref(flags), C.byref(prm),
+                                      C.byref(out)))
+        return out
+
     # -- stage-level API (reference call granularity) ------------------------------
     def render_cell(self, Twc, grid: Grid, sx, sy, sz) -> int:
         Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
@@ -208,6 +219,14 @@ def grid_resize(grid: Grid, s, w) -> Grid:
     w = np.asarray(w, dtype=np.int32)
     capi.load().nmi_grid_resize(C.byref(g), ptr(s), ptr(w))
     return g
+
+
+def grid_from_motion(initial: Grid, dist, rot, not_initialized=False) -> Grid:
+    out = Grid()
+    d = np.asarray(dist, dtype=np.float32)
+    r = np.asarray(rot, dtype=np.float32)
+    capi.load().nmi_grid_from_motion(C.byref(initial), ptr(d), ptr(r), int(not_initialized), C.byref(out))
+    return out
 
 
 def decode_key(grid: Grid, key: int) -> SearchResult:

@@ -145,3 +145,20 @@ def test_key_roundtrip_and_order(nmi_lib, oracle):
     # low word 0 == "no winner"
     r = search.decode_key(g, 0)
     assert r.best_index == -1
+
+
+def test_grid_from_motion_matches_oracle(nmi_lib, oracle):
+    init = GRIDS[0]
+    cases = [((0, 0, 0), (0, 0, 0), False), ((0, 0, 0), (0, 0, 0), True),
+             ((1.0, 0.1, 4.0), (0.2, 0.01, 0.5), False), ((0.3, 3.0, 0.0), (0.04, 0.0, 0.06), True)]
+    for dist, rot, ni in cases:
+        a = search.grid_from_motion(init, dist, rot, ni)
+        b = oracle.grid_from_motion(init, dist, rot, ni)
+        assert list(a.nS) == list(b.nS) and list(a.nW) == list(b.nW)
+        assert list(a.stepT) == list(b.stepT) and list(a.stepR) == list(b.stepR)
+    # 2 % of the motion, axes under 5 mm / 1 mrad collapse (Tracking.cc:2004-2043)
+    g = search.grid_from_motion(init, (1.0, 0.1, 4.0), (0.2, 0.01, 0.5), False)
+    assert list(g.nS) == [3, 1, 3] and list(g.nW) == [3, 1, 3]
+    assert g.stepT[0] == np.float32(np.float32(1.0) * 0.02)
+    # NOT_INITIALIZED: 5x5x5 translations (Tracking.cc:2057)
+    assert list(search.grid_from_motion(init, (0, 0, 0), (0, 0, 0), True).nS) == [5, 5, 5]

@@ -273,3 +273,35 @@ def test_full_size_properties(searcher):
     g1 = Grid.make((2, 1, 1), (1, 1, 1), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
     res = searcher.search(sc.Twc, g1, want_scores=True)
     assert res.best_index == 1 and res.scores[1] == pytest.approx(1.0, abs=1e-6)
+
+
+# ------------------------------------------------------------ multi-level driver ----
+@pytest.mark.parametrize("threshold,dist", [(0.05, (0, 0, 0)), (0.9, (0, 0, 0)), (0.3, (30.0, 0, 0))])
+def test_relocalize_matches_oracle_driver(searcher, oracle, threshold, dist):
+    """nmi_relocalize (csrc/driver.cpp) vs the oracle's restatement of
+    Tracking::RelocalizeWithNMIStrategy: same iterations, same accept/reject, same pose."""
+    sc = synth.make_scene("tiny")
+    g0 = Grid.make((3, 3, 1), (3, 1, 1), (0.4, 0.4, 0.5), (0.04, 0.02, 0.05))
+    # frame rendered one coarse cell away from the prior, so the search has something to find
+    t = oracle.cell_translation(sc.Twc, g0, 2, 0, 0)
+    _, img = oracle.render_points(sc, sc.Twc, t, sc.xyzi)
+    frame = synth.frame_from_render(img, seed=3)
+    searcher.set_scene(sc)
+    searcher.set_frame(frame)
+    got = searcher.relocalize(sc.Twc, g0, threshold=threshold, dist=dist)
+    rc, want = oracle.relocalize_points(sc, sc.Twc, g0, sc.xyzi, frame, threshold, dist=dist)
+    assert rc == 0
+    assert (got.iterations, got.relocalized, got.failed) == (want.iterations, want.relocalized, want.failed)
+    assert got.n_evals == want.n_evals
+    assert list(got.best_s) == list(want.best_s) and list(got.best_w) == list(want.best_w)
+    assert np.array_equal(np.array(got.Twc[:]), np.array(want.Twc[:]))
+    assert got.nmi == pytest.approx(want.nmi, rel=SCORE_RTOL)
+    assert list(got.final_grid.nS) == list(want.final_grid.nS)
+    assert list(got.final_grid.stepT) == list(want.final_grid.stepT)
+    assert list(got.final_grid.stepR) == list(want.final_grid.stepR)
+    if threshold < 0.5 and dist[0] == 0:
+        assert got.relocalized == 1 and got.iterations >= 2
+        moved = np.array(got.Twc[:]).reshape(4, 4)[:3, 3] - sc.Twc[:3, 3]
+        assert np.linalg.norm(moved - t) < 0.25  # ended near the planted offset
+    if threshold > 0.5:
+        assert got.failed == 1 and np.array_equal(np.array(got.Twc[:]).reshape(4, 4), sc.Twc)
