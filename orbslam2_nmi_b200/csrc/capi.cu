@@ -24,7 +24,7 @@ void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, co
                          uint32_t* out_idx, uint32_t* counter, cudaStream_t st);
 void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32_t* counter,
                           const float4* centres, int nviews, const ViewConst& vc,
-                          unsigned long long* zbuf, size_t P, cudaStream_t st);
+                          unsigned long long* zbuf, size_t P, uint32_t max_points, cudaStream_t st);
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -194,7 +194,7 @@ int render_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int n
   }
   if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
   launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->zbuf.p, c->P,
-                       c->stream);
+                       (uint32_t)c->n_pts, c->stream);
   c->launches++;
   if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
   launch_resolve(c->zbuf.p, c->val.p, nviews, c->P, images, c->pitch, winners, c->stream);
@@ -312,7 +312,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   for (int v0 = 0; v0 < nvl; v0 += group) {
     const int nv = nvl - v0 < group ? nvl - v0 : group;
     launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres + v0, nv, vc, c->zbuf.p, c->P,
-                         c->stream);
+                         (uint32_t)c->n_pts, c->stream);
     launch_resolve(c->zbuf.p, c->val.p, nv, c->P, c->renders.p + (size_t)v0 * c->pitch, c->pitch,
                    nullptr, c->stream);
     c->launches += 2;

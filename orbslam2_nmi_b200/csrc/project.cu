@@ -10,10 +10,13 @@
 //   cull_compact   one pass over the float4 cloud (coalesced 16 B loads): drops
 //                  points outside the union of all view frusta (conservative),
 //                  appends survivors {xyz, original index};
-//   project_splat  survivors x all views: fp32 projection, s x s splat, packed
-//                  (depth bits << 32 | point index) atomicMin into the per-view
-//                  z-buffer, with a plain-load early-z test in front;
+//   project_splat  runs of Morton-neighbouring survivors x the views of a group: fp32
+//                  projection, s x s splat resolved in a shared-memory tile, then one
+//                  packed (depth bits << 32 | point index) atomicMin per touched cell
+//                  into the per-view z-buffer, with a plain-load early-z test in front;
 //   resolve        z-buffer -> u8 render (background 255) and reset to ~0.
+#include <climits>
+
 #include "nmi_internal.h"
 
 namespace nmi {
@@ -85,49 +88,169 @@ cull_compact_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__
   }
 }
 
-// One thread per surviving point, looping over the views of the batch.
-__global__ void __launch_bounds__(256)
+// ---- project_splat: tile-binned splat -------------------------------------------------
+// One CTA = a run of kRun consecutive (Morton-ordered) survivors x the views of the group.
+// Neighbouring points land in a small image patch, so for each view the CTA
+//   1. projects its points (fp32, bit-identical to the oracle) and reduces their pixel
+//      bounding box,
+//   2. resolves all of the run's fragments inside a SHARED-MEMORY tile of that box with
+//      native 32-bit atomics: pass 1 atomicMin on the depth bits, pass 2 atomicMin on the
+//      original index among the fragments that hold the minimum depth (== the 64-bit
+//      packed-key minimum, split in two),
+//   3. flushes the touched cells to the global z-buffer with one early-z load + one packed
+//      64-bit atomicMin per CELL (coalesced row segments) instead of one per FRAGMENT.
+// A run whose box does not fit the tile falls back to per-fragment global atomics.
+constexpr int kSplatThreads = 256;
+constexpr int kPtsPerThread = 4;
+constexpr int kRun = kSplatThreads * kPtsPerThread;  // 1024 survivors per CTA
+constexpr int kTileCap = 8192;                       // cells of the shared-memory tile
+
+struct Frag {  // one projected point of one view
+  int i0, j0;
+  uint32_t zbits;  // 0xFFFFFFFF = clipped
+};
+
+__device__ __forceinline__ Frag project_point(const float4& p, const float4& c, const ViewConst& vc,
+                                              float half) {
+  Frag f;
+  f.i0 = f.j0 = 0;
+  f.zbits = 0xFFFFFFFFu;
+  const float dx = __fsub_rn(p.x, c.x), dy = __fsub_rn(p.y, c.y), dz = __fsub_rn(p.z, c.z);
+  const float Zc = __fmaf_rn(vc.r2[2], dz, __fmaf_rn(vc.r2[1], dy, __fmul_rn(vc.r2[0], dx)));
+  if (!(Zc >= vc.zn && Zc <= vc.zf)) return f;
+  const float Xc = __fmaf_rn(vc.r0[2], dz, __fmaf_rn(vc.r0[1], dy, __fmul_rn(vc.r0[0], dx)));
+  const float Yc = __fmaf_rn(vc.r1[2], dz, __fmaf_rn(vc.r1[1], dy, __fmul_rn(vc.r1[0], dx)));
+  const float nx = __fdiv_rn(__fmul_rn(vc.kx, Xc), Zc);
+  const float ny = __fdiv_rn(__fmul_rn(vc.ky, Yc), Zc);
+  if (!(fabsf(nx) <= 1.0f && fabsf(ny) <= 1.0f)) return f;
+  const float xw = __fmaf_rn(nx, vc.hw, vc.hw);
+  const float yr = __fmaf_rn(ny, vc.hh, vc.hh);
+  f.i0 = (int)floorf(__fsub_rn(xw, half));
+  f.j0 = (int)floorf(__fsub_rn(yr, half));
+  f.zbits = __float_as_uint(Zc);
+  return f;
+}
+
+__global__ void __launch_bounds__(kSplatThreads)
 project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ cidx,
                      const uint32_t* __restrict__ counter, const float4* __restrict__ centres,
                      int nviews, ViewConst vc, unsigned long long* __restrict__ zbuf, size_t P) {
-  extern __shared__ float4 s_c[];
-  for (int i = threadIdx.x; i < nviews; i += blockDim.x) s_c[i] = centres[i];
-  __syncthreads();
+  extern __shared__ uint32_t s_tile[];  // depth[kTileCap] | index[kTileCap]
+  uint32_t* s_depth = s_tile;
+  uint32_t* s_index = s_tile + kTileCap;
+  __shared__ int s_bb[4];  // xmin, xmax, ymin, ymax of the run's valid points (i0 / j0)
+
   const uint32_t count = *counter;
+  const uint32_t base = blockIdx.x * (uint32_t)kRun;
+  if (base >= count) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float half = 0.5f * (float)(vc.s - 1);
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count;
-       t += gridDim.x * blockDim.x) {
-    const float4 p = cpts[t];
-    const unsigned long long lo = cidx[t];
-    for (int v = 0; v < nviews; v++) {
-      const float4 c = s_c[v];
-      const float dx = __fsub_rn(p.x, c.x), dy = __fsub_rn(p.y, c.y), dz = __fsub_rn(p.z, c.z);
-      const float Zc =
-          __fmaf_rn(vc.r2[2], dz, __fmaf_rn(vc.r2[1], dy, __fmul_rn(vc.r2[0], dx)));
-      if (!(Zc >= vc.zn && Zc <= vc.zf)) continue;
-      const float Xc =
-          __fmaf_rn(vc.r0[2], dz, __fmaf_rn(vc.r0[1], dy, __fmul_rn(vc.r0[0], dx)));
-      const float Yc =
-          __fmaf_rn(vc.r1[2], dz, __fmaf_rn(vc.r1[1], dy, __fmul_rn(vc.r1[0], dx)));
-      const float nx = __fdiv_rn(__fmul_rn(vc.kx, Xc), Zc);
-      const float ny = __fdiv_rn(__fmul_rn(vc.ky, Yc), Zc);
-      if (!(fabsf(nx) <= 1.0f && fabsf(ny) <= 1.0f)) continue;
-      const float xw = __fmaf_rn(nx, vc.hw, vc.hw);
-      const float yr = __fmaf_rn(ny, vc.hh, vc.hh);
-      const int i0 = (int)floorf(__fsub_rn(xw, half));
-      const int j0 = (int)floorf(__fsub_rn(yr, half));
-      const unsigned long long key = ((unsigned long long)__float_as_uint(Zc) << 32) | lo;
-      unsigned long long* zb = zbuf + (size_t)v * P;
-      for (int j = j0; j < j0 + vc.s; j++) {
-        if (j < 0 || j >= vc.H) continue;
-        for (int ii = i0; ii < i0 + vc.s; ii++) {
-          if (ii < 0 || ii >= vc.W) continue;
-          unsigned long long* cell = zb + (size_t)j * vc.W + ii;
-          // early-z: the cell only ever decreases, so a stale read is conservative
-          if (key < *cell) atomicMin(cell, key);
+  const int S = vc.s;
+
+  float4 pt[kPtsPerThread];
+  uint32_t oi[kPtsPerThread];
+#pragma unroll
+  for (int k = 0; k < kPtsPerThread; k++) {
+    const uint32_t t = base + k * kSplatThreads + tid;
+    const bool in = t < count;
+    pt[k] = in ? cpts[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    oi[k] = in ? cidx[t] : 0xFFFFFFFFu;  // 0xFFFFFFFF marks a padding slot
+  }
+  if (tid == 0) { s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN; }
+  __syncthreads();
+
+  for (int v = 0; v < nviews; v++) {
+    const float4 c = centres[v];
+    unsigned long long* zb = zbuf + (size_t)v * P;
+    Frag f[kPtsPerThread];
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+#pragma unroll
+    for (int k = 0; k < kPtsPerThread; k++) {
+      f[k] = project_point(pt[k], c, vc, half);
+      if (oi[k] == 0xFFFFFFFFu) f[k].zbits = 0xFFFFFFFFu;
+      if (f[k].zbits != 0xFFFFFFFFu) {
+        xmin = min(xmin, f[k].i0); xmax = max(xmax, f[k].i0);
+        ymin = min(ymin, f[k].j0); ymax = max(ymax, f[k].j0);
+      }
+    }
+    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+    ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+    if (lane == 0 && xmin <= xmax) {
+      atomicMin(&s_bb[0], xmin); atomicMax(&s_bb[1], xmax);
+      atomicMin(&s_bb[2], ymin); atomicMax(&s_bb[3], ymax);
+    }
+    __syncthreads();  // (1) box complete
+    const int bx0 = s_bb[0], bx1 = s_bb[1], by0 = s_bb[2], by1 = s_bb[3];
+    if (bx0 > bx1) {  // nothing of this run is visible in this view (uniform)
+      __syncthreads();
+      continue;
+    }
+    const int x0 = max(bx0, 0), x1 = min(bx1 + S, vc.W);  // clipped cell box [x0,x1) x [y0,y1)
+    const int y0 = max(by0, 0), y1 = min(by1 + S, vc.H);
+    const int tw = x1 - x0, th = y1 - y0;
+    const bool tiled = tw > 0 && th > 0 && tw * th <= kTileCap;
+    if (tiled) {
+      const int ncell = tw * th;
+      for (int q = tid; q < ncell; q += kSplatThreads) { s_depth[q] = 0xFFFFFFFFu; s_index[q] = 0xFFFFFFFFu; }
+    }
+    __syncthreads();  // (2) tile cleared, everybody has read the box
+    if (tid == 0) { s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN; }
+    if (tiled) {
+      // pass 1: minimum depth per cell
+#pragma unroll
+      for (int k = 0; k < kPtsPerThread; k++) {
+        if (f[k].zbits == 0xFFFFFFFFu) continue;
+        for (int j = f[k].j0; j < f[k].j0 + S; j++) {
+          if (j < y0 || j >= y1) continue;
+          for (int i = f[k].i0; i < f[k].i0 + S; i++) {
+            if (i < x0 || i >= x1) continue;
+            atomicMin(&s_depth[(j - y0) * tw + (i - x0)], f[k].zbits);
+          }
+        }
+      }
+      __syncthreads();  // (3)
+      // pass 2: lowest original index among the fragments at the minimum depth
+#pragma unroll
+      for (int k = 0; k < kPtsPerThread; k++) {
+        if (f[k].zbits == 0xFFFFFFFFu) continue;
+        for (int j = f[k].j0; j < f[k].j0 + S; j++) {
+          if (j < y0 || j >= y1) continue;
+          for (int i = f[k].i0; i < f[k].i0 + S; i++) {
+            if (i < x0 || i >= x1) continue;
+            const int q = (j - y0) * tw + (i - x0);
+            if (s_depth[q] == f[k].zbits) atomicMin(&s_index[q], oi[k]);
+          }
+        }
+      }
+      __syncthreads();  // (4)
+      // flush: one early-z load + at most one 64-bit atomicMin per touched cell
+      for (int r = warp; r < th; r += kSplatThreads / 32) {
+        unsigned long long* row = zb + (size_t)(y0 + r) * vc.W + x0;
+        for (int x = lane; x < tw; x += 32) {
+          const uint32_t d = s_depth[r * tw + x];
+          if (d != 0xFFFFFFFFu) {
+            const unsigned long long key = ((unsigned long long)d << 32) | s_index[r * tw + x];
+            if (key < row[x]) atomicMin(row + x, key);
+          }
+        }
+      }
+    } else {
+      // box larger than the tile (Morton seam / degenerate view): per-fragment global path
+#pragma unroll
+      for (int k = 0; k < kPtsPerThread; k++) {
+        if (f[k].zbits == 0xFFFFFFFFu) continue;
+        const unsigned long long key = ((unsigned long long)f[k].zbits << 32) | oi[k];
+        for (int j = f[k].j0; j < f[k].j0 + S; j++) {
+          if (j < 0 || j >= vc.H) continue;
+          for (int i = f[k].i0; i < f[k].i0 + S; i++) {
+            if (i < 0 || i >= vc.W) continue;
+            unsigned long long* cell = zb + (size_t)j * vc.W + i;
+            if (key < *cell) atomicMin(cell, key);  // stale reads are conservative
+          }
         }
       }
     }
+    __syncthreads();  // (5) tile free again, s_bb reset visible
   }
 }
 
@@ -137,21 +260,31 @@ resolve_kernel(unsigned long long* __restrict__ zbuf, const uint8_t* __restrict_
   const int v = blockIdx.y;
   unsigned long long* zb = zbuf + (size_t)v * P;
   uint8_t* img = images + (size_t)v * pitch;
-  // 4 pixels per thread -> one 32-bit store of the render
-  size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  // 4 pixels per thread: two 16-byte key loads, two 16-byte resets, one 4-byte render store
+  const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (q >= P) return;
+  unsigned long long key[4];
+  const bool full = q + 3 < P && (((size_t)v * P + q) % 2 == 0);  // 16 B aligned quad
+  if (full) {
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(zb + q);
+    const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(zb + q + 2);
+    key[0] = a.x; key[1] = a.y; key[2] = b.x; key[3] = b.y;
+    const ulonglong2 ones = make_ulonglong2(~0ull, ~0ull);
+    *reinterpret_cast<ulonglong2*>(zb + q) = ones;
+    *reinterpret_cast<ulonglong2*>(zb + q + 2) = ones;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      key[k] = ~0ull;
+      if (q + k < P) { key[k] = zb[q + k]; zb[q + k] = ~0ull; }
+    }
+  }
   uint32_t packed = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    size_t p = q + k;
-    uint32_t pix = 0;
-    if (p < P) {
-      unsigned long long key = zb[p];
-      uint32_t w = key == ~0ull ? NMI_EMPTY : (uint32_t)(key & 0xFFFFFFFFull);
-      pix = w == NMI_EMPTY ? 255u : (uint32_t)__ldg(val + w);
-      if (winners) winners[(size_t)v * P + p] = w;
-      zb[p] = ~0ull;
-    }
+    const uint32_t w = key[k] == ~0ull ? NMI_EMPTY : (uint32_t)(key[k] & 0xFFFFFFFFull);
+    const uint32_t pix = w == NMI_EMPTY ? 255u : (uint32_t)__ldg(val + w);
+    if (winners && q + k < P) winners[(size_t)v * P + q + k] = w;
     packed |= pix << (8 * k);
   }
   if (q + 3 < P && (pitch % 4 == 0)) {
@@ -189,10 +322,19 @@ void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, co
 
 void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32_t* counter,
                           const float4* centres, int nviews, const ViewConst& vc,
-                          unsigned long long* zbuf, size_t P, cudaStream_t st) {
-  if (nviews == 0) return;
-  project_splat_kernel<<<148 * 16, 256, sizeof(float4) * nviews, st>>>(cpts, cidx, counter,
-                                                                      centres, nviews, vc, zbuf, P);
+                          unsigned long long* zbuf, size_t P, uint32_t max_points, cudaStream_t st) {
+  if (nviews == 0 || max_points == 0) return;
+  static bool configured = false;
+  const size_t smem = sizeof(uint32_t) * 2 * kTileCap;
+  if (!configured) {
+    cudaFuncSetAttribute(project_splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  // one CTA per run of kRun survivors; the survivor count lives on the device, so launch for
+  // the upper bound (all points) and let the surplus CTAs exit at once
+  const unsigned grid = (max_points + kRun - 1) / kRun;
+  project_splat_kernel<<<grid, kSplatThreads, smem, st>>>(cpts, cidx, counter, centres, nviews, vc,
+                                                          zbuf, P);
 }
 
 void launch_resolve(unsigned long long* zbuf, const uint8_t* val, int nviews, size_t P,
