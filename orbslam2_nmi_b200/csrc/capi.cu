@@ -21,7 +21,8 @@ namespace nmi {
 // project.cu (not in the header: only capi uses them)
 void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const ViewConst& vc,
                          const float c0[3], const float margin[3], float4* out_pts,
-                         uint32_t* out_idx, uint32_t* counter, cudaStream_t st);
+                         uint32_t* out_idx, uint32_t* counter, uint32_t* block_counts,
+                         cudaStream_t st);
 void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32_t* counter,
                           const float4* centres, int nviews, const ViewConst& vc,
                           unsigned long long* zbuf, size_t P, uint32_t max_points, cudaStream_t st);
@@ -94,6 +95,7 @@ struct nmi_ctx {
   DevBuf<float4> cpts;    // compacted survivors of the cull
   DevBuf<uint32_t> cidx;  // their original indices
   DevBuf<uint32_t> counter;
+  DevBuf<uint32_t> block_counts;  // per-CTA survivor counts / offsets of the stable compaction
 
   DevBuf<uint8_t> frame;
   uint8_t* h_frame = nullptr;  // pinned staging for host frames
@@ -186,11 +188,10 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int render_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nviews,
                  const float margin[3], bool recull, uint8_t* images, uint32_t* winners) {
   if (recull) {
-    CK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
     const float c0[3] = {c->Twc[3], c->Twc[7], c->Twc[11]};
     launch_cull_compact(c->pts.p, c->orig.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
-                        c->counter.p, c->stream);
-    c->launches++;
+                        c->counter.p, c->block_counts.p, c->stream);
+    c->launches += 3;
   }
   if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
   launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->zbuf.p, c->P,
@@ -301,12 +302,11 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   const uint32_t* d_index = reinterpret_cast<const uint32_t*>(c->params.p + off_i);
 
   memcpy(c->Twc, Twc, sizeof(float) * 16);
-  CK(cudaMemsetAsync(c->counter.p, 0, sizeof(uint32_t), c->stream));
   {
     const float c0[3] = {Twc[3], Twc[7], Twc[11]};
     launch_cull_compact(c->pts.p, c->orig.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
-                        c->counter.p, c->stream);
-    c->launches++;
+                        c->counter.p, c->block_counts.p, c->stream);
+    c->launches += 3;
   }
   if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
   for (int v0 = 0; v0 < nvl; v0 += group) {
@@ -393,7 +393,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->pts.release(); c->orig.release(); c->val.release(); c->cpts.release(); c->cidx.release(); c->counter.release();
+  c->pts.release(); c->orig.release(); c->val.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
   c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
@@ -486,6 +486,7 @@ int nmi_set_points(nmi_ctx* c, const float* xyzi, size_t n) {
   CK(c->val.reserve(n));
   CK(c->cpts.reserve(n));
   CK(c->cidx.reserve(n));
+  CK(c->block_counts.reserve((n + 255) / 256 + 1));
   CK(cudaMemcpyAsync(c->pts.p, sorted.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->orig.p, orig.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   launch_intensity_u8(c->pts.p, c->orig.p, c->val.p, n, c->stream);  // val[original index]

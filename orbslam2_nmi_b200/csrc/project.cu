@@ -7,9 +7,10 @@
 // round-to-nearest intrinsics so it is bit-identical to oracle/nmi_oracle.c.
 //
 // Three kernels:
-//   cull_compact   one pass over the float4 cloud (coalesced 16 B loads): drops
-//                  points outside the union of all view frusta (conservative),
-//                  appends survivors {xyz, original index};
+//   cull_*         two passes over the float4 cloud (coalesced 16 B loads): drop the
+//                  points outside the union of all view frusta (conservative) and
+//                  compact the survivors {xyz, original index} IN ORDER (count, scan,
+//                  scatter), so the Morton order of the cloud survives;
 //   project_splat  runs of Morton-neighbouring survivors x the views of a group: fp32
 //                  projection, s x s splat resolved in a shared-memory tile, then one
 //                  packed (depth bits << 32 | point index) atomicMin per touched cell
@@ -54,35 +55,91 @@ struct CullConst {
   float mx, my, mz;  // max |camera-frame offset| of any view in the batch
 };
 
-// Conservative frustum-union test, then warp-aggregated append.
-__global__ void __launch_bounds__(256)
-cull_compact_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ orig, uint32_t n,
-                    ViewConst vc, CullConst cc, float4* __restrict__ out_pts,
-                    uint32_t* __restrict__ out_idx, uint32_t* __restrict__ counter) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool keep = false;
+// Conservative frustum-union test (slack covers the fp32 rounding of the exact per-view test).
+__device__ __forceinline__ bool cull_keep(const float4& p, const ViewConst& vc, const CullConst& cc) {
+  const float dx = p.x - cc.c0[0], dy = p.y - cc.c0[1], dz = p.z - cc.c0[2];
+  const float X = vc.r0[0] * dx + vc.r0[1] * dy + vc.r0[2] * dz;
+  const float Y = vc.r1[0] * dx + vc.r1[1] * dy + vc.r1[2] * dz;
+  const float Z = vc.r2[0] * dx + vc.r2[1] * dy + vc.r2[2] * dz;
+  const float sl = 0.05f + 0.01f * (fabsf(X) + fabsf(Y) + fabsf(Z));  // 1 % + 5 cm
+  const float zmax = Z + cc.mz + sl;
+  return (Z >= vc.zn - cc.mz - sl) && (Z <= vc.zf + cc.mz + sl) &&
+         (vc.kx * (fabsf(X) - cc.mx - sl) <= zmax) && (vc.ky * (fabsf(Y) - cc.my - sl) <= zmax);
+}
+
+// Order-preserving (stable) compaction in three small kernels, so that the survivors keep
+// the Morton order of the cloud and a run of consecutive survivors stays a compact image
+// patch:  count per CTA -> exclusive scan of the CTA counts -> scatter.
+constexpr int kCullThreads = 256;
+
+__global__ void __launch_bounds__(kCullThreads)
+cull_count_kernel(const float4* __restrict__ pts, uint32_t n, ViewConst vc, CullConst cc,
+                  uint32_t* __restrict__ block_counts) {
+  const uint32_t i = blockIdx.x * kCullThreads + threadIdx.x;
+  const bool keep = i < n && cull_keep(ldg_stream(pts + i), vc, cc);
+  const int cnt = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
+}
+
+// single CTA: in-place exclusive scan of nblocks counts, total -> *counter
+__global__ void __launch_bounds__(1024)
+cull_scan_kernel(uint32_t* __restrict__ block_counts, uint32_t nblocks, uint32_t* __restrict__ counter) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nblocks; base += 1024) {
+    const uint32_t i = base + tid;
+    const uint32_t v = i < nblocks ? block_counts[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      s_warp[lane] = w;  // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    const uint32_t carry = s_carry;
+    const uint32_t incl = x + (warp ? s_warp[warp - 1] : 0u);
+    if (i < nblocks) block_counts[i] = carry + incl - v;  // exclusive
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *counter = s_carry;
+}
+
+__global__ void __launch_bounds__(kCullThreads)
+cull_scatter_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ orig, uint32_t n,
+                    ViewConst vc, CullConst cc, const uint32_t* __restrict__ block_offsets,
+                    float4* __restrict__ out_pts, uint32_t* __restrict__ out_idx) {
+  __shared__ uint32_t s_warp[kCullThreads / 32];
+  const uint32_t i = blockIdx.x * kCullThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 p = make_float4(0, 0, 0, 0);
+  bool keep = false;
   if (i < n) {
     p = ldg_stream(pts + i);
-    float dx = p.x - cc.c0[0], dy = p.y - cc.c0[1], dz = p.z - cc.c0[2];
-    float X = vc.r0[0] * dx + vc.r0[1] * dy + vc.r0[2] * dz;
-    float Y = vc.r1[0] * dx + vc.r1[1] * dy + vc.r1[2] * dz;
-    float Z = vc.r2[0] * dx + vc.r2[1] * dy + vc.r2[2] * dz;
-    // slack covers fp32 rounding of the exact per-view test (1 % + 5 cm)
-    float sl = 0.05f + 0.01f * (fabsf(X) + fabsf(Y) + fabsf(Z));
-    float zmax = Z + cc.mz + sl;
-    keep = (Z >= vc.zn - cc.mz - sl) && (Z <= vc.zf + cc.mz + sl) &&
-           (vc.kx * (fabsf(X) - cc.mx - sl) <= zmax) &&
-           (vc.ky * (fabsf(Y) - cc.my - sl) <= zmax);
+    keep = cull_keep(p, vc, cc);
   }
-  unsigned m = __ballot_sync(0xffffffffu, keep);
-  if (m == 0) return;
-  int lane = threadIdx.x & 31;
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) s_warp[warp] = (uint32_t)__popc(m);
+  __syncthreads();
+  uint32_t before = block_offsets[blockIdx.x];
+  for (int w = 0; w < warp; w++) before += s_warp[w];
   if (keep) {
-    uint32_t o = base + __popc(m & ((1u << lane) - 1u));
+    const uint32_t o = before + __popc(m & ((1u << lane) - 1u));
     out_pts[o] = p;
     out_idx[o] = orig[i];
   }
@@ -309,15 +366,19 @@ void launch_intensity_u8(const float4* pts, const uint32_t* orig, uint8_t* val, 
 
 void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const ViewConst& vc,
                          const float c0[3], const float margin[3], float4* out_pts,
-                         uint32_t* out_idx, uint32_t* counter, cudaStream_t st) {
+                         uint32_t* out_idx, uint32_t* counter, uint32_t* block_counts,
+                         cudaStream_t st) {
   if (n == 0) return;
   CullConst cc;
   for (int i = 0; i < 3; i++) cc.c0[i] = c0[i];
   cc.mx = margin[0];
   cc.my = margin[1];
   cc.mz = margin[2];
-  cull_compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(pts, orig, n, vc, cc, out_pts, out_idx,
-                                                       counter);
+  const uint32_t nblocks = (n + kCullThreads - 1) / kCullThreads;
+  cull_count_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, n, vc, cc, block_counts);
+  cull_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, counter);
+  cull_scatter_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, orig, n, vc, cc, block_counts, out_pts,
+                                                        out_idx);
 }
 
 void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32_t* counter,
