@@ -56,6 +56,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     P = C.c_void_p
     lib.orc_cell_translation.argtypes = [P, C.POINTER(OrcGrid), C.c_int, C.c_int, C.c_int, P]
     lib.orc_render_points.argtypes = [C.POINTER(OrcCamera), P, P, P, C.c_size_t, P, P]
+    lib.orc_render_mesh.argtypes = [C.POINTER(OrcCamera), P, P, P, C.c_size_t, P, C.c_size_t, P, P]
+    lib.orc_search_mesh.argtypes = [C.POINTER(OrcCamera), P, C.POINTER(OrcGrid), P, C.c_size_t, P, C.c_size_t,
+                                    P, C.c_int, C.c_int, C.c_int, P, P, P, C.c_int]
+    lib.orc_search_mesh.restype = C.c_int
     lib.orc_cell_angles.argtypes = [C.POINTER(OrcGrid), C.c_int, C.c_int, C.c_int, P]
     lib.orc_cell_homography_inv.argtypes = [C.POINTER(OrcCamera), C.POINTER(OrcGrid), C.c_int,
                                             C.c_int, C.c_int, P]
@@ -124,6 +128,36 @@ def render_points(cam, Twc, t, xyzi):
     xyzi = np.ascontiguousarray(xyzi, dtype=np.float32)
     load().orc_render_points(C.byref(camera(cam)), _p(T), _p(t), _p(xyzi), xyzi.shape[0], _p(win), _p(img))
     return win, img
+
+
+def render_mesh(cam, Twc, t, verts, tris):
+    W, H = cam.W, cam.H
+    win = np.empty((H, W), dtype=np.uint32)
+    img = np.empty((H, W), dtype=np.uint8)
+    T = _twc(Twc)
+    t = np.ascontiguousarray(t, dtype=np.float32)
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    tris = np.ascontiguousarray(tris, dtype=np.uint32)
+    load().orc_render_mesh(C.byref(camera(cam)), _p(T), _p(t), _p(verts), verts.shape[0], _p(tris),
+                           tris.shape[0], _p(win), _p(img))
+    return win, img
+
+
+def search_mesh(cam, Twc, g, verts, tris, frame, bins=256, bg=True, mode=SUC, keep_images=False, threads=0):
+    og = grid(g)
+    nS = g.nS[0] * g.nS[1] * g.nS[2]
+    nW = g.nW[0] * g.nW[1] * g.nW[2]
+    scores = np.zeros(nS * nW, dtype=np.float32)
+    renders = np.empty((nS, cam.H, cam.W), dtype=np.uint8) if keep_images else None
+    warps = np.empty((nW, cam.H, cam.W), dtype=np.uint8) if keep_images else None
+    T = _twc(Twc)
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    tris = np.ascontiguousarray(tris, dtype=np.uint32)
+    frame = np.ascontiguousarray(frame, dtype=np.uint8)
+    load().orc_search_mesh(C.byref(camera(cam)), _p(T), C.byref(og), _p(verts), verts.shape[0], _p(tris),
+                           tris.shape[0], _p(frame), bins, int(bg), mode, _p(scores), _p(renders), _p(warps),
+                           threads)
+    return scores, renders, warps
 
 
 def cell_homography_inv(cam, g, ix, iy, iz):

@@ -459,8 +459,11 @@ int nmi_set_points(nmi_ctx* c, const float* xyzi, size_t n) {
       if (v < lo[k]) lo[k] = v;
       if (v > hi[k]) hi[k] = v;
     }
+  // cubic cells (one scale for all axes): a thin axis only contributes its coarse bits
+  float ext = 0.0f;
+  for (int k = 0; k < 3; k++) ext = fmaxf(ext, hi[k] - lo[k]);
   float scale[3];
-  for (int k = 0; k < 3; k++) scale[k] = hi[k] > lo[k] ? 1023.0f / (hi[k] - lo[k]) : 0.0f;
+  for (int k = 0; k < 3; k++) scale[k] = ext > 0.0f ? 1023.0f / ext : 0.0f;
   std::vector<uint64_t> order(n);
 #pragma omp parallel for schedule(static)
   for (long long i = 0; i < (long long)n; i++) {

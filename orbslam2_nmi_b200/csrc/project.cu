@@ -156,11 +156,13 @@ cull_scatter_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__
 //      packed-key minimum, split in two),
 //   3. flushes the touched cells to the global z-buffer with one early-z load + one packed
 //      64-bit atomicMin per CELL (coalesced row segments) instead of one per FRAGMENT.
-// A run whose box does not fit the tile falls back to per-fragment global atomics.
+// A box larger than the tile is processed in horizontal strips; only a box needing more
+// than kMaxStrips strips falls back to per-fragment global atomics.
 constexpr int kSplatThreads = 256;
 constexpr int kPtsPerThread = 4;
 constexpr int kRun = kSplatThreads * kPtsPerThread;  // 1024 survivors per CTA
 constexpr int kTileCap = 8192;                       // cells of the shared-memory tile
+constexpr int kMaxStrips = 16;                       // box height / strip height before falling back
 
 struct Frag {  // one projected point of one view
   int i0, j0;
@@ -242,57 +244,56 @@ project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict
       __syncthreads();
       continue;
     }
-    const int x0 = max(bx0, 0), x1 = min(bx1 + S, vc.W);  // clipped cell box [x0,x1) x [y0,y1)
-    const int y0 = max(by0, 0), y1 = min(by1 + S, vc.H);
-    const int tw = x1 - x0, th = y1 - y0;
-    const bool tiled = tw > 0 && th > 0 && tw * th <= kTileCap;
-    if (tiled) {
-      const int ncell = tw * th;
-      for (int q = tid; q < ncell; q += kSplatThreads) { s_depth[q] = 0xFFFFFFFFu; s_index[q] = 0xFFFFFFFFu; }
-    }
-    __syncthreads();  // (2) tile cleared, everybody has read the box
+    const int x0 = max(bx0, 0), x1 = min(bx1 + S, vc.W);  // clipped cell box [x0,x1) x [Y0,Y1)
+    const int Y0 = max(by0, 0), Y1 = min(by1 + S, vc.H);
+    const int tw = x1 - x0, TH = Y1 - Y0;
+    // the box is processed in horizontal strips of at most kTileCap cells
+    const int strip_rows = tw > 0 ? kTileCap / tw : 0;
+    const int nstrips = (tw > 0 && TH > 0 && strip_rows > 0) ? (TH + strip_rows - 1) / strip_rows : 0;
+    const bool tiled = nstrips > 0 && nstrips <= kMaxStrips;
+    __syncthreads();  // (2) everybody has read the box
     if (tid == 0) { s_bb[0] = INT_MAX; s_bb[1] = INT_MIN; s_bb[2] = INT_MAX; s_bb[3] = INT_MIN; }
     if (tiled) {
-      // pass 1: minimum depth per cell
+      for (int sidx = 0; sidx < nstrips; sidx++) {
+        const int y0 = Y0 + sidx * strip_rows, y1 = min(y0 + strip_rows, Y1);
+        const int th = y1 - y0, ncell = tw * th;
+        for (int q = tid; q < ncell; q += kSplatThreads) { s_depth[q] = 0xFFFFFFFFu; s_index[q] = 0xFFFFFFFFu; }
+        __syncthreads();
+        // pass 1: minimum depth per cell
 #pragma unroll
-      for (int k = 0; k < kPtsPerThread; k++) {
-        if (f[k].zbits == 0xFFFFFFFFu) continue;
-        for (int j = f[k].j0; j < f[k].j0 + S; j++) {
-          if (j < y0 || j >= y1) continue;
-          for (int i = f[k].i0; i < f[k].i0 + S; i++) {
-            if (i < x0 || i >= x1) continue;
-            atomicMin(&s_depth[(j - y0) * tw + (i - x0)], f[k].zbits);
-          }
+        for (int k = 0; k < kPtsPerThread; k++) {
+          if (f[k].zbits == 0xFFFFFFFFu) continue;
+          for (int j = max(f[k].j0, y0); j < min(f[k].j0 + S, y1); j++)
+            for (int i = max(f[k].i0, x0); i < min(f[k].i0 + S, x1); i++)
+              atomicMin(&s_depth[(j - y0) * tw + (i - x0)], f[k].zbits);
         }
-      }
-      __syncthreads();  // (3)
-      // pass 2: lowest original index among the fragments at the minimum depth
+        __syncthreads();
+        // pass 2: lowest original index among the fragments at the minimum depth
 #pragma unroll
-      for (int k = 0; k < kPtsPerThread; k++) {
-        if (f[k].zbits == 0xFFFFFFFFu) continue;
-        for (int j = f[k].j0; j < f[k].j0 + S; j++) {
-          if (j < y0 || j >= y1) continue;
-          for (int i = f[k].i0; i < f[k].i0 + S; i++) {
-            if (i < x0 || i >= x1) continue;
-            const int q = (j - y0) * tw + (i - x0);
-            if (s_depth[q] == f[k].zbits) atomicMin(&s_index[q], oi[k]);
+        for (int k = 0; k < kPtsPerThread; k++) {
+          if (f[k].zbits == 0xFFFFFFFFu) continue;
+          for (int j = max(f[k].j0, y0); j < min(f[k].j0 + S, y1); j++)
+            for (int i = max(f[k].i0, x0); i < min(f[k].i0 + S, x1); i++) {
+              const int q = (j - y0) * tw + (i - x0);
+              if (s_depth[q] == f[k].zbits) atomicMin(&s_index[q], oi[k]);
+            }
+        }
+        __syncthreads();
+        // flush: one early-z load + at most one 64-bit atomicMin per touched cell
+        for (int r = warp; r < th; r += kSplatThreads / 32) {
+          unsigned long long* row = zb + (size_t)(y0 + r) * vc.W + x0;
+          for (int x = lane; x < tw; x += 32) {
+            const uint32_t d = s_depth[r * tw + x];
+            if (d != 0xFFFFFFFFu) {
+              const unsigned long long key = ((unsigned long long)d << 32) | s_index[r * tw + x];
+              if (key < row[x]) atomicMin(row + x, key);
+            }
           }
         }
-      }
-      __syncthreads();  // (4)
-      // flush: one early-z load + at most one 64-bit atomicMin per touched cell
-      for (int r = warp; r < th; r += kSplatThreads / 32) {
-        unsigned long long* row = zb + (size_t)(y0 + r) * vc.W + x0;
-        for (int x = lane; x < tw; x += 32) {
-          const uint32_t d = s_depth[r * tw + x];
-          if (d != 0xFFFFFFFFu) {
-            const unsigned long long key = ((unsigned long long)d << 32) | s_index[r * tw + x];
-            if (key < row[x]) atomicMin(row + x, key);
-          }
-        }
+        __syncthreads();  // strip done: the tile may be cleared again
       }
     } else {
-      // box larger than the tile (Morton seam / degenerate view): per-fragment global path
+      // box far larger than the tile (degenerate view): per-fragment global path
 #pragma unroll
       for (int k = 0; k < kPtsPerThread; k++) {
         if (f[k].zbits == 0xFFFFFFFFu) continue;

@@ -59,6 +59,30 @@ def make_cloud(n: int, seed: int = 1234, extent: float = 40.0) -> np.ndarray:
     return out
 
 
+def make_mesh(nx: int = 1000, ny: int = 1000, seed: int = 1234, extent: float = 40.0):
+    """Regular (nx+1) x (ny+1) vertex grid over the same height field -> 2*nx*ny triangles
+    (1000 x 1000 -> 2 M triangles), per-vertex grey in [0, 254]/256.
+    Winding is chosen so the triangles face a camera above the terrain looking down."""
+    rng = np.random.default_rng(seed)
+    xs = np.linspace(-extent, extent, nx + 1)
+    ys = np.linspace(-extent, extent, ny + 1)
+    X, Y = np.meshgrid(xs, ys)  # (ny+1, nx+1)
+    Z = height(X, Y) + 0.05 * rng.standard_normal(X.shape)
+    V = 127.0 + 60.0 * np.sin(0.5 * X) + 50.0 * np.cos(0.37 * Y) + 15.0 * rng.standard_normal(X.shape)
+    V = np.clip(np.rint(V), 0, 254)
+    verts = np.stack([X, Y, Z, V / 256.0], axis=-1).reshape(-1, 4).astype(np.float32)
+    j, i = np.mgrid[0:ny, 0:nx]
+    v00 = (j * (nx + 1) + i).reshape(-1)
+    v10 = v00 + 1
+    v01 = v00 + (nx + 1)
+    v11 = v01 + 1
+    t1 = np.stack([v00, v10, v11], axis=-1)
+    t2 = np.stack([v00, v11, v01], axis=-1)
+    tris = np.concatenate([t1, t2], axis=0)
+    tris = np.stack([t1, t2], axis=1).reshape(-1, 3).astype(np.uint32)
+    return verts, tris
+
+
 def prior_pose(height_above: float = 15.0, tilt_deg: float = 10.0) -> np.ndarray:
     """Camera `height_above` m over the terrain (world z up), looking down, tilted about x."""
     # CV camera: x right, y down, z forward.  Looking straight down: z_cam = -z_world.

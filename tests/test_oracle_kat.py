@@ -381,3 +381,93 @@ def test_golden_fixtures(oracle):
     assert zlib.crc32(J.tobytes()) == data["joint_crc32_pair00"]
     assert np.allclose(scores, np.array(data["scores"], dtype=np.float32), rtol=1e-6, atol=1e-7)
     assert oracle.argmax(scores)[0] == data["argmax"]
+
+
+# --------------------------------------------------------------- mesh raster -----
+def _mesh_cam():
+    cam = _cam(W=64, H=48, f=64.0)
+    return cam, np.eye(4, dtype=np.float32), np.zeros(3, np.float32)
+
+
+def _px_to_xyz(cam, px, py, z):
+    """World point (camera at origin, identity pose) that lands on window position (px, py)."""
+    return [(px - cam.W / 2) * z / (cam.fx * (cam.W / 2) / cam.cx), (py - cam.H / 2) * z / (cam.fy * (cam.H / 2) / cam.cy), z]
+
+
+def test_mesh_front_face_and_cull(oracle):
+    cam, T, t0 = _mesh_cam()
+    z = 10.0
+    a, b, c = _px_to_xyz(cam, 10, 10, z), _px_to_xyz(cam, 40, 10, z), _px_to_xyz(cam, 10, 40, z)
+    verts = np.array([a + [0.25], b + [0.5], c + [0.75]], dtype=np.float32)
+    # GL front face = counter-clockwise with y up = clockwise on a top-down image
+    win_cw, img = oracle.render_mesh(cam, T, t0, verts, np.array([[0, 1, 2]], np.uint32))
+    win_ccw, _ = oracle.render_mesh(cam, T, t0, verts, np.array([[0, 2, 1]], np.uint32))
+    on_cw, on_ccw = (win_cw != oracle.EMPTY).sum(), (win_ccw != oracle.EMPTY).sum()
+    assert (on_cw == 0) != (on_ccw == 0)  # exactly one winding is culled (rendering.hpp:300)
+    win = win_cw if on_cw else win_ccw
+    # right triangle with 30 px legs: ~450 pixel centres
+    assert 400 < (win != oracle.EMPTY).sum() < 500
+    assert win[15, 15] == 0 and win[45, 5] == oracle.EMPTY
+
+
+def test_mesh_watertight_shared_edge(oracle):
+    """Two triangles sharing an edge cover every pixel of the quad exactly once (top-left rule):
+    the union has no hole, and swapping the draw order changes no pixel's coverage."""
+    cam, T, t0 = _mesh_cam()
+    z = 12.0
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        x0, y0 = rng.uniform(5, 20, 2)
+        x1, y1 = x0 + rng.uniform(8, 30), y0 + rng.uniform(8, 20)
+        q = [_px_to_xyz(cam, x0, y0, z), _px_to_xyz(cam, x1, y0, z), _px_to_xyz(cam, x1, y1, z),
+             _px_to_xyz(cam, x0, y1, z)]
+        verts = np.array([p + [0.5] for p in q], dtype=np.float32)
+        for tris in ([[0, 2, 1], [0, 3, 2]], [[0, 1, 2], [0, 2, 3]]):
+            win, _ = oracle.render_mesh(cam, T, t0, verts, np.array(tris, np.uint32))
+            if (win != oracle.EMPTY).any():
+                break
+        cover = win != oracle.EMPTY
+        # pixel centres strictly inside the rectangle are all covered, exactly the snapped box
+        ys, xs = np.nonzero(cover)
+        assert cover[ys.min():ys.max() + 1, xs.min():xs.max() + 1].all()  # no hole along the diagonal
+        sx0, sx1 = np.rint(x0 * 256), np.rint(x1 * 256)
+        want_cols = [i for i in range(cam.W) if sx0 <= i * 256 + 128 < sx1]
+        assert xs.min() == want_cols[0] and xs.max() == want_cols[-1]  # left edge in, right edge out
+        both = np.array(tris, np.uint32)
+        w_ab, _ = oracle.render_mesh(cam, T, t0, verts, both)
+        w_ba, _ = oracle.render_mesh(cam, T, t0, verts, both[::-1].copy())
+        assert np.array_equal(w_ab != oracle.EMPTY, w_ba != oracle.EMPTY)
+        # each pixel belongs to exactly one triangle: drawing order only renames the winner
+        assert np.array_equal(np.where(w_ab == oracle.EMPTY, 9, 1 - w_ab), np.where(w_ba == oracle.EMPTY, 9, w_ba))
+
+
+def test_mesh_depth_ties_and_clip(oracle):
+    cam, T, t0 = _mesh_cam()
+
+    def tri(z, grey):
+        return [_px_to_xyz(cam, 10, 10, z) + [grey], _px_to_xyz(cam, 10, 40, z) + [grey],
+                _px_to_xyz(cam, 40, 10, z) + [grey]]
+
+    verts = np.array(tri(12.0, 0.1) + tri(8.0, 0.2) + tri(8.0, 0.3) + tri(4.0, 0.4) + tri(31.0, 0.5), np.float32)
+    tris = np.arange(15, dtype=np.uint32).reshape(5, 3)
+    win, img = oracle.render_mesh(cam, T, t0, verts, tris)
+    if not (win != oracle.EMPTY).any():
+        tris = tris[:, [0, 2, 1]].copy()
+        win, img = oracle.render_mesh(cam, T, t0, verts, tris)
+    # nearer wins; equal depth -> lower triangle index; outside [zn, zf] dropped
+    assert set(np.unique(win)) == {1, oracle.EMPTY}
+    assert img[15, 15] == int(np.floor(255 * np.float32(0.2) + 0.5))
+    # a triangle with ONE vertex beyond the far plane is dropped entirely (our definition)
+    verts2 = np.array(tri(12.0, 0.1), np.float32)
+    verts2[2, :3] = _px_to_xyz(cam, 40, 10, 31.0)
+    w2, _ = oracle.render_mesh(cam, T, t0, verts2, tris[:1])
+    assert not (w2 != oracle.EMPTY).any()
+
+
+def test_mesh_synthetic_terrain_renders(oracle):
+    sc = synth.make_scene("tiny", n_points=10)
+    verts, tris = synth.make_mesh(120, 120, extent=24.0)
+    win, img = oracle.render_mesh(sc, sc.Twc, np.zeros(3, np.float32), verts, tris)
+    covered = (win != oracle.EMPTY).mean()
+    assert covered > 0.95  # the terrain fills the view from 15 m up
+    assert 20 < img[win != oracle.EMPTY].mean() < 235
