@@ -96,6 +96,13 @@ int nmi_set_camera(nmi_ctx *ctx, const nmi_camera *cam);
  * xyzi: n x {x, y, z, I}, I = red/256 as the reference stores it.            */
 int nmi_set_points(nmi_ctx *ctx, const float *xyzi_host, size_t n);
 int nmi_set_points_device(nmi_ctx *ctx, const void *xyzi_dev, size_t n);
+/* loadOBJ -> VBO upload of Rendering<1> (objloader.cpp:140-223,
+ * rendering.hpp:219-229).  verts: nv x {x, y, z, grey 0..1}; tris: nt x 3 vertex
+ * indices in draw order.  Shading is flat with the first vertex's grey (the
+ * reference's mip-mapped texture lookup is a documented deviation).
+ * Setting a mesh replaces a point cloud and vice versa.                        */
+int nmi_set_mesh(nmi_ctx *ctx, const float *verts_host, size_t nv,
+                 const uint32_t *tris_host, size_t nt);
 /* Image::loadOriginal (image.cpp:130-135): H2D upload of the grey frame.     */
 int nmi_set_frame(nmi_ctx *ctx, const uint8_t *gray_host, int W, int H);
 int nmi_set_frame_device(nmi_ctx *ctx, const void *gray_dev, int W, int H);

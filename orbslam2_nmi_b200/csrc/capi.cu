@@ -27,6 +27,16 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
                           const float4* centres, int nviews, const ViewConst& vc,
                           unsigned long long* zbuf, size_t P, uint32_t max_points, cudaStream_t st);
 
+// mesh.cu
+void launch_mesh_values(const float4* verts, const uint3* tris, const uint32_t* tri_orig, uint8_t* val,
+                        uint32_t nt, cudaStream_t st);
+void launch_mesh_cull(const float4* verts, const uint3* tris, uint32_t nt, const ViewConst& vc,
+                      const float c0[3], const float margin[3], uint32_t* slots, uint32_t* counter,
+                      uint32_t* block_counts, cudaStream_t st);
+void launch_mesh_raster(const float4* verts, const uint3* tris, const uint32_t* tri_orig,
+                        const uint32_t* slots, const uint32_t* counter, const float4* centres, int nviews,
+                        const ViewConst& vc, unsigned long long* zbuf, size_t P, cudaStream_t st);
+
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 
@@ -90,12 +100,20 @@ struct nmi_ctx {
 
   DevBuf<float4> pts;
   DevBuf<uint32_t> orig;  // original index of every (Morton-ordered) point
+  DevBuf<uint32_t> tag;   // tie-break word of the z-buffer key: orig, or orig << 8 | value
+  bool packed_value = false;  // model has < 2^24 primitives: the key carries the value
   DevBuf<uint8_t> val;    // u8 intensity, indexed by ORIGINAL index
   size_t n_pts = 0;
   DevBuf<float4> cpts;    // compacted survivors of the cull
   DevBuf<uint32_t> cidx;  // their original indices
   DevBuf<uint32_t> counter;
   DevBuf<uint32_t> block_counts;  // per-CTA survivor counts / offsets of the stable compaction
+
+  // mesh model (Rendering<1>): Morton-ordered triangles + their original (draw-order) index
+  DevBuf<float4> mverts;
+  DevBuf<uint3> mtris;
+  DevBuf<uint32_t> mtri_orig, mslots;
+  size_t n_tris = 0;  // > 0: the model is a mesh, else a point cloud
 
   DevBuf<uint8_t> frame;
   uint8_t* h_frame = nullptr;  // pinned staging for host frames
@@ -184,24 +202,44 @@ bool valid_flags(const nmi_flags* f) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Cull the model against the union of the view frusta (order-preserving compaction).
+int cull_model(nmi_ctx* c, const ViewConst& vc, const float Twc[16], const float margin[3]) {
+  const float c0[3] = {Twc[3], Twc[7], Twc[11]};
+  if (c->n_tris) {
+    launch_mesh_cull(c->mverts.p, c->mtris.p, (uint32_t)c->n_tris, vc, c0, margin, c->mslots.p,
+                     c->counter.p, c->block_counts.p, c->stream);
+  } else {
+    launch_cull_compact(c->pts.p, c->tag.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
+                        c->counter.p, c->block_counts.p, c->stream);
+  }
+  c->launches += 3;
+  CK(cudaGetLastError());
+  return NMI_OK;
+}
+
+// z-buffer the culled model into `nviews` views (z-buffer views [0, nviews)) and resolve them.
+int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nviews, uint8_t* images,
+               uint32_t* winners) {
+  if (c->n_tris) {
+    launch_mesh_raster(c->mverts.p, c->mtris.p, c->mtri_orig.p, c->mslots.p, c->counter.p, d_centres,
+                       nviews, vc, c->zbuf.p, c->P, c->stream);
+  } else {
+    launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->zbuf.p, c->P,
+                         (uint32_t)c->n_pts, c->stream);
+  }
+  launch_resolve(c->zbuf.p, c->val.p, nviews, c->P, images, c->pitch, winners, c->packed_value,
+                 c->stream);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  return NMI_OK;
+}
+
 // Render `nviews` cells whose centres sit at d_centres into images[0..nviews).
 int render_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nviews,
                  const float margin[3], bool recull, uint8_t* images, uint32_t* winners) {
-  if (recull) {
-    const float c0[3] = {c->Twc[3], c->Twc[7], c->Twc[11]};
-    launch_cull_compact(c->pts.p, c->orig.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
-                        c->counter.p, c->block_counts.p, c->stream);
-    c->launches += 3;
-  }
-  if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
-  launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->zbuf.p, c->P,
-                       (uint32_t)c->n_pts, c->stream);
-  c->launches++;
-  if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
-  launch_resolve(c->zbuf.p, c->val.p, nviews, c->P, images, c->pitch, winners, c->stream);
-  c->launches++;
-  CK(cudaGetLastError());
-  return NMI_OK;
+  if (recull)
+    if (int rc = cull_model(c, vc, c->Twc, margin)) return rc;
+  return draw_views(c, vc, d_centres, nviews, images, winners);
 }
 
 int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_flags* f, int rank,
@@ -209,7 +247,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   REQUIRE(c && Twc, NMI_ERR_INVALID, "null ctx / Twc");
   REQUIRE(valid_grid(g), NMI_ERR_INVALID, "invalid grid (counts must be 1..4096, nP <= 2^26)");
   REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags (bins 256|64, score 0|1, variant 0..7)");
-  REQUIRE(c->has_cam && c->n_pts > 0 && c->has_frame, NMI_ERR_STATE,
+  REQUIRE(c->has_cam && (c->n_pts > 0 || c->n_tris > 0) && c->has_frame, NMI_ERR_STATE,
           "camera, model and frame must be set before a search");
   CK(cudaSetDevice(c->device));
 
@@ -302,20 +340,12 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   const uint32_t* d_index = reinterpret_cast<const uint32_t*>(c->params.p + off_i);
 
   memcpy(c->Twc, Twc, sizeof(float) * 16);
-  {
-    const float c0[3] = {Twc[3], Twc[7], Twc[11]};
-    launch_cull_compact(c->pts.p, c->orig.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
-                        c->counter.p, c->block_counts.p, c->stream);
-    c->launches += 3;
-  }
+  if (int rc = cull_model(c, vc, Twc, margin)) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
   for (int v0 = 0; v0 < nvl; v0 += group) {
     const int nv = nvl - v0 < group ? nvl - v0 : group;
-    launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres + v0, nv, vc, c->zbuf.p, c->P,
-                         (uint32_t)c->n_pts, c->stream);
-    launch_resolve(c->zbuf.p, c->val.p, nv, c->P, c->renders.p + (size_t)v0 * c->pitch, c->pitch,
-                   nullptr, c->stream);
-    c->launches += 2;
+    if (int rc = draw_views(c, vc, d_centres + v0, nv, c->renders.p + (size_t)v0 * c->pitch, nullptr))
+      return rc;
   }
   // stage events: [1] = project + resolve of all view groups (interleaved), [2] = 0
   if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
@@ -393,7 +423,8 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->pts.release(); c->orig.release(); c->val.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
+  c->pts.release(); c->orig.release(); c->tag.release(); c->val.release(); c->mverts.release(); c->mtris.release();
+  c->mtri_orig.release(); c->mslots.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
   c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
@@ -492,10 +523,71 @@ int nmi_set_points(nmi_ctx* c, const float* xyzi, size_t n) {
   CK(c->block_counts.reserve((n + 255) / 256 + 1));
   CK(cudaMemcpyAsync(c->pts.p, sorted.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->orig.p, orig.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  launch_intensity_u8(c->pts.p, c->orig.p, c->val.p, n, c->stream);  // val[original index]
+  CK(c->tag.reserve(n));
+  c->packed_value = n < (1u << 24);
+  launch_intensity_u8(c->pts.p, c->orig.p, c->val.p, c->tag.p, c->packed_value, n, c->stream);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   c->n_pts = n;
+  c->n_tris = 0;
+  c->has_search = false;
+  return NMI_OK;
+}
+
+int nmi_set_mesh(nmi_ctx* c, const float* verts, size_t nv, const uint32_t* tris, size_t nt) {
+  REQUIRE(c && verts && tris && nv > 0 && nt > 0 && nv < 0xFFFFFFFFull && nt < 0xFFFFFFFFull,
+          NMI_ERR_INVALID, "bad mesh");
+  for (size_t i = 0; i < 3 * nt; i++) REQUIRE(tris[i] < nv, NMI_ERR_INVALID, "triangle index out of range");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  // Morton order of the triangle centroids (load-time): neighbouring threads raster neighbouring
+  // pixels.  The ORIGINAL triangle index is the z-buffer key's tie-break (GL draw order).
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (size_t i = 0; i < nv; i++)
+    for (int k = 0; k < 3; k++) {
+      const float v = verts[4 * i + k];
+      if (v < lo[k]) lo[k] = v;
+      if (v > hi[k]) hi[k] = v;
+    }
+  float ext = 0.0f;
+  for (int k = 0; k < 3; k++) ext = fmaxf(ext, hi[k] - lo[k]);
+  const float scale = ext > 0.0f ? 1023.0f / ext : 0.0f;
+  std::vector<uint64_t> order(nt);
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)nt; i++) {
+    uint32_t q[3];
+    for (int k = 0; k < 3; k++) {
+      const float g = (verts[4 * (size_t)tris[3 * i] + k] + verts[4 * (size_t)tris[3 * i + 1] + k] +
+                       verts[4 * (size_t)tris[3 * i + 2] + k]) * (1.0f / 3.0f);
+      const float f = (g - lo[k]) * scale;
+      q[k] = f >= 0.0f ? (f < 1023.0f ? (uint32_t)f : 1023u) : 0u;
+    }
+    const uint64_t m = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+    order[i] = (m << 32) | (uint64_t)i;
+  }
+  std::sort(order.begin(), order.end());
+  std::vector<uint32_t> sorted(3 * nt), orig(nt);
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)nt; i++) {
+    const uint32_t src = (uint32_t)(order[i] & 0xFFFFFFFFu);
+    orig[i] = src;
+    for (int k = 0; k < 3; k++) sorted[3 * i + k] = tris[3 * (size_t)src + k];
+  }
+  CK(c->mverts.reserve(nv));
+  CK(c->mtris.reserve(nt));
+  CK(c->mtri_orig.reserve(nt));
+  CK(c->mslots.reserve(nt));
+  CK(c->val.reserve(nt));
+  CK(c->block_counts.reserve((nt + 255) / 256 + 1));
+  CK(cudaMemcpyAsync(c->mverts.p, verts, nv * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->mtris.p, sorted.data(), nt * sizeof(uint3), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->mtri_orig.p, orig.data(), nt * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  launch_mesh_values(c->mverts.p, c->mtris.p, c->mtri_orig.p, c->val.p, (uint32_t)nt, c->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  c->n_tris = nt;
+  c->packed_value = false;  // mesh keys carry the plain triangle index
+  c->n_pts = 0;
   c->has_search = false;
   return NMI_OK;
 }
@@ -577,7 +669,7 @@ int nmi_search_enqueue(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const
 
 int nmi_render_at(nmi_ctx* c, const float Twc[16], const float t[3], unsigned int* handle) {
   REQUIRE(c && Twc && t && handle, NMI_ERR_INVALID, "null argument");
-  REQUIRE(c->has_cam && c->n_pts > 0, NMI_ERR_STATE, "camera and model must be set");
+  REQUIRE(c->has_cam && (c->n_pts > 0 || c->n_tris > 0), NMI_ERR_STATE, "camera and model must be set");
   CK(cudaSetDevice(c->device));
   ViewConst vc;
   make_view_const(c->cam, Twc, &vc);

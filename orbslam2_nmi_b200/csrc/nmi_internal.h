@@ -25,11 +25,13 @@ inline size_t img_pitch(size_t P) { return (P + kImgAlign - 1) / kImgAlign * kIm
 
 // --- project.cu ------------------------------------------------------------
 void launch_fill_u64(unsigned long long* p, size_t n, unsigned long long v, cudaStream_t st);
-void launch_intensity_u8(const float4* pts, const uint32_t* orig, uint8_t* val, size_t n,
-                         cudaStream_t st);
+// val[orig[i]] = u8 intensity; tag[i] = orig[i] << 8 | value when `packed`, else orig[i]
+void launch_intensity_u8(const float4* pts, const uint32_t* orig, uint8_t* val, uint32_t* tag,
+                         bool packed, size_t n, cudaStream_t st);
 // z-buffer -> u8 image (+ optional winner indices); resets the z-buffer to ~0
 void launch_resolve(unsigned long long* zbuf, const uint8_t* val, int nviews, size_t P,
-                    uint8_t* images, size_t pitch, uint32_t* winners, cudaStream_t st);
+                    uint8_t* images, size_t pitch, uint32_t* winners, bool packed_value,
+                    cudaStream_t st);
 
 // --- warp.cu ---------------------------------------------------------------
 void launch_warp(const uint8_t* src, int W, int H, const float* minv /*nW x 9, device*/,

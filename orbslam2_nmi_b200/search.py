@@ -70,6 +70,12 @@ class NmiSearcher:
         assert xyzi.ndim == 2 and xyzi.shape[1] == 4
         check(self.lib.nmi_set_points(self.h, ptr(xyzi), xyzi.shape[0]))
 
+    def set_mesh(self, verts: np.ndarray, tris: np.ndarray):
+        verts = np.ascontiguousarray(verts, dtype=np.float32)
+        tris = np.ascontiguousarray(tris, dtype=np.uint32)
+        assert verts.ndim == 2 and verts.shape[1] == 4 and tris.ndim == 2 and tris.shape[1] == 3
+        check(self.lib.nmi_set_mesh(self.h, ptr(verts), verts.shape[0], ptr(tris), tris.shape[0]))
+
     def set_frame(self, gray: np.ndarray):
         gray = np.ascontiguousarray(gray, dtype=np.uint8)
         check(self.lib.nmi_set_frame(self.h, ptr(gray), gray.shape[1], gray.shape[0]))

@@ -305,3 +305,55 @@ def test_relocalize_matches_oracle_driver(searcher, oracle, threshold, dist):
         assert np.linalg.norm(moved - t) < 0.25  # ended near the planted offset
     if threshold > 0.5:
         assert got.failed == 1 and np.array_equal(np.array(got.Twc[:]).reshape(4, 4), sc.Twc)
+
+
+# ---------------------------------------------------------------- mesh model (C3) ----
+@pytest.mark.parametrize("bins", [256, 64])
+def test_mesh_search_matches_oracle(searcher, oracle, bins):
+    """Rendering<1> path: triangle raster with the A.4 rules, 64-bin mode as in BASELINE config 3."""
+    sc = synth.make_scene("tiny", n_points=10)
+    verts, tris = synth.make_mesh(150, 150, extent=24.0)
+    # make it less regular: a few big triangles, a back-facing patch, one beyond the far plane
+    extra_v = np.array([[-3, -3, 1.0, 0.3], [3, -3, 1.2, 0.6], [0, 4, 0.8, 0.9],
+                        [-2, -2, -40.0, 0.5], [2, -2, -40.0, 0.5], [0, 2, -40.0, 0.5]], dtype=np.float32)
+    n0 = verts.shape[0]
+    verts = np.vstack([verts, extra_v])
+    tris = np.vstack([tris, np.array([[n0, n0 + 1, n0 + 2], [n0, n0 + 2, n0 + 1], [n0 + 3, n0 + 4, n0 + 5]],
+                                     dtype=np.uint32)])
+    g = Grid.make((2, 2, 1), (2, 1, 2), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    frame = synth.frame_textured(sc.W, sc.H, seed=31)
+    searcher.set_camera(sc.W, sc.H, sc.fx, sc.fy, sc.cx, sc.cy, sc.zn, sc.zf, sc.point_size)
+    searcher.set_mesh(verts, tris)
+    searcher.set_frame(frame)
+    fl = searcher.flags(bins=bins)
+    res = searcher.search(sc.Twc, g, fl, want_scores=True)
+    scores, renders, warps = oracle.search_mesh(sc, sc.Twc, g, verts, tris, frame, bins=bins, keep_images=True)
+    for s in range(g.n_synth):
+        sx, sy, sz = s % 2, (s // 2) % 2, 0
+        t = oracle.cell_translation(sc.Twc, g, sx, sy, sz)
+        win, img = oracle.render_mesh(sc, sc.Twc, t, verts, tris)
+        assert (win != oracle.EMPTY).mean() > 0.9
+        assert np.array_equal(searcher.get_winners(s), win), f"mesh z-buffer winners differ, view {s}"
+        assert np.array_equal(searcher.get_render(s), img)
+    assert_scores_close(res.scores, scores)
+    assert res.best_index == oracle.argmax(scores)[0]
+    # switching back to a point cloud works
+    sc2 = synth.make_scene("tiny")
+    searcher.set_scene(sc2)
+    r2 = searcher.search(sc2.Twc, g, want_scores=True)
+    s2, _, _ = oracle.search_points(sc2, sc2.Twc, g, sc2.xyzi, frame)
+    assert_scores_close(r2.scores, s2)
+
+
+def test_large_cloud_uses_gather_path(searcher, oracle):
+    """>= 2^24 points: the key cannot carry the value, resolve gathers it (both paths exact)."""
+    sc = synth.make_scene("tiny", n_points=(1 << 24) + 1000)
+    g = Grid.make((2, 1, 1), (1, 1, 1), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    frame = synth.frame_textured(sc.W, sc.H, seed=2)
+    searcher.set_scene(sc)
+    searcher.set_frame(frame)
+    res = searcher.search(sc.Twc, g, want_scores=True)
+    t = oracle.cell_translation(sc.Twc, g, 1, 0, 0)
+    win, img = oracle.render_points(sc, sc.Twc, t, sc.xyzi)
+    assert np.array_equal(searcher.get_winners(1), win)
+    assert np.array_equal(searcher.get_render(1), img)
