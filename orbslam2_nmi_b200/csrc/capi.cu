@@ -27,6 +27,16 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
                           const float4* centres, int nviews, const ViewConst& vc,
                           unsigned long long* zbuf, size_t P, uint32_t max_points, cudaStream_t st);
 
+void launch_scan_counts(uint32_t* block_counts, uint32_t nblocks, uint32_t* counter, cudaStream_t st);
+void launch_bin_points(bool scatter, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
+                       const float4* centres, int nviews, const ViewConst& vc, uint32_t* counts,
+                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t* overflow,
+                       cudaStream_t st);
+int tiles_per_view(int W, int H);
+void launch_tile_resolve(const uint4* rec, const uint32_t* offsets, const uint32_t* total, int nviews,
+                         const ViewConst& vc, const uint8_t* val, bool packed, uint8_t* images,
+                         size_t pitch, uint32_t* winners, size_t P, cudaStream_t st);
+
 // mesh.cu
 void launch_mesh_values(const float4* verts, const uint3* tris, const uint32_t* tri_orig, uint8_t* val,
                         uint32_t nt, cudaStream_t st);
@@ -115,6 +125,11 @@ struct nmi_ctx {
   DevBuf<uint32_t> mtri_orig, mslots;
   size_t n_tris = 0;  // > 0: the model is a mesh, else a point cloud
 
+  // binned tile renderer scratch (point clouds)
+  DevBuf<uint32_t> bin_offsets, bin_cursor;  // [views of a group * tiles]
+  DevBuf<uint32_t> bin_total;                // [0] records of the group, [1] overflow flag
+  DevBuf<uint4> records;
+
   DevBuf<uint8_t> frame;
   uint8_t* h_frame = nullptr;  // pinned staging for host frames
   size_t h_frame_cap = 0;
@@ -183,6 +198,38 @@ int ensure_zbuf(nmi_ctx* c, size_t elems) {
   return NMI_OK;
 }
 
+int vc_point_size(const nmi_camera& cam) {
+  const int s = (int)lround(cam.point_size);
+  return s < 1 ? 1 : s;
+}
+
+// Record buffer of the tile renderer: one 16-byte record per (splat, tile).  A splat of
+// s <= 32 px touches at most 4 tiles but ~1.13 on average; the buffer is sized for
+// 1.5 records per (point, view) of a group and the group shrinks until that fits 2 GiB.
+// bin_scatter never writes past the buffer; an overflow raises a flag that every
+// synchronous entry point turns into an error (never a silently wrong render).
+int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
+  const size_t cap_records = (2ull << 30) / sizeof(uint4);
+  const size_t per_view = (size_t)((double)c->n_pts * 1.5) + 65536;
+  int g = (int)(cap_records / per_view);
+  if (g < 1) g = 1;
+  if (g > nviews) g = nviews;
+  if (g > kMaxViewsPerLaunch) g = kMaxViewsPerLaunch;
+  *group = g;
+  const size_t nbins = (size_t)g * tiles_per_view(c->cam.W, c->cam.H);
+  CK(c->bin_offsets.reserve(nbins));
+  CK(c->bin_cursor.reserve(nbins));
+  CK(c->bin_total.reserve(2));
+  size_t want = per_view * (size_t)g;
+  if (want > cap_records) want = cap_records;
+  if (want > c->records.cap) {
+    CK(cudaStreamSynchronize(c->stream));
+    CK(c->records.reserve(want));
+  }
+  CK(cudaMemsetAsync(c->bin_total.p, 0, 2 * sizeof(uint32_t), c->stream));
+  return NMI_OK;
+}
+
 bool valid_grid(const nmi_grid* g) {
   if (!g) return false;
   long np = 1;
@@ -220,6 +267,23 @@ int cull_model(nmi_ctx* c, const ViewConst& vc, const float Twc[16], const float
 // z-buffer the culled model into `nviews` views (z-buffer views [0, nviews)) and resolve them.
 int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nviews, uint8_t* images,
                uint32_t* winners) {
+  if (!c->n_tris && vc.s <= 32) {
+    // point cloud: binned tile renderer, no global z-buffer
+    const size_t nbins = (size_t)nviews * tiles_per_view(vc.W, vc.H);
+    CK(cudaMemsetAsync(c->bin_offsets.p, 0, nbins * sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(c->bin_cursor.p, 0, nbins * sizeof(uint32_t), c->stream));
+    launch_bin_points(false, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_offsets.p,
+                      nullptr, nullptr, 0, nullptr, c->stream);
+    launch_scan_counts(c->bin_offsets.p, (uint32_t)nbins, c->bin_total.p, c->stream);
+    launch_bin_points(true, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_cursor.p,
+                      c->bin_offsets.p, c->records.p, (uint32_t)c->records.cap, c->bin_total.p + 1,
+                      c->stream);
+    launch_tile_resolve(c->records.p, c->bin_offsets.p, c->bin_total.p, nviews, vc, c->val.p,
+                        c->packed_value, images, c->pitch, winners, c->P, c->stream);
+    c->launches += 4;
+    CK(cudaGetLastError());
+    return NMI_OK;
+  }
   if (c->n_tris) {
     launch_mesh_raster(c->mverts.p, c->mtris.p, c->mtri_orig.p, c->mslots.p, c->counter.p, d_centres,
                        nviews, vc, c->zbuf.p, c->P, c->stream);
@@ -328,7 +392,12 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   if (group < 1) group = 1;
   if (group > nvl) group = nvl;
   if (group > kMaxViewsPerLaunch) group = kMaxViewsPerLaunch;
-  if (int rc = ensure_zbuf(c, (size_t)group * c->P)) return rc;
+  const bool tiled = !c->n_tris && vc_point_size(c->cam) <= 32;
+  if (tiled) {
+    if (int rc = ensure_tile_buffers(c, nvl, &group)) return rc;
+  } else {
+    if (int rc = ensure_zbuf(c, (size_t)group * c->P)) return rc;
+  }
 
   c->launches = 0;
   if (c->timed) CK(cudaEventRecord(c->ev[0], c->stream));
@@ -424,7 +493,8 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->pts.release(); c->orig.release(); c->tag.release(); c->val.release(); c->mverts.release(); c->mtris.release();
-  c->mtri_orig.release(); c->mslots.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
+  c->mtri_orig.release(); c->mslots.release(); c->bin_offsets.release(); c->bin_cursor.release();
+  c->bin_total.release(); c->records.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
   c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
@@ -643,13 +713,17 @@ int nmi_search(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fla
   REQUIRE(out, NMI_ERR_INVALID, "null result");
   if (int rc = search_impl(c, Twc, g, f, 0, 1, nullptr, nullptr)) return rc;
   unsigned long long key = 0;
+  uint32_t tile_state[2] = {0, 0};
   CK(cudaMemcpyAsync(&key, c->key.p, sizeof key, cudaMemcpyDeviceToHost, c->stream));
+  if (c->bin_total.p)
+    CK(cudaMemcpyAsync(tile_state, c->bin_total.p, sizeof tile_state, cudaMemcpyDeviceToHost, c->stream));
   if (scores_host) {
     const size_t nP = (size_t)c->nvl * c->nwl;
     CK(cudaMemcpyAsync(scores_host, c->scores.p, nP * sizeof(float), cudaMemcpyDeviceToHost,
                        c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));
+  REQUIRE(tile_state[1] == 0, NMI_ERR_CUDA, "tile renderer record buffer overflow (model too dense for 2 GiB of records)");
   float ms = 0;
   if (c->timed) cudaEventElapsedTime(&ms, c->ev[0], c->ev[6]);
   const int rc = nmi_decode_key(g, key, out);
@@ -676,7 +750,12 @@ int nmi_render_at(nmi_ctx* c, const float Twc[16], const float t[3], unsigned in
   if (int rc = ensure_pinned(&c->h_params, &c->h_params_cap, 4096)) return rc;
   CK(c->params.reserve(4096));
   CK(c->one_render.reserve(c->pitch));
-  if (int rc = ensure_zbuf(c, c->P)) return rc;
+  if (!c->n_tris && vc.s <= 32) {
+    int g1 = 1;
+    if (int rc = ensure_tile_buffers(c, 1, &g1)) return rc;
+  } else {
+    if (int rc = ensure_zbuf(c, c->P)) return rc;
+  }
   CK(cudaStreamSynchronize(c->stream));
   float4 centre = make_float4(Twc[3] + t[0], Twc[7] + t[1], Twc[11] + t[2], 0.0f);
   memcpy(c->h_params, &centre, sizeof centre);

@@ -15,6 +15,9 @@
 //                  (depth bits << 32 | tie-break word) atomicMin into the per-view
 //                  z-buffer, with a plain-load early-z test in front;
 //   resolve        z-buffer -> u8 render (background 255) and reset to ~0.
+// Point clouds go through the binned TILE renderer further down (bin_count / scan /
+// bin_scatter / tile_resolve); the global z-buffer path above serves the mesh model and
+// oversized splats.
 #include <climits>
 
 #include "nmi_internal.h"
@@ -196,6 +199,148 @@ project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict
   }
 }
 
+// ---- binned tile renderer (point clouds) ---------------------------------------------------
+// The classic tiled rasteriser, exact by construction:
+//   bin_count    every (survivor, view) pair is projected (fp32, bit-identical to the oracle)
+//                and counted into the 32x32-pixel tiles its s x s splat touches;
+//   (scan)       exclusive scan of the [view][tile] counts -> record offsets;
+//   bin_scatter  same projection again, one 16-byte record {i0|j0, depth bits, tag} per
+//                (splat, tile) written at its slot;
+//   tile_resolve one CTA per (view, tile): the tile's z-buffer lives in SHARED memory
+//                (depth + tag words), every record's fragments are resolved there with
+//                native 32-bit atomics -- pass 1 min depth, pass 2 min tag among the
+//                fragments at the minimum depth (== the packed 64-bit key minimum) -- and
+//                the CTA, sole owner of the tile, stores the finished u8 pixels directly.
+// No global z-buffer, no global atomics on pixels, no separate resolve pass.
+constexpr int kTile = 32;
+constexpr int kTileCells = kTile * kTile;
+constexpr int kTileThreads = 128;
+
+struct Splat {
+  int i0, j0;
+  uint32_t zbits;
+  bool ok;
+};
+
+__device__ __forceinline__ Splat project_splat_point(const float4& p, const float4& c, const ViewConst& vc,
+                                                     float half) {
+  Splat f;
+  f.i0 = f.j0 = 0;
+  f.zbits = 0;
+  f.ok = false;
+  const float dx = __fsub_rn(p.x, c.x), dy = __fsub_rn(p.y, c.y), dz = __fsub_rn(p.z, c.z);
+  const float Zc = __fmaf_rn(vc.r2[2], dz, __fmaf_rn(vc.r2[1], dy, __fmul_rn(vc.r2[0], dx)));
+  if (!(Zc >= vc.zn && Zc <= vc.zf)) return f;
+  const float Xc = __fmaf_rn(vc.r0[2], dz, __fmaf_rn(vc.r0[1], dy, __fmul_rn(vc.r0[0], dx)));
+  const float Yc = __fmaf_rn(vc.r1[2], dz, __fmaf_rn(vc.r1[1], dy, __fmul_rn(vc.r1[0], dx)));
+  const float nx = __fdiv_rn(__fmul_rn(vc.kx, Xc), Zc);
+  const float ny = __fdiv_rn(__fmul_rn(vc.ky, Yc), Zc);
+  if (!(fabsf(nx) <= 1.0f && fabsf(ny) <= 1.0f)) return f;
+  const float xw = __fmaf_rn(nx, vc.hw, vc.hw);
+  const float yr = __fmaf_rn(ny, vc.hh, vc.hh);
+  f.i0 = (int)floorf(__fsub_rn(xw, half));
+  f.j0 = (int)floorf(__fsub_rn(yr, half));
+  f.zbits = __float_as_uint(Zc);
+  // the splat must touch the image at all
+  f.ok = f.i0 < vc.W && f.j0 < vc.H && f.i0 + vc.s > 0 && f.j0 + vc.s > 0;
+  return f;
+}
+
+// SCATTER == false: count records per (view, tile).  SCATTER == true: write them.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
+           const uint32_t* __restrict__ counter, const float4* __restrict__ centres, int nviews,
+           ViewConst vc, int ntx, int nt, uint32_t* __restrict__ counts,
+           const uint32_t* __restrict__ offsets, uint4* __restrict__ rec, uint32_t rec_cap,
+           uint32_t* __restrict__ overflow) {
+  extern __shared__ float4 s_c[];
+  for (int i = threadIdx.x; i < nviews; i += blockDim.x) s_c[i] = centres[i];
+  __syncthreads();
+  const uint32_t count = *counter;
+  const float half = 0.5f * (float)(vc.s - 1);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+    const float4 p = cpts[t];
+    const uint32_t tag = SCATTER ? ctag[t] : 0u;
+    for (int v = 0; v < nviews; v++) {
+      const Splat f = project_splat_point(p, s_c[v], vc, half);
+      if (!f.ok) continue;
+      const int tx0 = max(f.i0, 0) / kTile, tx1 = min(f.i0 + vc.s - 1, vc.W - 1) / kTile;
+      const int ty0 = max(f.j0, 0) / kTile, ty1 = min(f.j0 + vc.s - 1, vc.H - 1) / kTile;
+      for (int ty = ty0; ty <= ty1; ty++)
+        for (int tx = tx0; tx <= tx1; tx++) {
+          const uint32_t bin = (uint32_t)v * nt + ty * ntx + tx;
+          const uint32_t slot = atomicAdd(&counts[bin], 1u);
+          if (SCATTER) {
+            const uint32_t pos = offsets[bin] + slot;
+            if (pos < rec_cap)
+              rec[pos] = make_uint4((uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16), f.zbits, tag, 0u);
+            else
+              *overflow = 1u;
+          }
+        }
+    }
+  }
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(kTileThreads)
+tile_resolve_kernel(const uint4* __restrict__ rec, const uint32_t* __restrict__ offsets,
+                    const uint32_t* __restrict__ total, int ntx, int nt, int W, int H, int S,
+                    const uint8_t* __restrict__ val, uint8_t* __restrict__ images, size_t pitch,
+                    uint32_t* __restrict__ winners, size_t P) {
+  __shared__ uint32_t s_depth[kTileCells];
+  __shared__ uint32_t s_tag[kTileCells];
+  const uint32_t bin = blockIdx.x;
+  const int v = bin / nt, tile = bin - v * nt;
+  const int ty = tile / ntx, tx = tile - ty * ntx;
+  const int x0 = tx * kTile, y0 = ty * kTile;
+  const int tid = threadIdx.x;
+  const uint32_t start = offsets[bin];
+  const uint32_t end = bin + 1 < gridDim.x ? offsets[bin + 1] : *total;
+  for (int q = tid; q < kTileCells; q += kTileThreads) { s_depth[q] = 0xFFFFFFFFu; s_tag[q] = 0xFFFFFFFFu; }
+  __syncthreads();
+  // pass 1: minimum depth per cell
+  for (uint32_t r = start + tid; r < end; r += kTileThreads) {
+    const uint4 e = rec[r];
+    const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
+    for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
+      for (int i = max(li, 0); i < min(li + S, kTile); i++) atomicMin(&s_depth[j * kTile + i], e.y);
+  }
+  __syncthreads();
+  // pass 2: lowest tie-break word among the fragments at the minimum depth
+  for (uint32_t r = start + tid; r < end; r += kTileThreads) {
+    const uint4 e = rec[r];
+    const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
+    for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
+      for (int i = max(li, 0); i < min(li + S, kTile); i++)
+        if (s_depth[j * kTile + i] == e.y) atomicMin(&s_tag[j * kTile + i], e.z);
+  }
+  __syncthreads();
+  // the CTA owns the tile: plain stores of the finished pixels (8 per thread, one row segment)
+  uint8_t* img = images + (size_t)v * pitch;
+  const int row = tid >> 2, col = (tid & 3) * 8;
+  const int y = y0 + row;
+  if (y < H) {
+    unsigned long long packed = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t d = s_depth[row * kTile + col + k], tg = s_tag[row * kTile + col + k];
+      const bool empty = d == 0xFFFFFFFFu;
+      const uint32_t pix = empty ? 255u : (PACKED ? (tg & 0xFFu) : (uint32_t)__ldg(val + tg));
+      packed |= (unsigned long long)pix << (8 * k);
+      const int x = x0 + col + k;
+      if (winners && x < W) winners[(size_t)v * P + (size_t)y * W + x] = empty ? NMI_EMPTY : (PACKED ? tg >> 8 : tg);
+    }
+    const size_t o = (size_t)y * W + x0 + col;
+    if (x0 + col + 7 < W && ((reinterpret_cast<size_t>(img) + o) & 7) == 0) {
+      *reinterpret_cast<unsigned long long*>(img + o) = packed;
+    } else {
+      for (int k = 0; k < 8 && x0 + col + k < W; k++) img[o + k] = (uint8_t)(packed >> (8 * k));
+    }
+  }
+}
+
 // z-buffer -> u8 render (background 255, rendering.hpp:533) + reset to ~0.
 // PACKED: the key's low word is (original index << 8 | value): no gather is needed.
 template <bool PACKED>
@@ -271,6 +416,37 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
   if (nviews == 0 || max_points == 0) return;
   project_splat_kernel<<<148 * 16, 256, sizeof(float4) * nviews, st>>>(cpts, cidx, counter,
                                                                       centres, nviews, vc, zbuf, P);
+}
+
+// counts / offsets: [nviews * nt] (+ the scan's total in *total); rec: rec_cap records
+void launch_bin_points(bool scatter, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
+                       const float4* centres, int nviews, const ViewConst& vc, uint32_t* counts,
+                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t* overflow,
+                       cudaStream_t st) {
+  if (nviews == 0) return;
+  const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
+  if (scatter)
+    bin_kernel<true><<<148 * 16, 256, sizeof(float4) * nviews, st>>>(
+        cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts, offsets, rec, rec_cap, overflow);
+  else
+    bin_kernel<false><<<148 * 16, 256, sizeof(float4) * nviews, st>>>(
+        cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts, offsets, rec, rec_cap, overflow);
+}
+
+int tiles_per_view(int W, int H) { return ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile); }
+
+void launch_tile_resolve(const uint4* rec, const uint32_t* offsets, const uint32_t* total, int nviews,
+                         const ViewConst& vc, const uint8_t* val, bool packed, uint8_t* images,
+                         size_t pitch, uint32_t* winners, size_t P, cudaStream_t st) {
+  if (nviews == 0) return;
+  const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
+  const unsigned grid = (unsigned)nviews * ntx * nty;
+  if (packed)
+    tile_resolve_kernel<true><<<grid, kTileThreads, 0, st>>>(rec, offsets, total, ntx, ntx * nty, vc.W, vc.H,
+                                                              vc.s, val, images, pitch, winners, P);
+  else
+    tile_resolve_kernel<false><<<grid, kTileThreads, 0, st>>>(rec, offsets, total, ntx, ntx * nty, vc.W, vc.H,
+                                                               vc.s, val, images, pitch, winners, P);
 }
 
 void launch_resolve(unsigned long long* zbuf, const uint8_t* val, int nviews, size_t P,
