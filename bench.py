@@ -199,7 +199,7 @@ def run_gpu(args):
             searcher.search_enqueue(scene.Twc, grid, flags, rank, world, key.data_ptr())
             if world > 1:
                 dist.all_reduce(key, op=dist.ReduceOp.MAX)
-        stream.synchronize()
+        searcher.sync()  # stream sync + surfaces a record-buffer overflow of the enqueued search
 
     def step_e2e():
         # public API with HOST buffers: frame H2D + search + winner key D2H, every step
@@ -209,7 +209,7 @@ def run_gpu(args):
             if world > 1:
                 dist.all_reduce(key, op=dist.ReduceOp.MAX)
             h_key.copy_(key, non_blocking=True)
-        stream.synchronize()
+        searcher.sync()
         return int(h_key.item())
 
     def timed(fn, steps, collect=None):

@@ -125,6 +125,12 @@ struct nmi_ctx {
   DevBuf<uint32_t> mtri_orig, mslots;
   size_t n_tris = 0;  // > 0: the model is a mesh, else a point cloud
 
+  // feedback from the previous search, copied to pinned host memory asynchronously:
+  // [0] survivors, [1] records of the last view group, [2] overflow flag, [3] views of that group
+  uint32_t* h_feedback = nullptr;
+  cudaEvent_t ev_feedback = nullptr;
+  bool feedback_pending = false;
+  bool force_conservative = false;
   // binned tile renderer scratch (point clouds)
   DevBuf<uint32_t> bin_offsets, bin_cursor;  // [views of a group * tiles]
   DevBuf<uint32_t> bin_total;                // [0] records of the group, [1] overflow flag
@@ -210,7 +216,15 @@ int vc_point_size(const nmi_camera& cam) {
 // synchronous entry point turns into an error (never a silently wrong render).
 int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   const size_t cap_records = (2ull << 30) / sizeof(uint4);
-  const size_t per_view = (size_t)((double)c->n_pts * 1.5) + 65536;
+  size_t per_view = (size_t)((double)c->n_pts * 1.5) + 65536;  // safe for any pose
+  // steady state: size from what the previous search really produced (x1.5), so that all the
+  // views of a search usually fit one group; an overflow is detected, never silent
+  if (c->h_feedback && !c->force_conservative && c->feedback_pending &&
+      cudaEventQuery(c->ev_feedback) == cudaSuccess && c->h_feedback[3] > 0 && c->h_feedback[2] == 0) {
+    const size_t seen = (size_t)c->h_feedback[1] / c->h_feedback[3];
+    const size_t guess = seen + seen / 2 + 65536;
+    if (guess < per_view) per_view = guess;
+  }
   int g = (int)(cap_records / per_view);
   if (g < 1) g = 1;
   if (g > nviews) g = nviews;
@@ -281,6 +295,14 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
     launch_tile_resolve(c->records.p, c->bin_offsets.p, c->bin_total.p, nviews, vc, c->val.p,
                         c->packed_value, images, c->pitch, winners, c->P, c->stream);
     c->launches += 4;
+    if (c->h_feedback) {  // survivors / records / overflow of this group -> pinned host words
+      CK(cudaMemcpyAsync(c->h_feedback, c->counter.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(c->h_feedback + 1, c->bin_total.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                         c->stream));
+      c->h_feedback[3] = (uint32_t)nviews;
+      CK(cudaEventRecord(c->ev_feedback, c->stream));
+      c->feedback_pending = true;
+    }
     CK(cudaGetLastError());
     return NMI_OK;
   }
@@ -478,6 +500,9 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& e : c->ev) CK(cudaEventCreate(&e));
   CK(cudaEventCreateWithFlags(&c->ev_params, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_feedback, cudaEventDisableTiming));
+  CK(cudaMallocHost(&c->h_feedback, 4 * sizeof(uint32_t)));
+  memset(c->h_feedback, 0, 4 * sizeof(uint32_t));
   CK(c->counter.reserve(1));
   CK(c->key.reserve(1));
   CK(c->one_score.reserve(1));
@@ -503,6 +528,8 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (c->h_params) cudaFreeHost(c->h_params);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->ev_params) cudaEventDestroy(c->ev_params);
+  if (c->ev_feedback) cudaEventDestroy(c->ev_feedback);
+  if (c->h_feedback) cudaFreeHost(c->h_feedback);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -512,6 +539,13 @@ void* nmi_ctx_stream(nmi_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int nmi_ctx_sync(nmi_ctx* c) {
   REQUIRE(c, NMI_ERR_INVALID, "null ctx");
   CK(cudaStreamSynchronize(c->stream));
+  if (c->feedback_pending && c->h_feedback && c->h_feedback[2] != 0) {
+    c->force_conservative = true;  // the next search uses the pose-independent sizing
+    set_error("tile renderer record buffer overflow in an enqueued search: its renders are incomplete; "
+              "re-enqueue it");
+    c->h_feedback[2] = 0;
+    return NMI_ERR_CUDA;
+  }
   return NMI_OK;
 }
 
@@ -590,7 +624,7 @@ int nmi_set_points(nmi_ctx* c, const float* xyzi, size_t n) {
   CK(c->val.reserve(n));
   CK(c->cpts.reserve(n));
   CK(c->cidx.reserve(n));
-  CK(c->block_counts.reserve((n + 255) / 256 + 1));
+  CK(c->block_counts.reserve((n + 255) / 256 + 1));  // >= CTAs of either cull kernel
   CK(cudaMemcpyAsync(c->pts.p, sorted.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->orig.p, orig.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   CK(c->tag.reserve(n));
@@ -723,6 +757,14 @@ int nmi_search(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fla
                        c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));
+  if (tile_state[1] != 0 && !c->force_conservative) {
+    // the record-buffer guess from the previous search was too small for this pose: redo the
+    // search with the pose-independent sizing
+    c->force_conservative = true;
+    const int rc2 = nmi_search(c, Twc, g, f, out, scores_host);
+    c->force_conservative = false;
+    return rc2;
+  }
   REQUIRE(tile_state[1] == 0, NMI_ERR_CUDA, "tile renderer record buffer overflow (model too dense for 2 GiB of records)");
   float ms = 0;
   if (c->timed) cudaEventElapsedTime(&ms, c->ev[0], c->ev[6]);

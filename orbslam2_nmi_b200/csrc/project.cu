@@ -76,14 +76,29 @@ __device__ __forceinline__ bool cull_keep(const float4& p, const ViewConst& vc, 
 // the Morton order of the cloud and a run of consecutive survivors stays a compact image
 // patch:  count per CTA -> exclusive scan of the CTA counts -> scatter.
 constexpr int kCullThreads = 256;
+constexpr int kCullPer = 4;                              // points per thread
+constexpr int kCullBlock = kCullThreads * kCullPer;      // 1024 points per CTA
 
 __global__ void __launch_bounds__(kCullThreads)
 cull_count_kernel(const float4* __restrict__ pts, uint32_t n, ViewConst vc, CullConst cc,
                   uint32_t* __restrict__ block_counts) {
-  const uint32_t i = blockIdx.x * kCullThreads + threadIdx.x;
-  const bool keep = i < n && cull_keep(ldg_stream(pts + i), vc, cc);
-  const int cnt = __syncthreads_count(keep);
-  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
+  __shared__ uint32_t s_cnt[kCullThreads / 32];
+  const uint32_t base = blockIdx.x * kCullBlock;
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < kCullPer; k++) {
+    const uint32_t i = base + k * kCullThreads + threadIdx.x;
+    mine += (i < n && cull_keep(ldg_stream(pts + i), vc, cc)) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d /= 2) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kCullThreads / 32; w++) t += s_cnt[w];
+    block_counts[blockIdx.x] = t;
+  }
 }
 
 // single CTA: in-place exclusive scan of nblocks counts, total -> *counter
@@ -129,24 +144,36 @@ __global__ void __launch_bounds__(kCullThreads)
 cull_scatter_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ tag, uint32_t n,
                     ViewConst vc, CullConst cc, const uint32_t* __restrict__ block_offsets,
                     float4* __restrict__ out_pts, uint32_t* __restrict__ out_idx) {
-  __shared__ uint32_t s_warp[kCullThreads / 32];
-  const uint32_t i = blockIdx.x * kCullThreads + threadIdx.x;
+  __shared__ uint32_t s_warp[kCullPer][kCullThreads / 32];
+  const uint32_t base = blockIdx.x * kCullBlock;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 p = make_float4(0, 0, 0, 0);
-  bool keep = false;
-  if (i < n) {
-    p = ldg_stream(pts + i);
-    keep = cull_keep(p, vc, cc);
+  float4 p[kCullPer];
+  unsigned m[kCullPer];
+  bool keep[kCullPer];
+#pragma unroll
+  for (int k = 0; k < kCullPer; k++) {  // sub-block k holds points base + k*256 .. +255 (in order)
+    const uint32_t i = base + k * kCullThreads + threadIdx.x;
+    keep[k] = false;
+    p[k] = make_float4(0, 0, 0, 0);
+    if (i < n) {
+      p[k] = ldg_stream(pts + i);
+      keep[k] = cull_keep(p[k], vc, cc);
+    }
+    m[k] = __ballot_sync(0xffffffffu, keep[k]);
+    if (lane == 0) s_warp[k][warp] = (uint32_t)__popc(m[k]);
   }
-  const unsigned m = __ballot_sync(0xffffffffu, keep);
-  if (lane == 0) s_warp[warp] = (uint32_t)__popc(m);
   __syncthreads();
   uint32_t before = block_offsets[blockIdx.x];
-  for (int w = 0; w < warp; w++) before += s_warp[w];
-  if (keep) {
-    const uint32_t o = before + __popc(m & ((1u << lane) - 1u));
-    out_pts[o] = p;
-    out_idx[o] = tag[i];  // the z-buffer key's tie-break word of this point
+#pragma unroll
+  for (int k = 0; k < kCullPer; k++) {
+    uint32_t off = before;
+    for (int w = 0; w < warp; w++) off += s_warp[k][w];
+    if (keep[k]) {
+      const uint32_t o = off + __popc(m[k] & ((1u << lane) - 1u));
+      out_pts[o] = p[k];
+      out_idx[o] = tag[base + k * kCullThreads + threadIdx.x];  // the z-buffer key's tie-break word
+    }
+    for (int w = 0; w < kCullThreads / 32; w++) before += s_warp[k][w];
   }
 }
 
@@ -259,26 +286,35 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
   __syncthreads();
   const uint32_t count = *counter;
   const float half = 0.5f * (float)(vc.s - 1);
+  auto emit = [&](const Splat& f, int v, uint32_t tag) {
+    const int tx0 = max(f.i0, 0) / kTile, tx1 = min(f.i0 + vc.s - 1, vc.W - 1) / kTile;
+    const int ty0 = max(f.j0, 0) / kTile, ty1 = min(f.j0 + vc.s - 1, vc.H - 1) / kTile;
+    for (int ty = ty0; ty <= ty1; ty++)
+      for (int tx = tx0; tx <= tx1; tx++) {
+        const uint32_t bin = (uint32_t)v * nt + ty * ntx + tx;
+        const uint32_t slot = atomicAdd(&counts[bin], 1u);
+        if (SCATTER) {
+          const uint32_t pos = offsets[bin] + slot;
+          if (pos < rec_cap)
+            rec[pos] = make_uint4((uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16), f.zbits, tag, 0u);
+          else
+            *overflow = 1u;
+        }
+      }
+  };
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
     const float4 p = cpts[t];
     const uint32_t tag = SCATTER ? ctag[t] : 0u;
-    for (int v = 0; v < nviews; v++) {
-      const Splat f = project_splat_point(p, s_c[v], vc, half);
-      if (!f.ok) continue;
-      const int tx0 = max(f.i0, 0) / kTile, tx1 = min(f.i0 + vc.s - 1, vc.W - 1) / kTile;
-      const int ty0 = max(f.j0, 0) / kTile, ty1 = min(f.j0 + vc.s - 1, vc.H - 1) / kTile;
-      for (int ty = ty0; ty <= ty1; ty++)
-        for (int tx = tx0; tx <= tx1; tx++) {
-          const uint32_t bin = (uint32_t)v * nt + ty * ntx + tx;
-          const uint32_t slot = atomicAdd(&counts[bin], 1u);
-          if (SCATTER) {
-            const uint32_t pos = offsets[bin] + slot;
-            if (pos < rec_cap)
-              rec[pos] = make_uint4((uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16), f.zbits, tag, 0u);
-            else
-              *overflow = 1u;
-          }
-        }
+    int v = 0;
+    for (; v + 1 < nviews; v += 2) {  // two independent projections in flight
+      const Splat f0 = project_splat_point(p, s_c[v], vc, half);
+      const Splat f1 = project_splat_point(p, s_c[v + 1], vc, half);
+      if (f0.ok) emit(f0, v, tag);
+      if (f1.ok) emit(f1, v + 1, tag);
+    }
+    if (v < nviews) {
+      const Splat f0 = project_splat_point(p, s_c[v], vc, half);
+      if (f0.ok) emit(f0, v, tag);
     }
   }
 }
@@ -300,21 +336,51 @@ tile_resolve_kernel(const uint4* __restrict__ rec, const uint32_t* __restrict__ 
   const uint32_t end = bin + 1 < gridDim.x ? offsets[bin + 1] : *total;
   for (int q = tid; q < kTileCells; q += kTileThreads) { s_depth[q] = 0xFFFFFFFFu; s_tag[q] = 0xFFFFFFFFu; }
   __syncthreads();
-  // pass 1: minimum depth per cell
-  for (uint32_t r = start + tid; r < end; r += kTileThreads) {
-    const uint4 e = rec[r];
-    const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
-    for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
-      for (int i = max(li, 0); i < min(li + S, kTile); i++) atomicMin(&s_depth[j * kTile + i], e.y);
-  }
-  __syncthreads();
-  // pass 2: lowest tie-break word among the fragments at the minimum depth
-  for (uint32_t r = start + tid; r < end; r += kTileThreads) {
-    const uint4 e = rec[r];
-    const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
-    for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
-      for (int i = max(li, 0); i < min(li + S, kTile); i++)
-        if (s_depth[j * kTile + i] == e.y) atomicMin(&s_tag[j * kTile + i], e.z);
+  if (S == 3) {
+    // the reference's glPointSize(3): fully unrolled 3x3, one range test per row / column
+    for (uint32_t r = start + tid; r < end; r += kTileThreads) {  // pass 1: minimum depth per cell
+      const uint4 e = rec[r];
+      const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
+      const int q = lj * kTile + li;
+#pragma unroll
+      for (int dj = 0; dj < 3; dj++) {
+        if ((unsigned)(lj + dj) >= (unsigned)kTile) continue;
+#pragma unroll
+        for (int di = 0; di < 3; di++)
+          if ((unsigned)(li + di) < (unsigned)kTile) atomicMin(&s_depth[q + dj * kTile + di], e.y);
+      }
+    }
+    __syncthreads();
+    for (uint32_t r = start + tid; r < end; r += kTileThreads) {  // pass 2: min tag at the min depth
+      const uint4 e = rec[r];
+      const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
+      const int q = lj * kTile + li;
+#pragma unroll
+      for (int dj = 0; dj < 3; dj++) {
+        if ((unsigned)(lj + dj) >= (unsigned)kTile) continue;
+#pragma unroll
+        for (int di = 0; di < 3; di++)
+          if ((unsigned)(li + di) < (unsigned)kTile && s_depth[q + dj * kTile + di] == e.y)
+            atomicMin(&s_tag[q + dj * kTile + di], e.z);
+      }
+    }
+  } else {
+    // pass 1: minimum depth per cell
+    for (uint32_t r = start + tid; r < end; r += kTileThreads) {
+      const uint4 e = rec[r];
+      const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
+      for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
+        for (int i = max(li, 0); i < min(li + S, kTile); i++) atomicMin(&s_depth[j * kTile + i], e.y);
+    }
+    __syncthreads();
+    // pass 2: lowest tie-break word among the fragments at the minimum depth
+    for (uint32_t r = start + tid; r < end; r += kTileThreads) {
+      const uint4 e = rec[r];
+      const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
+      for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
+        for (int i = max(li, 0); i < min(li + S, kTile); i++)
+          if (s_depth[j * kTile + i] == e.y) atomicMin(&s_tag[j * kTile + i], e.z);
+    }
   }
   __syncthreads();
   // the CTA owns the tile: plain stores of the finished pixels (8 per thread, one row segment)
@@ -399,7 +465,7 @@ void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, co
   cc.mx = margin[0];
   cc.my = margin[1];
   cc.mz = margin[2];
-  const uint32_t nblocks = (n + kCullThreads - 1) / kCullThreads;
+  const uint32_t nblocks = (n + kCullBlock - 1) / kCullBlock;
   cull_count_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, n, vc, cc, block_counts);
   cull_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, counter);
   cull_scatter_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, orig, n, vc, cc, block_counts, out_pts,

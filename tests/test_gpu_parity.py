@@ -357,3 +357,24 @@ def test_large_cloud_uses_gather_path(searcher, oracle):
     win, img = oracle.render_points(sc, sc.Twc, t, sc.xyzi)
     assert np.array_equal(searcher.get_winners(1), win)
     assert np.array_equal(searcher.get_render(1), img)
+
+
+def test_record_buffer_guess_overflow_is_recovered(searcher, oracle):
+    """The tile renderer sizes its record buffer from the previous search.  A pose that sees
+    nothing followed by one that sees the whole model makes that guess far too small: the
+    overflow must be detected and the search redone, never a silently incomplete render."""
+    sc = synth.make_scene("small")
+    g = Grid.make((2, 2, 1), (1, 1, 1), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    frame = synth.frame_textured(sc.W, sc.H, seed=9)
+    searcher.set_scene(sc)
+    searcher.set_frame(frame)
+    away = sc.Twc.copy()
+    away[:3, 3] += np.array([500.0, 0.0, 0.0], dtype=np.float32)  # nothing in view
+    r0 = searcher.search(away, g, want_scores=True)
+    assert (searcher.get_render(0) == 255).all()
+    for _ in range(2):
+        res = searcher.search(sc.Twc, g, want_scores=True)
+        scores, renders, _ = oracle.search_points(sc, sc.Twc, g, sc.xyzi, frame, keep_images=True)
+        for s in range(g.n_synth):
+            assert np.array_equal(searcher.get_render(s), renders[s])
+        assert_scores_close(res.scores, scores)
