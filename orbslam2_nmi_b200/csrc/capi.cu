@@ -33,7 +33,7 @@ void launch_bin_points(bool scatter, const float4* cpts, const uint32_t* ctag, c
                        const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t* overflow,
                        cudaStream_t st);
 int tiles_per_view(int W, int H);
-void launch_tile_resolve(const uint4* rec, const uint32_t* offsets, const uint32_t* total, int nviews,
+void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, const uint32_t* offsets, const uint32_t* total, int nviews,
                          const ViewConst& vc, const uint8_t* val, bool packed, uint8_t* images,
                          size_t pitch, uint32_t* winners, size_t P, cudaStream_t st);
 
@@ -292,7 +292,7 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
     launch_bin_points(true, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_cursor.p,
                       c->bin_offsets.p, c->records.p, (uint32_t)c->records.cap, c->bin_total.p + 1,
                       c->stream);
-    launch_tile_resolve(c->records.p, c->bin_offsets.p, c->bin_total.p, nviews, vc, c->val.p,
+    launch_tile_resolve(c->records.p, (uint32_t)c->records.cap, c->bin_offsets.p, c->bin_total.p, nviews, vc, c->val.p,
                         c->packed_value, images, c->pitch, winners, c->P, c->stream);
     c->launches += 4;
     if (c->h_feedback) {  // survivors / records / overflow of this group -> pinned host words
@@ -563,6 +563,7 @@ int nmi_set_camera(nmi_ctx* c, const nmi_camera* cam) {
     c->has_search = false;
   }
   c->cam = *cam;
+  c->feedback_pending = false;
   c->P = (size_t)cam->W * cam->H;
   c->pitch = img_pitch(c->P);
   c->has_cam = true;
@@ -634,6 +635,7 @@ int nmi_set_points(nmi_ctx* c, const float* xyzi, size_t n) {
   CK(cudaStreamSynchronize(c->stream));
   c->n_pts = n;
   c->n_tris = 0;
+  c->feedback_pending = false;  // record-count feedback belongs to the previous model
   c->has_search = false;
   return NMI_OK;
 }

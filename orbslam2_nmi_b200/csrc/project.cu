@@ -321,7 +321,7 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
 
 template <bool PACKED>
 __global__ void __launch_bounds__(kTileThreads)
-tile_resolve_kernel(const uint4* __restrict__ rec, const uint32_t* __restrict__ offsets,
+tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, const uint32_t* __restrict__ offsets,
                     const uint32_t* __restrict__ total, int ntx, int nt, int W, int H, int S,
                     const uint8_t* __restrict__ val, uint8_t* __restrict__ images, size_t pitch,
                     uint32_t* __restrict__ winners, size_t P) {
@@ -332,8 +332,10 @@ tile_resolve_kernel(const uint4* __restrict__ rec, const uint32_t* __restrict__ 
   const int ty = tile / ntx, tx = tile - ty * ntx;
   const int x0 = tx * kTile, y0 = ty * kTile;
   const int tid = threadIdx.x;
-  const uint32_t start = offsets[bin];
-  const uint32_t end = bin + 1 < gridDim.x ? offsets[bin + 1] : *total;
+  // clamp to the record buffer: after an overflow (flagged by bin_scatter, the search is then
+  // redone) the offsets may point past it
+  const uint32_t start = min(offsets[bin], rec_cap);
+  const uint32_t end = min(bin + 1 < gridDim.x ? offsets[bin + 1] : *total, rec_cap);
   for (int q = tid; q < kTileCells; q += kTileThreads) { s_depth[q] = 0xFFFFFFFFu; s_tag[q] = 0xFFFFFFFFu; }
   __syncthreads();
   if (S == 3) {
@@ -501,17 +503,17 @@ void launch_bin_points(bool scatter, const float4* cpts, const uint32_t* ctag, c
 
 int tiles_per_view(int W, int H) { return ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile); }
 
-void launch_tile_resolve(const uint4* rec, const uint32_t* offsets, const uint32_t* total, int nviews,
+void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, const uint32_t* offsets, const uint32_t* total, int nviews,
                          const ViewConst& vc, const uint8_t* val, bool packed, uint8_t* images,
                          size_t pitch, uint32_t* winners, size_t P, cudaStream_t st) {
   if (nviews == 0) return;
   const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
   const unsigned grid = (unsigned)nviews * ntx * nty;
   if (packed)
-    tile_resolve_kernel<true><<<grid, kTileThreads, 0, st>>>(rec, offsets, total, ntx, ntx * nty, vc.W, vc.H,
+    tile_resolve_kernel<true><<<grid, kTileThreads, 0, st>>>(rec, rec_cap, offsets, total, ntx, ntx * nty, vc.W, vc.H,
                                                               vc.s, val, images, pitch, winners, P);
   else
-    tile_resolve_kernel<false><<<grid, kTileThreads, 0, st>>>(rec, offsets, total, ntx, ntx * nty, vc.W, vc.H,
+    tile_resolve_kernel<false><<<grid, kTileThreads, 0, st>>>(rec, rec_cap, offsets, total, ntx, ntx * nty, vc.W, vc.H,
                                                                vc.s, val, images, pitch, winners, P);
 }
 
