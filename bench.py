@@ -33,6 +33,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+_OUT = sys.stdout
 METRIC = "nmi_pose_evals_per_s"
 UNIT = "evals/s"
 WORKLOAD = "C2 ZU-MAV-shaped search: 1920x1080 frame, 10M-point cloud, 4^3 synth x 4^3 warp = 4096 poses per GPU, 256 bins, SUC"
@@ -152,7 +153,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     return 0
 
 
@@ -293,14 +294,25 @@ def run_gpu(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def _quiet_stdout():
+    """Route fd 1 to stderr for the whole run (NCCL prints its version banner to stdout) and
+    return a file object on the real stdout for the single JSON line."""
+    real = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    global _OUT
+    _OUT = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -213,7 +213,8 @@ int nmi_get_warp(nmi_ctx *ctx, int w, uint8_t *host);      /* W*H u8         */
 int nmi_get_hist(nmi_ctx *ctx, int s, int w, const nmi_flags *flags,
                  uint32_t *J, uint32_t *HA, uint32_t *HB, float *score);
 /* per-stage device times of the last search, ms:
- * [0] params+cull [1] project [2] resolve [3] warp [4] hist+score [5] argmax
+ * [0] params+cull [1] render (bin + tile resolve, all view groups) [2] unused
+ * [3] warp [4] hist+score [5] argmax
  * [6] total.  launches = kernels launched by the last search.                */
 int nmi_get_timings(nmi_ctx *ctx, float ms[8], int *launches);
 

@@ -179,7 +179,7 @@ class NmiSearcher:
         ms = np.zeros(8, dtype=np.float32)
         n = C.c_int(0)
         check(self.lib.nmi_get_timings(self.h, ptr(ms), C.byref(n)))
-        names = ["params_cull", "project", "resolve", "warp", "hist_score", "argmax", "total"]
+        names = ["params_cull", "render", "spare", "warp", "hist_score", "argmax", "total"]
         return {k: float(ms[i]) for i, k in enumerate(names)}, n.value
 
 
