@@ -56,4 +56,20 @@ class Yaml {
 // Like the reference's `while(!in.eof())` loop, a trailing newline duplicates the last point.
 bool loadXYZ(const char* path, const char* offset_path, std::vector<float>& xyzi);
 
+// loadOBJ (objloader.cpp:140-223): "v x y z", "vt u v", "f a/b c/d e/f" (1-based); any other
+// face syntax is rejected like the reference ("File can't be read by this simple parser").
+// Output is un-indexed like the reference's VBOs: 3 positions + 3 uvs per triangle.
+bool loadOBJ(const char* path, std::vector<float>& xyz /*3 per vertex*/, std::vector<float>& uv /*2 per vertex*/);
+// loadBMP_custom (texture.cpp:31-107): 24-bpp uncompressed BMP; bytes are returned exactly as
+// the reference hands them to glTexImage2D(GL_RGB): file order B,G,R is READ AS R,G,B, rows
+// bottom-up.
+bool loadBMP24(const char* path, int& width, int& height, std::vector<unsigned char>& rgb);
+// Mesh model for nmi_set_mesh from the reference's OBJ + BMP: per vertex the fragment
+// shader's luma 0.299 r + 0.587 g + 0.114 b (ShadingWithTexture.fragmentshader:16) of the
+// NEAREST level-0 texel under GL_REPEAT (texture.cpp:100-101), on the byte-swapped channels
+// the reference uploads.  The reference samples a trilinear mip-mapped texture per fragment;
+// flat per-triangle shading from the first vertex is this build's documented deviation.
+bool meshFromObjBmp(const char* obj_path, const char* bmp_path, std::vector<float>& verts_xyzg,
+                    std::vector<uint32_t>& tris);
+
 }  // namespace nmi_compat

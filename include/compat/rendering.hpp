@@ -58,7 +58,6 @@ class Rendering {
     cam.zn = near_clipping_plane; cam.zf = far_clipping_plane;  // rendering.hpp:198-199
     cam.point_size = pointSize;                              // rendering.hpp:307
     nmi_compat::apply_camera();
-    (void)object_path; (void)texture_path;
     if (RenderingMode == RENDER_POINT_CLOUD) {
       if (!cloud_path.empty()) {
         std::vector<float> xyzi;
@@ -68,11 +67,21 @@ class Rendering {
         }
         setCloud(xyzi.data(), xyzi.size() / 4);
       }
-    } else {
-      std::fprintf(stderr, "Rendering<%d>: mesh rendering is not part of this build yet "
-                           "(DESIGN.md, out of scope this round)\n", (int)RenderingMode);
-      std::exit(EXIT_FAILURE);
+    } else if (!object_path.empty()) {
+      // RENDER_TEXTURE (rendering.hpp:172-178, 219-229): OBJ + 24-bpp BMP
+      std::vector<float> verts;
+      std::vector<uint32_t> tris;
+      if (!nmi_compat::meshFromObjBmp(object_path.c_str(), texture_path.c_str(), verts, tris)) {
+        std::fprintf(stderr, "Rendering: cannot load %s / %s\n", object_path.c_str(), texture_path.c_str());
+        std::exit(EXIT_FAILURE);
+      }
+      setMesh(verts.data(), verts.size() / 4, tris.data(), tris.size() / 3);
     }
+  }
+
+  // extension: hand over an in-memory mesh (nv x {x,y,z,grey}, nt x 3 indices)
+  void setMesh(const float* verts, size_t nv, const uint32_t* tris, size_t nt) {
+    nmi_compat::check(nmi_set_mesh(nmi_compat::context(), verts, nv, tris, nt), "Rendering::setMesh");
   }
 
   // extension: hand over an in-memory cloud (n x {x,y,z,I}) instead of a file

@@ -168,6 +168,93 @@ bool loadXYZ(const char* path, const char* offset_path, std::vector<float>& xyzi
   return !xyzi.empty();
 }
 
+// ---- .obj / .bmp loaders (objloader.cpp:140-223, texture.cpp:31-107) ---------------------
+bool loadOBJ(const char* path, std::vector<float>& xyz, std::vector<float>& uv) {
+  std::ifstream in(path);
+  if (!in.is_open()) return false;
+  std::vector<float> v, vt;
+  std::vector<unsigned> vi, ti;
+  std::string line;
+  while (std::getline(in, line)) {
+    std::istringstream ss(line);
+    std::string head;
+    if (!(ss >> head)) continue;
+    if (head == "v") {
+      float x, y, z;
+      if (!(ss >> x >> y >> z)) return false;
+      v.insert(v.end(), {x, y, z});
+    } else if (head == "vt") {
+      float a, b;
+      if (!(ss >> a >> b)) return false;
+      vt.insert(vt.end(), {a, b});
+    } else if (head == "f") {
+      for (int k = 0; k < 3; k++) {
+        std::string tok;
+        if (!(ss >> tok)) return false;
+        unsigned a = 0, b = 0;
+        if (std::sscanf(tok.c_str(), "%u/%u", &a, &b) != 2 || tok.find('/') != tok.rfind('/')) return false;
+        vi.push_back(a);
+        ti.push_back(b);
+      }
+      std::string extra;
+      if (ss >> extra) return false;  // quads etc.: "can't be read by this simple parser"
+    }  // anything else: comment / unsupported statement, skipped like the reference
+  }
+  xyz.clear();
+  uv.clear();
+  for (size_t i = 0; i < vi.size(); i++) {
+    if (vi[i] == 0 || ti[i] == 0 || 3 * (size_t)vi[i] > v.size() || 2 * (size_t)ti[i] > vt.size()) return false;
+    xyz.insert(xyz.end(), v.begin() + 3 * (vi[i] - 1), v.begin() + 3 * (vi[i] - 1) + 3);
+    uv.insert(uv.end(), vt.begin() + 2 * (ti[i] - 1), vt.begin() + 2 * (ti[i] - 1) + 2);
+  }
+  return !xyz.empty();
+}
+
+bool loadBMP24(const char* path, int& width, int& height, std::vector<unsigned char>& rgb) {
+  std::ifstream f(path, std::ios::binary);
+  unsigned char h[54];
+  if (!f.read(reinterpret_cast<char*>(h), 54) || h[0] != 'B' || h[1] != 'M') return false;
+  auto u32 = [&](int o) { return (unsigned)h[o] | ((unsigned)h[o + 1] << 8) | ((unsigned)h[o + 2] << 16) | ((unsigned)h[o + 3] << 24); };
+  if (u32(0x1E) != 0 || (u32(0x1C) & 0xFFFF) != 24) return false;  // texture.cpp:58-59
+  unsigned dataPos = u32(0x0A), imageSize = u32(0x22);
+  width = (int)u32(0x12);
+  height = (int)u32(0x16);
+  if (width <= 0 || height <= 0) return false;
+  if (imageSize == 0) imageSize = (unsigned)width * height * 3;  // texture.cpp:68
+  if (dataPos == 0) dataPos = 54;
+  rgb.assign(imageSize, 0);
+  f.seekg(dataPos);
+  f.read(reinterpret_cast<char*>(rgb.data()), imageSize);
+  return (size_t)f.gcount() >= (size_t)width * height * 3;
+}
+
+bool meshFromObjBmp(const char* obj_path, const char* bmp_path, std::vector<float>& verts,
+                    std::vector<uint32_t>& tris) {
+  std::vector<float> xyz, uv;
+  std::vector<unsigned char> tex;
+  int tw = 0, th = 0;
+  if (!loadOBJ(obj_path, xyz, uv) || !loadBMP24(bmp_path, tw, th, tex)) return false;
+  const size_t nv = xyz.size() / 3;
+  verts.resize(4 * nv);
+  tris.resize(nv);
+  for (size_t i = 0; i < nv; i++) {
+    // GL_REPEAT + nearest texel of level 0; the reference uploads tightly packed rows
+    // (GL_UNPACK_ALIGNMENT 1, rendering.hpp:313), i.e. stride = 3 * width
+    const float u = uv[2 * i] - std::floor(uv[2 * i]), v = uv[2 * i + 1] - std::floor(uv[2 * i + 1]);
+    int tx = (int)std::floor(u * tw), ty = (int)std::floor(v * th);
+    tx = tx < 0 ? 0 : (tx >= tw ? tw - 1 : tx);
+    ty = ty < 0 ? 0 : (ty >= th ? th - 1 : ty);
+    const unsigned char* t = &tex[3 * ((size_t)ty * tw + tx)];
+    const float r = t[0] / 255.0f, g = t[1] / 255.0f, b = t[2] / 255.0f;  // file B,G,R read as R,G,B
+    verts[4 * i] = xyz[3 * i];
+    verts[4 * i + 1] = xyz[3 * i + 1];
+    verts[4 * i + 2] = xyz[3 * i + 2];
+    verts[4 * i + 3] = 0.299f * r + 0.587f * g + 0.114f * b;
+    tris[i] = (uint32_t)i;
+  }
+  return nv >= 3 && nv % 3 == 0;
+}
+
 }  // namespace nmi_compat
 
 // ---- CUDAF::NMIWithCuda_noMask (kernel.cuh:37, kernel.cu:49-114) -------------------------

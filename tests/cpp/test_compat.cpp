@@ -22,6 +22,32 @@
     }                                                                 \
   } while (0)
 
+static int loader_checks(const char* obj, const char* bmp) {
+  // loadOBJ (objloader.cpp:140-223): 2 triangles, un-indexed output in face order
+  std::vector<float> xyz, uv;
+  EXPECT(nmi_compat::loadOBJ(obj, xyz, uv));
+  EXPECT(xyz.size() == 18 && uv.size() == 12);
+  EXPECT(xyz[0] == 0.0f && xyz[3] == 1.0f && xyz[7] == 1.0f);     // v1, v2, v3 of face 1
+  EXPECT(uv[0] == 0.25f && uv[1] == 0.25f && uv[2] == 0.75f);
+  // loadBMP24 (texture.cpp:31-107): 2x2, bytes as stored (B,G,R read as R,G,B), rows bottom-up
+  int w = 0, h = 0;
+  std::vector<unsigned char> rgb;
+  EXPECT(nmi_compat::loadBMP24(bmp, w, h, rgb));
+  EXPECT(w == 2 && h == 2 && rgb.size() >= 12);
+  EXPECT(rgb[0] == 10 && rgb[1] == 20 && rgb[2] == 30);  // bottom-left texel as written in the file
+  // meshFromObjBmp: luma of the nearest texel on the swapped channels
+  std::vector<float> verts;
+  std::vector<uint32_t> tris;
+  EXPECT(nmi_compat::meshFromObjBmp(obj, bmp, verts, tris));
+  EXPECT(verts.size() == 24 && tris.size() == 6 && tris[5] == 5);
+  const float want = 0.299f * (10 / 255.0f) + 0.587f * (20 / 255.0f) + 0.114f * (30 / 255.0f);
+  EXPECT(std::fabs(verts[3] - want) < 1e-6f);             // uv (0.25, 0.25) -> texel (0, 0)
+  const float want2 = 0.299f * (40 / 255.0f) + 0.587f * (50 / 255.0f) + 0.114f * (60 / 255.0f);
+  EXPECT(std::fabs(verts[7] - want2) < 1e-6f);            // uv (0.75, 0.25) -> texel (1, 0)
+  std::printf("LOADERS OK\n");
+  return 0;
+}
+
 static int host_checks(const char* yaml, const char* xyz, const char* off) {
   // NmiSearchKernel (nmiSearchKernel.cpp)
   NmiSearchKernel k(3, 3, 3, 3, 3, 3, 0.2f, 0.2f, 0.5f, 0.02f, 0.02f, 0.05f);
@@ -167,6 +193,7 @@ static int gpu_checks(const char* yaml, const char* frame_raw, const char* twc_t
 }
 
 int main(int argc, char** argv) {
+  if (argc >= 4 && std::string(argv[1]) == "loaders") return loader_checks(argv[2], argv[3]);
   if (argc >= 5 && std::string(argv[1]) == "host") return host_checks(argv[2], argv[3], argv[4]);
   if (argc >= 5 && std::string(argv[1]) == "gpu") return gpu_checks(argv[2], argv[3], argv[4]);
   std::printf("usage: test_compat host|gpu ...\n");

@@ -91,6 +91,25 @@ def test_compat_host_logic(exe, workdir):
     assert res.returncode == 0 and "HOST OK" in res.stdout, res.stdout + res.stderr
 
 
+def test_compat_obj_bmp_loaders(exe, tmp_path):
+    """loadOBJ / loadBMP_custom formats (objloader.cpp:140-223, texture.cpp:31-107)."""
+    import struct
+
+    obj = tmp_path / "m.obj"
+    obj.write_text("# comment\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\n"
+                   "vt 0.25 0.25\nvt 0.75 0.25\nvt 0.25 0.75\nvt 0.75 0.75\n"
+                   "f 1/1 2/2 3/3\nf 2/2 4/4 3/3\n")
+    px = bytes([10, 20, 30, 40, 50, 60, 0, 0,      # bottom row (2 texels + 2 pad bytes)
+                70, 80, 90, 100, 110, 120, 0, 0])  # top row
+    hdr = b"BM" + struct.pack("<IHHI", 54 + len(px), 0, 0, 54) + struct.pack(
+        "<IiiHHIIiiII", 40, 2, 2, 1, 24, 0, 0, 2835, 2835, 0, 0)
+    bmp = tmp_path / "t.bmp"
+    # the reference reads tightly packed rows (GL_UNPACK_ALIGNMENT 1): write an unpadded image
+    bmp.write_bytes(hdr[:34] + struct.pack("<I", 12) + hdr[38:] + bytes([10, 20, 30, 40, 50, 60, 70, 80, 90, 100, 110, 120]))
+    res = subprocess.run([str(exe), "loaders", str(obj), str(bmp)], capture_output=True, text=True)
+    assert res.returncode == 0 and "LOADERS OK" in res.stdout, res.stdout + res.stderr
+
+
 def _loaded_cloud(d):
     """What loadXYZ produces (float64 parse, offset subtraction, float cast, /256, duplicate)."""
     raw = np.loadtxt(d / "cloud.xyz")
