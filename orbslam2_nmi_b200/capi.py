@@ -12,7 +12,10 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
-LIB_PATH = ROOT / "orbslam2_nmi_b200" / "_lib" / "libnmi_b200.so"
+import os
+
+# NMI_B200_LIB lets an experiment load an alternative build of the same library
+LIB_PATH = Path(os.environ.get("NMI_B200_LIB", ROOT / "orbslam2_nmi_b200" / "_lib" / "libnmi_b200.so"))
 
 NMI_OK, NMI_ERR_INVALID, NMI_ERR_CUDA, NMI_ERR_STATE, NMI_ERR_NO_WINNER = range(5)
 SCORE_ENMI, SCORE_SUC = 0, 1

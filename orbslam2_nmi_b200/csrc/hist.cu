@@ -42,13 +42,21 @@
 namespace nmi {
 namespace {
 
-constexpr int kChunk = 8192;  // pixels per stage and image
-constexpr int kStages = 4;
+#ifndef NMI_HIST_CHUNK
+#define NMI_HIST_CHUNK 8192
+#endif
+#ifndef NMI_HIST_STAGES
+#define NMI_HIST_STAGES 4
+#endif
+constexpr int kChunk = NMI_HIST_CHUNK;  // pixels per stage and image
+constexpr int kStages = NMI_HIST_STAGES;
+static_assert((2 * kStages - 1) * kChunk < 15 * 4096, "in-flight pixels must stay below 15 crossings");
 constexpr int kEvCap = 2048;       // >= npix / 4096 drain events (npix <= 8.3M)
 constexpr uint32_t kFlagMask = 0xF000F000u;  // a field >= 4096 has one of these bits set
 constexpr uint32_t kCross = 0x0FFFu;         // low 12 bits of a field: 0 right after a crossing
 constexpr int kHistWords = 32768;  // 128 KiB
 constexpr int kB64Copies = 8;
+constexpr int kTermTab = 1024;     // counts below this take their entropy term from a table
 
 enum Policy { P_U16G = 0, P_U32X2 = 2, P_B64 = 3 };
 
@@ -62,6 +70,7 @@ struct __align__(16) Smem {
   uint32_t HA[256];
   uint32_t HB[256];
   float sums[4];
+  float term_tab[kTermTab];  // e(c) for small counts, filled per CTA with term() itself
   uint32_t ev_count;
   uint16_t ev_list[kEvCap];  // bin of every repaid crossing (+4096 each)
 };
@@ -109,6 +118,11 @@ __device__ __forceinline__ float term(uint32_t c, float L) {
   if (c == 0) return 0.0f;
   const float p = __fdiv_rn((float)c, L);
   return __fmul_rn(p, log2f(p));
+}
+// Same value as term(c, L): small counts (the vast majority of non-empty bins) are looked up in
+// the per-CTA table that was filled with term() itself, so the result is bit-identical.
+__device__ __forceinline__ float term_t(const float* tab, uint32_t c, float L) {
+  return c < (uint32_t)kTermTab ? tab[c] : term(c, L);
 }
 // Pairwise tree of NMI.cu:270-287 / :295-338 for n = 32*K values, lane l holding
 // x[l + 32k]: strides 16K..32 fold k, strides 16..1 are shuffles. Result in lane 0.
@@ -276,8 +290,8 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
         rs += c[2 * k] + c[2 * k + 1];
         col[2 * k] += c[2 * k];
         col[2 * k + 1] += c[2 * k + 1];
-        vl[k] = term(c[2 * k], L);
-        vh[k] = term(c[2 * k + 1], L);
+        vl[k] = term_t(sm.term_tab, c[2 * k], L);
+        vh[k] = term_t(sm.term_tab, c[2 * k + 1], L);
         if (dump) {
           a.dumpJ[row * 256 + 2 * (lane + 32 * k)] = c[2 * k];
           a.dumpJ[row * 256 + 2 * (lane + 32 * k) + 1] = c[2 * k + 1];
@@ -311,7 +325,7 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
         const uint32_t c = sm.hist[lr * 256 + lane + 32 * k];
         rs += c;
         col[k] += c;
-        v[k] = term(c, L);
+        v[k] = term_t(sm.term_tab, c, L);
         if (dump) a.dumpJ[row * 256 + lane + 32 * k] = c;
       }
       rs = warp_sum(rs);
@@ -342,7 +356,7 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
         const uint32_t c = sm.hist[row * 64 + lane + 32 * k];
         rs += c;
         col[k] += c;
-        v[k] = term(c, L);
+        v[k] = term_t(sm.term_tab, c, L);
         if (dump) a.dumpJ[row * 64 + lane + 32 * k] = c;
       }
       rs = warp_sum(rs);
@@ -410,6 +424,7 @@ joint_hist_score_kernel(const HistArgs a) {
     uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
     for (int i = tid; i < kHistWords / 4; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
     if (tid < 256) sm.HB[tid] = 0;
+    for (int i = tid; i < kTermTab; i += kThreads) sm.term_tab[i] = term((uint32_t)i, L);
     if (tid == 0) {
       sm.ev_count = 0;
       for (int s = 0; s < kStages; s++) {
