@@ -31,7 +31,7 @@ void launch_scan_counts(uint32_t* block_counts, uint32_t nblocks, uint32_t* coun
 void launch_bin_points(bool scatter, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
                        const float4* centres, int nviews, const ViewConst& vc, uint32_t* counts,
                        const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t* overflow,
-                       uint2* splats, size_t splat_cap, cudaStream_t st);
+                       cudaStream_t st);
 int tiles_per_view(int W, int H);
 void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, const uint32_t* offsets, const uint32_t* total, int nviews,
                          const ViewConst& vc, const uint8_t* val, bool packed, uint8_t* images,
@@ -135,7 +135,6 @@ struct nmi_ctx {
   DevBuf<uint32_t> bin_offsets, bin_cursor;  // [views of a group * tiles]
   DevBuf<uint32_t> bin_total;                // [0] records of the group, [1] overflow flag
   DevBuf<uint4> records;
-  DevBuf<uint2> splats;  // projected splats of a view group, kept between the two binning passes
 
   DevBuf<uint8_t> frame;
   uint8_t* h_frame = nullptr;  // pinned staging for host frames
@@ -241,18 +240,6 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
     CK(cudaStreamSynchronize(c->stream));
     CK(c->records.reserve(want));
   }
-  // splat store (8 B per survivor and view): sized from the previous search's survivor count;
-  // when it is too small the second binning pass simply projects again (decided on the device)
-  if (c->h_feedback && c->feedback_pending && cudaEventQuery(c->ev_feedback) == cudaSuccess &&
-      c->h_feedback[0] > 0) {
-    size_t want_s = ((size_t)c->h_feedback[0] + c->h_feedback[0] / 4 + 4096) * (size_t)g;
-    const size_t cap_s = (2ull << 30) / sizeof(uint2);
-    if (want_s > cap_s) want_s = cap_s;
-    if (want_s > c->splats.cap) {
-      CK(cudaStreamSynchronize(c->stream));
-      CK(c->splats.reserve(want_s));
-    }
-  }
   CK(cudaMemsetAsync(c->bin_total.p, 0, 2 * sizeof(uint32_t), c->stream));
   return NMI_OK;
 }
@@ -300,11 +287,11 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
     CK(cudaMemsetAsync(c->bin_offsets.p, 0, nbins * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->bin_cursor.p, 0, nbins * sizeof(uint32_t), c->stream));
     launch_bin_points(false, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_offsets.p,
-                      nullptr, nullptr, 0, nullptr, c->splats.p, c->splats.cap, c->stream);
+                      nullptr, nullptr, 0, nullptr, c->stream);
     launch_scan_counts(c->bin_offsets.p, (uint32_t)nbins, c->bin_total.p, c->stream);
     launch_bin_points(true, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_cursor.p,
                       c->bin_offsets.p, c->records.p, (uint32_t)c->records.cap, c->bin_total.p + 1,
-                      c->splats.p, c->splats.cap, c->stream);
+                      c->stream);
     launch_tile_resolve(c->records.p, (uint32_t)c->records.cap, c->bin_offsets.p, c->bin_total.p, nviews, vc, c->val.p,
                         c->packed_value, images, c->pitch, winners, c->P, c->stream);
     c->launches += 4;
@@ -532,7 +519,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->pts.release(); c->orig.release(); c->tag.release(); c->val.release(); c->mverts.release(); c->mtris.release();
   c->mtri_orig.release(); c->mslots.release(); c->bin_offsets.release(); c->bin_cursor.release();
-  c->bin_total.release(); c->records.release(); c->splats.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
+  c->bin_total.release(); c->records.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
   c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();

@@ -273,26 +273,22 @@ __device__ __forceinline__ Splat project_splat_point(const float4& p, const floa
   return f;
 }
 
-// SCATTER == false: project every (survivor, view), count records per (view, tile) and, when
-// the splat store is large enough (uniform decision from the device-side survivor count),
-// keep the projected splat {i0|j0, depth bits} so the second pass need not project again.
-// SCATTER == true: write the records (splats re-read from the store, or re-projected).
+// SCATTER == false: count records per (view, tile).  SCATTER == true: write them.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
 bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
            const uint32_t* __restrict__ counter, const float4* __restrict__ centres, int nviews,
            ViewConst vc, int ntx, int nt, uint32_t* __restrict__ counts,
            const uint32_t* __restrict__ offsets, uint4* __restrict__ rec, uint32_t rec_cap,
-           uint32_t* __restrict__ overflow, uint2* __restrict__ splats, size_t splat_cap) {
+           uint32_t* __restrict__ overflow) {
   extern __shared__ float4 s_c[];
   for (int i = threadIdx.x; i < nviews; i += blockDim.x) s_c[i] = centres[i];
   __syncthreads();
   const uint32_t count = *counter;
-  const bool stored = (size_t)count * (size_t)nviews <= splat_cap;  // same answer in both passes
   const float half = 0.5f * (float)(vc.s - 1);
-  auto emit = [&](int i0, int j0, uint32_t zbits, int v, uint32_t tag) {
-    const int tx0 = max(i0, 0) / kTile, tx1 = min(i0 + vc.s - 1, vc.W - 1) / kTile;
-    const int ty0 = max(j0, 0) / kTile, ty1 = min(j0 + vc.s - 1, vc.H - 1) / kTile;
+  auto emit = [&](const Splat& f, int v, uint32_t tag) {
+    const int tx0 = max(f.i0, 0) / kTile, tx1 = min(f.i0 + vc.s - 1, vc.W - 1) / kTile;
+    const int ty0 = max(f.j0, 0) / kTile, ty1 = min(f.j0 + vc.s - 1, vc.H - 1) / kTile;
     for (int ty = ty0; ty <= ty1; ty++)
       for (int tx = tx0; tx <= tx1; tx++) {
         const uint32_t bin = (uint32_t)v * nt + ty * ntx + tx;
@@ -300,52 +296,25 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
         if (SCATTER) {
           const uint32_t pos = offsets[bin] + slot;
           if (pos < rec_cap)
-            rec[pos] = make_uint4((uint32_t)(i0 + 32768) | ((uint32_t)(j0 + 32768) << 16), zbits, tag, 0u);
+            rec[pos] = make_uint4((uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16), f.zbits, tag, 0u);
           else
             *overflow = 1u;
         }
       }
   };
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
-    if (SCATTER && stored) {
-      const uint32_t tag = ctag[t];
-      int v = 0;
-      for (; v + 3 < nviews; v += 4) {  // four independent loads in flight
-        uint2 e[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) e[k] = splats[(size_t)(v + k) * count + t];
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (e[k].y != 0xFFFFFFFFu)
-            emit((int)(e[k].x & 0xFFFFu) - 32768, (int)(e[k].x >> 16) - 32768, e[k].y, v + k, tag);
-      }
-      for (; v < nviews; v++) {
-        const uint2 e = splats[(size_t)v * count + t];
-        if (e.y != 0xFFFFFFFFu) emit((int)(e.x & 0xFFFFu) - 32768, (int)(e.x >> 16) - 32768, e.y, v, tag);
-      }
-      continue;
-    }
     const float4 p = cpts[t];
     const uint32_t tag = SCATTER ? ctag[t] : 0u;
     int v = 0;
     for (; v + 1 < nviews; v += 2) {  // two independent projections in flight
       const Splat f0 = project_splat_point(p, s_c[v], vc, half);
       const Splat f1 = project_splat_point(p, s_c[v + 1], vc, half);
-      if (!SCATTER && stored) {
-        splats[(size_t)v * count + t] =
-            make_uint2((uint32_t)(f0.i0 + 32768) | ((uint32_t)(f0.j0 + 32768) << 16), f0.ok ? f0.zbits : 0xFFFFFFFFu);
-        splats[(size_t)(v + 1) * count + t] =
-            make_uint2((uint32_t)(f1.i0 + 32768) | ((uint32_t)(f1.j0 + 32768) << 16), f1.ok ? f1.zbits : 0xFFFFFFFFu);
-      }
-      if (f0.ok) emit(f0.i0, f0.j0, f0.zbits, v, tag);
-      if (f1.ok) emit(f1.i0, f1.j0, f1.zbits, v + 1, tag);
+      if (f0.ok) emit(f0, v, tag);
+      if (f1.ok) emit(f1, v + 1, tag);
     }
     if (v < nviews) {
       const Splat f0 = project_splat_point(p, s_c[v], vc, half);
-      if (!SCATTER && stored)
-        splats[(size_t)v * count + t] =
-            make_uint2((uint32_t)(f0.i0 + 32768) | ((uint32_t)(f0.j0 + 32768) << 16), f0.ok ? f0.zbits : 0xFFFFFFFFu);
-      if (f0.ok) emit(f0.i0, f0.j0, f0.zbits, v, tag);
+      if (f0.ok) emit(f0, v, tag);
     }
   }
 }
@@ -521,17 +490,15 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
 void launch_bin_points(bool scatter, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
                        const float4* centres, int nviews, const ViewConst& vc, uint32_t* counts,
                        const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t* overflow,
-                       uint2* splats, size_t splat_cap, cudaStream_t st) {
+                       cudaStream_t st) {
   if (nviews == 0) return;
   const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
   if (scatter)
     bin_kernel<true><<<148 * 16, 256, sizeof(float4) * nviews, st>>>(
-        cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts, offsets, rec, rec_cap, overflow,
-        splats, splat_cap);
+        cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts, offsets, rec, rec_cap, overflow);
   else
     bin_kernel<false><<<148 * 16, 256, sizeof(float4) * nviews, st>>>(
-        cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts, offsets, rec, rec_cap, overflow,
-        splats, splat_cap);
+        cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts, offsets, rec, rec_cap, overflow);
 }
 
 int tiles_per_view(int W, int H) { return ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile); }
