@@ -99,6 +99,8 @@ struct DevBuf {
 struct nmi_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // the frame warps run here, concurrently with the render stage
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_params = nullptr;  // completion of the last H2D from h_params
   bool params_in_flight = false;
@@ -431,6 +433,13 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   const uint32_t* d_index = reinterpret_cast<const uint32_t*>(c->params.p + off_i);
 
   memcpy(c->Twc, Twc, sizeof(float) * 16);
+  // fork: the warps of the camera frame (issue-bound) overlap the render stage (atomic- and
+  // latency-bound) on a second stream; both only need the uploaded parameters
+  CK(cudaEventRecord(c->ev_fork, c->stream));
+  CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  launch_warp(c->frame.p, c->cam.W, c->cam.H, d_minv, nwl, c->warps.p, c->pitch, c->stream2);
+  c->launches++;
+  CK(cudaEventRecord(c->ev_join, c->stream2));
   if (int rc = cull_model(c, vc, Twc, margin)) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
   for (int v0 = 0; v0 < nvl; v0 += group) {
@@ -441,8 +450,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   // stage events: [1] = project + resolve of all view groups (interleaved), [2] = 0
   if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
   if (c->timed) CK(cudaEventRecord(c->ev[3], c->stream));
-  launch_warp(c->frame.p, c->cam.W, c->cam.H, d_minv, nwl, c->warps.p, c->pitch, c->stream);
-  c->launches++;
+  CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join: the warps are done
   if (c->timed) CK(cudaEventRecord(c->ev[4], c->stream));
 
   HistArgs a{};
@@ -498,6 +506,9 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   nmi_ctx* c = new nmi_ctx();
   c->device = device;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto& e : c->ev) CK(cudaEventCreate(&e));
   CK(cudaEventCreateWithFlags(&c->ev_params, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_feedback, cudaEventDisableTiming));
@@ -530,6 +541,9 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (c->ev_params) cudaEventDestroy(c->ev_params);
   if (c->ev_feedback) cudaEventDestroy(c->ev_feedback);
   if (c->h_feedback) cudaFreeHost(c->h_feedback);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
