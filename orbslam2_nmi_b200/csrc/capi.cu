@@ -28,12 +28,12 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
                           unsigned long long* zbuf, size_t P, uint32_t max_points, cudaStream_t st);
 
 void launch_scan_counts(uint32_t* block_counts, uint32_t nblocks, uint32_t* counter, cudaStream_t st);
-void launch_bin_points(bool scatter, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
+void launch_bin_points(int mode, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
                        const float4* centres, int nviews, const ViewConst& vc, uint32_t* counts,
-                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t* overflow,
-                       cudaStream_t st);
+                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t bin_cap,
+                       uint32_t* overflow, cudaStream_t st);
 int tiles_per_view(int W, int H);
-void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, const uint32_t* offsets, const uint32_t* total, int nviews,
+void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, uint32_t bin_cap, const uint32_t* offsets, uint32_t* total, int nviews,
                          const ViewConst& vc, const uint8_t* val, bool packed, uint8_t* images,
                          size_t pitch, uint32_t* winners, size_t P, cudaStream_t st);
 
@@ -128,8 +128,10 @@ struct nmi_ctx {
   size_t n_tris = 0;  // > 0: the model is a mesh, else a point cloud
 
   // feedback from the previous search, copied to pinned host memory asynchronously:
-  // [0] survivors, [1] records of the last view group, [2] overflow flag, [3] views of that group
+  // [0] survivors, [1] records of the last view group, [2] overflow flag, [3] fullest bin,
+  // [4] views of that group (host-written)
   uint32_t* h_feedback = nullptr;
+  uint32_t bin_cap = 0;  // > 0: this search bins in a single pass into bins of that capacity
   cudaEvent_t ev_feedback = nullptr;
   bool feedback_pending = false;
   bool force_conservative = false;
@@ -217,13 +219,35 @@ int vc_point_size(const nmi_camera& cam) {
 // bin_scatter never writes past the buffer; an overflow raises a flag that every
 // synchronous entry point turns into an error (never a silently wrong render).
 int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
+  const size_t tiles = (size_t)tiles_per_view(c->cam.W, c->cam.H);
+  const bool fb = c->h_feedback && !c->force_conservative && c->feedback_pending &&
+                  cudaEventQuery(c->ev_feedback) == cudaSuccess && c->h_feedback[4] > 0 &&
+                  c->h_feedback[2] == 0;
+  CK(c->bin_total.reserve(4));
+  c->bin_cap = 0;
+  // (a) single pass: every bin gets the capacity of the previous search's fullest bin (+25 %)
+  if (fb && c->h_feedback[3] > 0 && nviews <= kMaxViewsPerLaunch) {
+    size_t cap = (size_t)c->h_feedback[3] + c->h_feedback[3] / 4 + 32;
+    cap = (cap + 7) / 8 * 8;
+    const size_t want = tiles * (size_t)nviews * cap;
+    if (want <= (4ull << 30) / sizeof(uint4) && want < 0xFFFFFFFFull) {
+      if (want > c->records.cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(c->records.reserve(want));
+      }
+      c->bin_cap = (uint32_t)cap;
+      *group = nviews;
+      CK(c->bin_cursor.reserve(tiles * (size_t)nviews));
+      CK(cudaMemsetAsync(c->bin_total.p, 0, 4 * sizeof(uint32_t), c->stream));
+      return NMI_OK;
+    }
+  }
+  // (b) two-pass counting sort; record buffer sized for any pose (1.5 records per point and
+  // view) or, in steady state, from what the previous search really produced (x1.5)
   const size_t cap_records = (2ull << 30) / sizeof(uint4);
-  size_t per_view = (size_t)((double)c->n_pts * 1.5) + 65536;  // safe for any pose
-  // steady state: size from what the previous search really produced (x1.5), so that all the
-  // views of a search usually fit one group; an overflow is detected, never silent
-  if (c->h_feedback && !c->force_conservative && c->feedback_pending &&
-      cudaEventQuery(c->ev_feedback) == cudaSuccess && c->h_feedback[3] > 0 && c->h_feedback[2] == 0) {
-    const size_t seen = (size_t)c->h_feedback[1] / c->h_feedback[3];
+  size_t per_view = (size_t)((double)c->n_pts * 1.5) + 65536;
+  if (fb && c->h_feedback[1] > 0) {  // ([1] is only filled by a two-pass search)
+    const size_t seen = (size_t)c->h_feedback[1] / c->h_feedback[4];
     const size_t guess = seen + seen / 2 + 65536;
     if (guess < per_view) per_view = guess;
   }
@@ -232,17 +256,16 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   if (g > nviews) g = nviews;
   if (g > kMaxViewsPerLaunch) g = kMaxViewsPerLaunch;
   *group = g;
-  const size_t nbins = (size_t)g * tiles_per_view(c->cam.W, c->cam.H);
+  const size_t nbins = (size_t)g * tiles;
   CK(c->bin_offsets.reserve(nbins));
   CK(c->bin_cursor.reserve(nbins));
-  CK(c->bin_total.reserve(2));
   size_t want = per_view * (size_t)g;
   if (want > cap_records) want = cap_records;
   if (want > c->records.cap) {
     CK(cudaStreamSynchronize(c->stream));
     CK(c->records.reserve(want));
   }
-  CK(cudaMemsetAsync(c->bin_total.p, 0, 2 * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(c->bin_total.p, 0, 4 * sizeof(uint32_t), c->stream));
   return NMI_OK;
 }
 
@@ -286,22 +309,33 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
   if (!c->n_tris && vc.s <= 32) {
     // point cloud: binned tile renderer, no global z-buffer
     const size_t nbins = (size_t)nviews * tiles_per_view(vc.W, vc.H);
-    CK(cudaMemsetAsync(c->bin_offsets.p, 0, nbins * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(c->bin_cursor.p, 0, nbins * sizeof(uint32_t), c->stream));
-    launch_bin_points(false, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_offsets.p,
-                      nullptr, nullptr, 0, nullptr, c->stream);
-    launch_scan_counts(c->bin_offsets.p, (uint32_t)nbins, c->bin_total.p, c->stream);
-    launch_bin_points(true, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_cursor.p,
-                      c->bin_offsets.p, c->records.p, (uint32_t)c->records.cap, c->bin_total.p + 1,
-                      c->stream);
-    launch_tile_resolve(c->records.p, (uint32_t)c->records.cap, c->bin_offsets.p, c->bin_total.p, nviews, vc, c->val.p,
-                        c->packed_value, images, c->pitch, winners, c->P, c->stream);
-    c->launches += 4;
+    if (c->bin_cap) {
+      // steady state: the fullest bin of the previous search bounds every bin -> one pass
+      launch_bin_points(2, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_cursor.p,
+                        nullptr, c->records.p, (uint32_t)c->records.cap, c->bin_cap, c->bin_total.p + 1,
+                        c->stream);
+      launch_tile_resolve(c->records.p, (uint32_t)c->records.cap, c->bin_cap, c->bin_cursor.p,
+                          c->bin_total.p, nviews, vc, c->val.p, c->packed_value, images, c->pitch, winners,
+                          c->P, c->stream);
+      c->launches += 2;
+    } else {
+      CK(cudaMemsetAsync(c->bin_offsets.p, 0, nbins * sizeof(uint32_t), c->stream));
+      launch_bin_points(0, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_offsets.p,
+                        nullptr, nullptr, 0, 0, nullptr, c->stream);
+      launch_scan_counts(c->bin_offsets.p, (uint32_t)nbins, c->bin_total.p, c->stream);
+      launch_bin_points(1, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_cursor.p,
+                        c->bin_offsets.p, c->records.p, (uint32_t)c->records.cap, 0, c->bin_total.p + 1,
+                        c->stream);
+      launch_tile_resolve(c->records.p, (uint32_t)c->records.cap, 0, c->bin_offsets.p, c->bin_total.p,
+                          nviews, vc, c->val.p, c->packed_value, images, c->pitch, winners, c->P, c->stream);
+      c->launches += 4;
+    }
     if (c->h_feedback) {  // survivors / records / overflow of this group -> pinned host words
       CK(cudaMemcpyAsync(c->h_feedback, c->counter.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaMemcpyAsync(c->h_feedback + 1, c->bin_total.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+      CK(cudaMemcpyAsync(c->h_feedback + 1, c->bin_total.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                          c->stream));
-      c->h_feedback[3] = (uint32_t)nviews;
+      c->h_feedback[4] = (uint32_t)nviews;
       CK(cudaEventRecord(c->ev_feedback, c->stream));
       c->feedback_pending = true;
     }
@@ -512,8 +546,8 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   for (auto& e : c->ev) CK(cudaEventCreate(&e));
   CK(cudaEventCreateWithFlags(&c->ev_params, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_feedback, cudaEventDisableTiming));
-  CK(cudaMallocHost(&c->h_feedback, 4 * sizeof(uint32_t)));
-  memset(c->h_feedback, 0, 4 * sizeof(uint32_t));
+  CK(cudaMallocHost(&c->h_feedback, 8 * sizeof(uint32_t)));
+  memset(c->h_feedback, 0, 8 * sizeof(uint32_t));
   CK(c->counter.reserve(1));
   CK(c->key.reserve(1));
   CK(c->one_score.reserve(1));

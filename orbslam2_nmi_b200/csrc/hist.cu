@@ -373,9 +373,12 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
 
 template <int NW>
 __device__ __forceinline__ void load_words(uint32_t (&dst)[NW], const uint8_t* p) {
-  if (NW == 4) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p);
-    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[NW - 1] = v.w;
+  if (NW % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < NW / 4; j++) {
+      const uint4 v = *reinterpret_cast<const uint4*>(p + 16 * j);
+      dst[4 * j] = v.x; dst[4 * j + 1] = v.y; dst[4 * j + 2] = v.z; dst[4 * j + 3] = v.w;
+    }
   } else {
     const uint2 v = *reinterpret_cast<const uint2*>(p);
     dst[0] = v.x; dst[NW - 1] = v.y;
@@ -383,9 +386,12 @@ __device__ __forceinline__ void load_words(uint32_t (&dst)[NW], const uint8_t* p
 }
 template <int NW>
 __device__ __forceinline__ void ldg_words(uint32_t (&dst)[NW], const uint8_t* p) {
-  if (NW == 4) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[NW - 1] = v.w;
+  if (NW % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < NW / 4; j++) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + 16 * j));
+      dst[4 * j] = v.x; dst[4 * j + 1] = v.y; dst[4 * j + 2] = v.z; dst[4 * j + 3] = v.w;
+    }
   } else {
     const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
     dst[0] = v.x; dst[NW - 1] = v.y;

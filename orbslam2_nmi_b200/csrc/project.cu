@@ -273,14 +273,17 @@ __device__ __forceinline__ Splat project_splat_point(const float4& p, const floa
   return f;
 }
 
-// SCATTER == false: count records per (view, tile).  SCATTER == true: write them.
-template <bool SCATTER>
+// MODE 0: count records per (view, tile).  MODE 1: write them at offsets[bin] + slot (second
+// pass of the counting sort).  MODE 2: single pass into fixed-capacity bins (capacity known
+// from the previous search; a bin that fills up raises the overflow flag).
+template <int MODE>
 __global__ void __launch_bounds__(256)
 bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
            const uint32_t* __restrict__ counter, const float4* __restrict__ centres, int nviews,
            ViewConst vc, int ntx, int nt, uint32_t* __restrict__ counts,
            const uint32_t* __restrict__ offsets, uint4* __restrict__ rec, uint32_t rec_cap,
-           uint32_t* __restrict__ overflow) {
+           uint32_t bin_cap, uint32_t* __restrict__ overflow) {
+  constexpr bool SCATTER = MODE != 0;
   extern __shared__ float4 s_c[];
   for (int i = threadIdx.x; i < nviews; i += blockDim.x) s_c[i] = centres[i];
   __syncthreads();
@@ -293,10 +296,16 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
       for (int tx = tx0; tx <= tx1; tx++) {
         const uint32_t bin = (uint32_t)v * nt + ty * ntx + tx;
         const uint32_t slot = atomicAdd(&counts[bin], 1u);
-        if (SCATTER) {
+        if (MODE == 1) {
           const uint32_t pos = offsets[bin] + slot;
           if (pos < rec_cap)
             rec[pos] = make_uint4((uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16), f.zbits, tag, 0u);
+          else
+            *overflow = 1u;
+        } else if (MODE == 2) {
+          if (slot < bin_cap)
+            rec[(size_t)bin * bin_cap + slot] =
+                make_uint4((uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16), f.zbits, tag, 0u);
           else
             *overflow = 1u;
         }
@@ -321,8 +330,9 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
 
 template <bool PACKED>
 __global__ void __launch_bounds__(kTileThreads)
-tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, const uint32_t* __restrict__ offsets,
-                    const uint32_t* __restrict__ total, int ntx, int nt, int W, int H, int S,
+tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bin_cap,
+                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ total, int ntx, int nt,
+                    int W, int H, int S,
                     const uint8_t* __restrict__ val, uint8_t* __restrict__ images, size_t pitch,
                     uint32_t* __restrict__ winners, size_t P) {
   __shared__ uint32_t s_depth[kTileCells];
@@ -334,13 +344,21 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, const uint3
   const int tid = threadIdx.x;
   // clamp to the record buffer: after an overflow (flagged by bin_scatter, the search is then
   // redone) the offsets may point past it
-  const uint32_t start = min(offsets[bin], rec_cap);
-  const uint32_t end = min(bin + 1 < gridDim.x ? offsets[bin + 1] : *total, rec_cap);
+  // bin_cap > 0: fixed-capacity bins, `offsets` holds the fill counts; else counting-sort offsets
+  size_t start, end;
+  if (bin_cap) {
+    start = (size_t)bin * bin_cap;
+    end = start + min(offsets[bin], bin_cap);
+  } else {
+    start = min(offsets[bin], rec_cap);
+    end = min(bin + 1 < gridDim.x ? offsets[bin + 1] : *total, rec_cap);
+  }
+  if (tid == 0) atomicMax(total + 2, (uint32_t)(end - start));  // feedback: fullest bin
   for (int q = tid; q < kTileCells; q += kTileThreads) { s_depth[q] = 0xFFFFFFFFu; s_tag[q] = 0xFFFFFFFFu; }
   __syncthreads();
   if (S == 3) {
     // the reference's glPointSize(3): fully unrolled 3x3, one range test per row / column
-    for (uint32_t r = start + tid; r < end; r += kTileThreads) {  // pass 1: minimum depth per cell
+    for (size_t r = start + tid; r < end; r += kTileThreads) {  // pass 1: minimum depth per cell
       const uint4 e = rec[r];
       const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
       const int q = lj * kTile + li;
@@ -353,7 +371,7 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, const uint3
       }
     }
     __syncthreads();
-    for (uint32_t r = start + tid; r < end; r += kTileThreads) {  // pass 2: min tag at the min depth
+    for (size_t r = start + tid; r < end; r += kTileThreads) {  // pass 2: min tag at the min depth
       const uint4 e = rec[r];
       const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
       const int q = lj * kTile + li;
@@ -368,7 +386,7 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, const uint3
     }
   } else {
     // pass 1: minimum depth per cell
-    for (uint32_t r = start + tid; r < end; r += kTileThreads) {
+    for (size_t r = start + tid; r < end; r += kTileThreads) {
       const uint4 e = rec[r];
       const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
       for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
@@ -376,7 +394,7 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, const uint3
     }
     __syncthreads();
     // pass 2: lowest tie-break word among the fragments at the minimum depth
-    for (uint32_t r = start + tid; r < end; r += kTileThreads) {
+    for (size_t r = start + tid; r < end; r += kTileThreads) {
       const uint4 e = rec[r];
       const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
       for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
@@ -486,34 +504,40 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
                                                                       centres, nviews, vc, zbuf, P);
 }
 
-// counts / offsets: [nviews * nt] (+ the scan's total in *total); rec: rec_cap records
-void launch_bin_points(bool scatter, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
+// mode 0 = count, 1 = scatter at offsets (two-pass counting sort), 2 = single pass into
+// fixed-capacity bins.  counts / offsets: [nviews * tiles]; rec: rec_cap records.
+void launch_bin_points(int mode, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
                        const float4* centres, int nviews, const ViewConst& vc, uint32_t* counts,
-                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t* overflow,
-                       cudaStream_t st) {
+                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t bin_cap,
+                       uint32_t* overflow, cudaStream_t st) {
   if (nviews == 0) return;
   const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
-  if (scatter)
-    bin_kernel<true><<<148 * 16, 256, sizeof(float4) * nviews, st>>>(
-        cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts, offsets, rec, rec_cap, overflow);
+  const dim3 grid(148 * 16), block(256);
+  const size_t smem = sizeof(float4) * nviews;
+  if (mode == 0)
+    bin_kernel<0><<<grid, block, smem, st>>>(cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts,
+                                             offsets, rec, rec_cap, bin_cap, overflow);
+  else if (mode == 1)
+    bin_kernel<1><<<grid, block, smem, st>>>(cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts,
+                                             offsets, rec, rec_cap, bin_cap, overflow);
   else
-    bin_kernel<false><<<148 * 16, 256, sizeof(float4) * nviews, st>>>(
-        cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts, offsets, rec, rec_cap, overflow);
+    bin_kernel<2><<<grid, block, smem, st>>>(cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts,
+                                             offsets, rec, rec_cap, bin_cap, overflow);
 }
 
 int tiles_per_view(int W, int H) { return ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile); }
 
-void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, const uint32_t* offsets, const uint32_t* total, int nviews,
+void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, uint32_t bin_cap, const uint32_t* offsets, uint32_t* total, int nviews,
                          const ViewConst& vc, const uint8_t* val, bool packed, uint8_t* images,
                          size_t pitch, uint32_t* winners, size_t P, cudaStream_t st) {
   if (nviews == 0) return;
   const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
   const unsigned grid = (unsigned)nviews * ntx * nty;
   if (packed)
-    tile_resolve_kernel<true><<<grid, kTileThreads, 0, st>>>(rec, rec_cap, offsets, total, ntx, ntx * nty, vc.W, vc.H,
+    tile_resolve_kernel<true><<<grid, kTileThreads, 0, st>>>(rec, rec_cap, bin_cap, offsets, total, ntx, ntx * nty, vc.W, vc.H,
                                                               vc.s, val, images, pitch, winners, P);
   else
-    tile_resolve_kernel<false><<<grid, kTileThreads, 0, st>>>(rec, rec_cap, offsets, total, ntx, ntx * nty, vc.W, vc.H,
+    tile_resolve_kernel<false><<<grid, kTileThreads, 0, st>>>(rec, rec_cap, bin_cap, offsets, total, ntx, ntx * nty, vc.W, vc.H,
                                                                vc.s, val, images, pitch, winners, P);
 }
 
