@@ -239,7 +239,7 @@ project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict
 //                fragments at the minimum depth (== the packed 64-bit key minimum) -- and
 //                the CTA, sole owner of the tile, stores the finished u8 pixels directly.
 // No global z-buffer, no global atomics on pixels, no separate resolve pass.
-constexpr int kTile = 32;
+constexpr int kTile = 32;  // (bin_kernel shifts by 5)
 constexpr int kTileCells = kTile * kTile;
 constexpr int kTileThreads = 128;
 
@@ -289,27 +289,35 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
   __syncthreads();
   const uint32_t count = *counter;
   const float half = 0.5f * (float)(vc.s - 1);
+  const int W = vc.W, H = vc.H, S = vc.s;
+  auto emit1 = [&](uint32_t bin, uint32_t ij, uint32_t zbits, uint32_t tag) {
+    const uint32_t slot = atomicAdd(&counts[bin], 1u);
+    if (MODE == 1) {
+      const uint32_t pos = offsets[bin] + slot;
+      if (pos < rec_cap)
+        rec[pos] = make_uint4(ij, zbits, tag, 0u);
+      else
+        *overflow = 1u;
+    } else if (MODE == 2) {
+      if (slot < bin_cap)
+        rec[(size_t)bin * bin_cap + slot] = make_uint4(ij, zbits, tag, 0u);
+      else
+        *overflow = 1u;
+    }
+  };
+  // a splat of s <= 32 pixels touches at most 2 x 2 tiles (usually one)
   auto emit = [&](const Splat& f, int v, uint32_t tag) {
-    const int tx0 = max(f.i0, 0) / kTile, tx1 = min(f.i0 + vc.s - 1, vc.W - 1) / kTile;
-    const int ty0 = max(f.j0, 0) / kTile, ty1 = min(f.j0 + vc.s - 1, vc.H - 1) / kTile;
-    for (int ty = ty0; ty <= ty1; ty++)
-      for (int tx = tx0; tx <= tx1; tx++) {
-        const uint32_t bin = (uint32_t)v * nt + ty * ntx + tx;
-        const uint32_t slot = atomicAdd(&counts[bin], 1u);
-        if (MODE == 1) {
-          const uint32_t pos = offsets[bin] + slot;
-          if (pos < rec_cap)
-            rec[pos] = make_uint4((uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16), f.zbits, tag, 0u);
-          else
-            *overflow = 1u;
-        } else if (MODE == 2) {
-          if (slot < bin_cap)
-            rec[(size_t)bin * bin_cap + slot] =
-                make_uint4((uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16), f.zbits, tag, 0u);
-          else
-            *overflow = 1u;
-        }
-      }
+    const int xa = max(f.i0, 0) >> 5, xb = min(f.i0 + S - 1, W - 1) >> 5;
+    const int ya = max(f.j0, 0) >> 5, yb = min(f.j0 + S - 1, H - 1) >> 5;
+    const uint32_t ij = (uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16);
+    const uint32_t row_a = (uint32_t)v * nt + ya * ntx;
+    emit1(row_a + xa, ij, f.zbits, tag);
+    if (xb != xa) emit1(row_a + xb, ij, f.zbits, tag);
+    if (yb != ya) {
+      const uint32_t row_b = (uint32_t)v * nt + yb * ntx;
+      emit1(row_b + xa, ij, f.zbits, tag);
+      if (xb != xa) emit1(row_b + xb, ij, f.zbits, tag);
+    }
   };
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
     const float4 p = cpts[t];
