@@ -113,11 +113,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
-// Ask the TMA engine to pull a range into L2 ahead of the real load (no shared memory needed).
-__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-
 // ---- entropy pieces (NMI.cu:240-266) ---------------------------------------
 __device__ __forceinline__ float term(uint32_t c, float L) {
   if (c == 0) return 0.0f;
@@ -457,15 +452,6 @@ joint_hist_score_kernel(const HistArgs a) {
     mbar_expect_tx(&sm.full[st], 2 * bytes);
     tma_load_1d(sm.rbuf[st], rimg + off, bytes, &sm.full[st]);
     tma_load_1d(sm.wbuf[st], wimg + off, bytes, &sm.full[st]);
-    // and warm L2 for the chunk one ring-length further on, so that its load is an L2 hit
-    const int ahead = ck + kStages;
-    if (ahead < nchunks) {
-      const uint32_t off2 = (uint32_t)ahead * kChunk;
-      uint32_t b2 = npix - off2;
-      b2 = b2 > (uint32_t)kChunk ? (uint32_t)kChunk : ((b2 + 15u) & ~15u);
-      tma_prefetch_l2(rimg + off2, b2);
-      tma_prefetch_l2(wimg + off2, b2);
-    }
   };
 
   if (!INLINE_PRODUCER && warp == NWARPS) {
