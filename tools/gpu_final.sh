@@ -10,8 +10,8 @@ python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err;
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_short.json 2> gpurun_out/bench_short.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-# full captures of the second search (first one uses the conservative 8-group sizing: 36 render-stage launches)
+# full captures of one steady-state search (profile_run.py brackets its last search with cudaProfilerStart/Stop)
 python tools/profile_run.py 0 > gpurun_out/prof_plain.log 2>&1 && \
-ncu --set full --import-source on --clock-control none -k regex:"cull_|bin_kernel|tile_resolve|warp_kernel" -s 36 -c 8 -f -o gpurun_out/prof_render python tools/profile_run.py 0 > gpurun_out/prof_ncu_render.log 2>&1 && \
-ncu --set full --import-source on --clock-control none -k regex:"joint_hist" -s 1 -c 1 -f -o gpurun_out/prof_hist python tools/profile_run.py 0 > gpurun_out/prof_ncu_hist.log 2>&1
+ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"cull_|bin_kernel|tile_resolve|warp_kernel|argmax" -c 12 -f -o gpurun_out/prof_render python tools/profile_run.py 0 > gpurun_out/prof_ncu_render.log 2>&1 && \
+ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"joint_hist" -c 1 -f -o gpurun_out/prof_hist python tools/profile_run.py 0 > gpurun_out/prof_ncu_hist.log 2>&1
 tail -1 gpurun_out/prof_ncu_render.log; tail -1 gpurun_out/prof_ncu_hist.log
