@@ -13,6 +13,7 @@
 #include "compat/ioData.hpp"
 #include "compat/kernel.cuh"
 #include "compat/localization.hpp"
+#include "compat/nmi_outputs.hpp"
 
 #define EXPECT(c)                                                     \
   do {                                                                \
@@ -21,6 +22,54 @@
       return 1;                                                       \
     }                                                                 \
   } while (0)
+
+// SaveFullTrajectory / overlay writer (System.cc:514-599, ioData.cpp:262-285)
+static int output_checks(const char* dir) {
+  using namespace nmi_compat;
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  float q[4];
+  rotation_to_quaternion(I, q);
+  EXPECT(q[0] == 0 && q[1] == 0 && q[2] == 0 && q[3] == 1);
+  const double Rz180[9] = {-1, 0, 0, 0, -1, 0, 0, 0, 1};  // trace < 0: pivot branch
+  rotation_to_quaternion(Rz180, q);
+  EXPECT(q[0] == 0 && q[1] == 0 && q[2] == 1 && q[3] == 0);
+  const double c = std::cos(0.5), sn = std::sin(0.5);
+  const double Rx[9] = {1, 0, 0, 0, c, -sn, 0, sn, c};
+  rotation_to_quaternion(Rx, q);
+  EXPECT(std::fabs(q[0] - (float)std::sin(0.25)) < 1e-7f && std::fabs(q[3] - (float)std::cos(0.25)) < 1e-7f);
+
+  TrajectoryRecorder tr;
+  float T[16] = {1, 0, 0, 1.5f, 0, 1, 0, -2.25f, 0, 0, 1, 3, 0, 0, 0, 1};
+  tr.add(7, 12.5, T, true);
+  nmi_reloc_result r{};
+  for (int i = 0; i < 16; i++) r.Twc[i] = T[i];
+  r.Twc[3] = 1.75f;
+  r.relocalized = 1;
+  r.n_prev = 1;
+  for (int i = 0; i < 16; i++) r.prev_Twc[0][i] = T[i];
+  tr.add(8, 12.6, r, true);
+  r.relocalized = 0;
+  r.failed = 1;
+  r.n_prev = 0;
+  tr.add(9, 12.7, r, true);
+  tr.add(10, 12.8, T, false);        // ordinary frame: no tag
+  tr.add(11, 12.9, T, false, true);  // lost: skipped
+  EXPECT(tr.size() == 5);
+  EXPECT(tr.SaveFullTrajectory(std::string(dir) + "/FrameTrajectory"));
+
+  const int W = 5, H = 3;  // 15-byte rows -> 1 pad byte
+  std::vector<uint8_t> img(W * H), syn(W * H);
+  for (int i = 0; i < W * H; i++) {
+    img[i] = (uint8_t)(10 + i);
+    syn[i] = (uint8_t)(100 + i);
+  }
+  EXPECT(saveOverlayBMP((std::string(dir) + "/overlay.bmp").c_str(), img.data(), syn.data(), W, H));
+  nmi_grid g{{3, 3, 3}, {3, 3, 3}, {0.2f, 0.2f, 0.5f}, {0.02f, 0.02f, 0.05f}};
+  const int32_t bs[3] = {0, 1, 2}, bw[3] = {2, 1, 0};
+  std::printf("NAME %s\n", overlay_name("res", 12, g, 0.25f, bs, bw).c_str());
+  std::printf("OUTPUTS OK\n");
+  return 0;
+}
 
 static int loader_checks(const char* obj, const char* bmp) {
   // loadOBJ (objloader.cpp:140-223): 2 triangles, un-indexed output in face order
@@ -193,6 +242,7 @@ static int gpu_checks(const char* yaml, const char* frame_raw, const char* twc_t
 }
 
 int main(int argc, char** argv) {
+  if (argc >= 3 && std::string(argv[1]) == "outputs") return output_checks(argv[2]);
   if (argc >= 4 && std::string(argv[1]) == "loaders") return loader_checks(argv[2], argv[3]);
   if (argc >= 5 && std::string(argv[1]) == "host") return host_checks(argv[2], argv[3], argv[4]);
   if (argc >= 5 && std::string(argv[1]) == "gpu") return gpu_checks(argv[2], argv[3], argv[4]);

@@ -110,6 +110,34 @@ def test_compat_obj_bmp_loaders(exe, tmp_path):
     assert res.returncode == 0 and "LOADERS OK" in res.stdout, res.stdout + res.stderr
 
 
+def test_compat_output_files(exe, tmp_path):
+    """FrameTrajectory*.txt tags / layout (System.cc:514-599) and the red/green overlay."""
+    import struct
+
+    res = subprocess.run([str(exe), "outputs", str(tmp_path)], capture_output=True, text=True)
+    assert res.returncode == 0 and "OUTPUTS OK" in res.stdout, res.stdout + res.stderr
+    lines = (tmp_path / "FrameTrajectory.txt").read_text().splitlines()
+    assert lines == [
+        "7 12.500000 KF 1.500000000 -2.250000000 3.000000000 0.000000000 0.000000000 0.000000000 1.000000000",
+        "8 12.600000 KF, NMI 1.750000000 -2.250000000 3.000000000 0.000000000 0.000000000 0.000000000 1.000000000",
+        "9 12.700000 KF, FAILED 1.750000000 -2.250000000 3.000000000 0.000000000 0.000000000 0.000000000 1.000000000",
+        "10 12.800000 1.500000000 -2.250000000 3.000000000 0.000000000 0.000000000 0.000000000 1.000000000",
+    ]
+    twc = (tmp_path / "FrameTrajectory_twc.txt").read_text()
+    assert twc.startswith("7 12.500000 KF\n[1, 0, 0, 1.5;\n 0, 1, 0, -2.25;\n 0, 0, 1, 3;\n 0, 0, 0, 1]\n")
+    assert "8 12.600000 KF, NMI\n//////////Previous Poses" + "\\" * 10 + "\n[1, 0, 0, 1.5;" in twc
+    assert "//////////Previous Poses End" + "\\" * 10 + "\n[1, 0, 0, 1.75;" in twc
+    assert "\n11 " not in twc
+    bmp = (tmp_path / "overlay.bmp").read_bytes()
+    assert bmp[:2] == b"BM" and struct.unpack_from("<I", bmp, 2)[0] == len(bmp) == 54 + 16 * 3
+    assert struct.unpack_from("<iiHH", bmp, 18) == (5, 3, 1, 24)
+    # first stored row is the image's bottom row (y = 2): B 0, G render, R camera
+    assert bmp[54:60] == bytes([0, 110, 20, 0, 111, 21]) and bmp[54 + 15] == 0
+    assert bmp[54 + 32:54 + 35] == bytes([0, 100, 10])  # top row stored last
+    name = [l for l in res.stdout.splitlines() if l.startswith("NAME ")][0][5:]
+    assert name == "res/0012_NMI_[0.25]_WzyxSzyx_[0,1,2,2,1,0]_grid_[3x3x3_3x3x3].bmp"
+
+
 def _loaded_cloud(d):
     """What loadXYZ produces (float64 parse, offset subtraction, float cast, /256, duplicate)."""
     raw = np.loadtxt(d / "cloud.xyz")
