@@ -7,7 +7,7 @@ python - <<PY
 import json
 try:
     d=json.load(open("gpurun_out/bench_quick_$f.json"))
-    print("$f", round(d["value"]), "evals/s e2e", round(d["e2e"]["value"]), {k: round(x,3) for k,x in d["stage_ms"].items()})
+    print("$f", round(d["value"]), "evals/s e2e", round(d["e2e"]["value"]), {k: round(x,3) for k,x in d["stage_ms"].items()}, "launches", d["gpu_launches"])
 except Exception as e:
     print("FAILED", e, open("gpurun_out/bench_quick_$f.err").read()[-400:])
 PY
