@@ -446,10 +446,19 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   // together (~64 MB of the 126 MB): the z-buffer is written, resolved and reset without
   // ever being streamed through HBM, and only `group` views of it exist.
   const size_t zb_view = c->P * sizeof(unsigned long long);
-  int group = (int)((64ull << 20) / (zb_view ? zb_view : 1));
+  static const size_t zb_budget = [] {  // bytes of z-buffer kept in flight (L2 is 126 MB)
+    const char* e = getenv("NMI_ZBUF_MB");
+    return (size_t)(e && atoi(e) > 0 ? atoi(e) : 64) << 20;
+  }();
+  int group = (int)(zb_budget / (zb_view ? zb_view : 1));
   if (group < 1) group = 1;
   if (group > nvl) group = nvl;
   if (group > kMaxViewsPerLaunch) group = kMaxViewsPerLaunch;
+  if (c->n_tris) {  // the mesh rasteriser gives every view of a group a lane: power-of-two groups
+    int p2 = 1;
+    while (p2 * 2 <= group && p2 < 32) p2 *= 2;
+    group = p2;
+  }
   const bool tiled = !c->n_tris && vc_point_size(c->cam) <= 32;
   if (tiled) {
     if (int rc = ensure_tile_buffers(c, nvl, &group)) return rc;
