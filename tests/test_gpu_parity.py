@@ -165,6 +165,26 @@ def test_all_zero_scores_pick_first(searcher, oracle):
     assert res.best_index == 0 and res.best_score == 0.0
 
 
+@pytest.mark.parametrize("size", [1.0, 2.0, 5.0, 32.0, 40.0])
+def test_point_sizes(searcher, oracle, size):
+    """NMI.Render.PointSize other than the default 3 (rendering.hpp:307): generic s x s splats
+    in the tile renderer (s <= 32: up to 2 x 2 tiles per splat) and the global z-buffer path
+    for larger ones; twice, so the second search takes the single-pass bins."""
+    sc = synth.make_scene("tiny", n_points=3000)
+    sc.point_size = size
+    g = Grid.make((2, 1, 2), (1, 2, 1), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    frame = synth.frame_textured(sc.W, sc.H, seed=5)
+    searcher.set_scene(sc)
+    searcher.set_frame(frame)
+    scores, renders, _ = oracle.search_points(sc, sc.Twc, g, sc.xyzi, frame, keep_images=True)
+    for _ in range(2):
+        res = searcher.search(sc.Twc, g, want_scores=True)
+        for s in range(g.n_synth):
+            assert np.array_equal(searcher.get_render(s), renders[s]), f"render {s} differs at size {size}"
+        assert_scores_close(res.scores, scores)
+        assert res.best_index == oracle.argmax(scores)[0]
+
+
 # ------------------------------------------------------------------ planted pose ----
 def test_planted_pose_recovered(searcher, oracle):
     sc = synth.make_scene("small")
@@ -308,6 +328,25 @@ def test_relocalize_matches_oracle_driver(searcher, oracle, threshold, dist):
 
 
 # ---------------------------------------------------------------- mesh model (C3) ----
+@pytest.mark.parametrize("nS", [(1, 1, 1), (3, 1, 1), (3, 3, 1), (3, 3, 2), (4, 3, 3)])
+def test_mesh_view_group_widths(searcher, oracle, nS):
+    """The mesh rasteriser gives every view of a group a lane (1, 2, 4, ... 32 lanes per
+    triangle): every width, with ragged last groups, renders what the oracle renders."""
+    sc = synth.make_scene("tiny", n_points=10)
+    verts, tris = synth.make_mesh(90, 90, extent=24.0)
+    g = Grid.make(nS, (1, 1, 1), (0.3, 0.2, 0.5), (0.02, 0.02, 0.05))
+    searcher.set_camera(sc.W, sc.H, sc.fx, sc.fy, sc.cx, sc.cy, sc.zn, sc.zf, sc.point_size)
+    searcher.set_mesh(verts, tris)
+    searcher.set_frame(synth.frame_textured(sc.W, sc.H, seed=4))
+    searcher.search(sc.Twc, g)
+    for s in range(g.n_synth):
+        sx, sy, sz = s % nS[0], (s // nS[0]) % nS[1], s // (nS[0] * nS[1])
+        t = oracle.cell_translation(sc.Twc, g, sx, sy, sz)
+        win, img = oracle.render_mesh(sc, sc.Twc, t, verts, tris)
+        assert np.array_equal(searcher.get_winners(s), win), f"view {s} of {nS}"
+        assert np.array_equal(searcher.get_render(s), img)
+
+
 @pytest.mark.parametrize("bins", [256, 64])
 def test_mesh_search_matches_oracle(searcher, oracle, bins):
     """Rendering<1> path: triangle raster with the A.4 rules, 64-bin mode as in BASELINE config 3."""
