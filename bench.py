@@ -175,9 +175,10 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     build.build_cuda()
 
-    scene = synth.make_scene("C2")  # same seed on every rank: the cloud is replicated
+    scene = synth.make_scene("C2", extent=args.extent)  # same seed on every rank: the cloud is replicated
     frame = {"textured": synth.frame_textured, "uniform": synth.frame_uniform,
-             "constant": synth.frame_constant}[args.frame](scene.W, scene.H)
+             "constant": synth.frame_constant, "sky": synth.frame_sky,
+             "smooth": synth.frame_smooth}[args.frame](scene.W, scene.H)
     grid = grid_for(world)
     searcher = NmiSearcher(local)
     searcher.set_scene(scene)
@@ -320,7 +321,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="histogram kernel variant (0..7)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--frame", default="textured", choices=["textured", "uniform", "constant"])
+    ap.add_argument("--frame", default="textured", choices=["textured", "uniform", "constant", "sky", "smooth"])
+    ap.add_argument("--extent", type=float, default=None,
+                    help="half-width of the synthetic cloud in metres (default 40; small values leave "
+                         "render background, a stress case -- not the BASELINE workload)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

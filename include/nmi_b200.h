@@ -88,6 +88,14 @@ const char *nmi_last_error(void);
 /* CUDA stream (cudaStream_t) every kernel of this context is enqueued on.    */
 void *nmi_ctx_stream(nmi_ctx *ctx);
 int nmi_ctx_sync(nmi_ctx *ctx);
+/* Histogram kernel option, no reference counterpart (the reference's global-atomic
+ * histogram, NMI.cu:52-108, degrades the same way on flat images): where all 16
+ * pixels of a thread sit at the most frequent grey level of the render (or of the
+ * warp) they are kept out of the shared-memory joint histogram and counted in small
+ * side tables that the epilogue adds back.  0 never, 1 automatic (default; also
+ * $NMI_HIST_SKIP): when those two levels cover >= 1/6 of the pixels, 2 always.
+ * Results are bit-identical in every mode.                                     */
+int nmi_ctx_set_hist_skip(nmi_ctx *ctx, int mode);
 
 /* ---- model / camera / frame -------------------------------------------- */
 /* Rendering ctor + initVBO projection (rendering.hpp:167-236, 196-202).      */

@@ -91,6 +91,7 @@ SYMBOLS = [
     ("nmi_last_error", C.c_char_p, []),
     ("nmi_ctx_stream", _P, [_P]),
     ("nmi_ctx_sync", C.c_int, [_P]),
+    ("nmi_ctx_set_hist_skip", C.c_int, [_P, C.c_int]),
     ("nmi_set_camera", C.c_int, [_P, C.POINTER(Camera)]),
     ("nmi_set_points", C.c_int, [_P, _P, C.c_size_t]),
     ("nmi_set_points_device", C.c_int, [_P, _P, C.c_size_t]),

@@ -148,6 +148,14 @@ struct nmi_ctx {
   size_t zbuf_clean = 0;  // elements known to hold ~0
   DevBuf<uint8_t> renders, warps;
   DevBuf<float> scores;
+  // hot-bin skipping of the histogram kernel (hist.cu): sampled mode per image; hot[0..1] =
+  // largest mode count over the renders / warps, copied to h_feedback[5..6] after every
+  // search so the NEXT search knows whether to launch the build with the side tables
+  DevBuf<uint32_t> img_mode, hot;
+  int hist_skip = 1;  // 0 never, 1 automatic, 2 always ($NMI_HIST_SKIP, nmi_ctx_set_hist_skip)
+  cudaEvent_t ev_hot = nullptr;
+  bool hot_pending = false;
+  uint32_t hot_total = 0;  // pixels sampled per image when h_feedback[5..6] were written
   DevBuf<unsigned long long> key;
   DevBuf<unsigned char> params;  // device copy of the per-search parameter block
   unsigned char* h_params = nullptr;
@@ -495,7 +503,23 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   if (c->timed) CK(cudaEventRecord(c->ev[3], c->stream));
   CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join: the warps are done
   if (c->timed) CK(cudaEventRecord(c->ev[4], c->stream));
-
+  // hot-bin skipping: sample every image's dominant grey level (decides per pair inside the
+  // kernel); the build with the side tables is launched when the previous search saw levels
+  // that can reach the 1/6 threshold
+  const bool use_skip = c->hist_skip != 0 && f->bins == 256 && f->bg;
+  bool skipcap = c->hist_skip == 2;
+  if (use_skip) {
+    if (c->hist_skip == 1 && c->hot_pending && cudaEventQuery(c->ev_hot) == cudaSuccess)
+      skipcap = ((unsigned long long)c->h_feedback[5] + c->h_feedback[6]) * 6ull >= c->hot_total;
+    CK(c->img_mode.reserve((size_t)(nvl + nwl)));
+    CK(c->hot.reserve(2));
+    c->launches += launch_image_modes(c->renders.p, c->pitch, nvl, c->warps.p, c->pitch, nwl, (uint32_t)c->P,
+                                      c->img_mode.p, c->hot.p, c->stream);
+    CK(cudaMemcpyAsync(c->h_feedback + 5, c->hot.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev_hot, c->stream));
+    c->hot_pending = true;
+    c->hot_total = image_mode_sample_total((uint32_t)c->P);
+  }
   HistArgs a{};
   a.renders = c->renders.p;
   a.warps = c->warps.p;
@@ -510,6 +534,13 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   a.mode = f->score_mode;
   a.variant = f->variant;
   a.scores = scores_dev ? scores_dev : c->scores.p;
+  if (use_skip) {
+    a.img_mode = c->img_mode.p;
+    a.sample_total = image_mode_sample_total((uint32_t)c->P);
+    a.nrenders = nvl;
+    a.skip_mode = c->hist_skip;
+    a.skipcap = skipcap;
+  }
   const int nl = launch_joint_hist_score(a, c->stream);
   REQUIRE(nl >= 0, NMI_ERR_CUDA, "histogram kernel configuration failed");
   c->launches += nl;
@@ -555,6 +586,7 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   for (auto& e : c->ev) CK(cudaEventCreate(&e));
   CK(cudaEventCreateWithFlags(&c->ev_params, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_feedback, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_hot, cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_feedback, 8 * sizeof(uint32_t)));
   memset(c->h_feedback, 0, 8 * sizeof(uint32_t));
   CK(c->counter.reserve(1));
@@ -563,6 +595,10 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   CK(c->zero_pair.reserve(1));
   CK(cudaMemset(c->zero_pair.p, 0, sizeof(int2)));
   c->timed = true;
+  if (const char* e = getenv("NMI_HIST_SKIP")) {
+    const int m = atoi(e);
+    if (m >= 0 && m <= 2) c->hist_skip = m;
+  }
   *out = c;
   return NMI_OK;
 }
@@ -576,13 +612,14 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   c->bin_total.release(); c->records.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
-  c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
+  c->img_mode.release(); c->hot.release(); c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
   c->one_score.release(); c->zero_pair.release();
   if (c->h_frame) cudaFreeHost(c->h_frame);
   if (c->h_params) cudaFreeHost(c->h_params);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->ev_params) cudaEventDestroy(c->ev_params);
   if (c->ev_feedback) cudaEventDestroy(c->ev_feedback);
+  if (c->ev_hot) cudaEventDestroy(c->ev_hot);
   if (c->h_feedback) cudaFreeHost(c->h_feedback);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -592,6 +629,12 @@ void nmi_ctx_destroy(nmi_ctx* c) {
 }
 
 void* nmi_ctx_stream(nmi_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int nmi_ctx_set_hist_skip(nmi_ctx* c, int mode) {
+  REQUIRE(c && mode >= 0 && mode <= 2, NMI_ERR_INVALID, "mode must be 0 (never), 1 (automatic) or 2 (always)");
+  c->hist_skip = mode;
+  return NMI_OK;
+}
 
 int nmi_ctx_sync(nmi_ctx* c) {
   REQUIRE(c, NMI_ERR_INVALID, "null ctx");
@@ -948,6 +991,18 @@ static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped,
     a.dumpJ = c->dumpJ.p;
     a.dumpHA = c->dumpH.p;
     a.dumpHB = c->dumpH.p + 256;
+  }
+  if (c->hist_skip != 0 && f->bins == 256 && f->bg && ((uintptr_t)render % 16) == 0 &&
+      ((uintptr_t)warped % 16) == 0) {
+    // single evaluation: always the build with the side tables, the kernel decides
+    CK(c->img_mode.reserve(2));
+    CK(c->hot.reserve(2));
+    launch_image_modes(render, 0, 1, warped, 0, 1, npix, c->img_mode.p, c->hot.p, c->stream);
+    a.img_mode = c->img_mode.p;
+    a.sample_total = image_mode_sample_total(npix);
+    a.nrenders = 1;
+    a.skip_mode = c->hist_skip;
+    a.skipcap = true;
   }
   REQUIRE(launch_joint_hist_score(a, c->stream) >= 0, NMI_ERR_CUDA,
           "histogram kernel configuration failed");

@@ -34,6 +34,17 @@
 //           leaves the chunk, and while a thread sits in one chunk the TMA ring lets
 //           the other warps process at most 2*kStages-1 = 7 chunks = 57 344 pixels
 //           < 15*4096.  (The LDG variant re-synchronises every two chunks instead.)
+//           Hot-bin skipping (template SKIPCAP, BG mode): shared-memory atomics on ONE word
+//           retire at roughly one per ~100 cycles however many warps issue them, so a flat
+//           region (render background 255, saturated sky, warp border) that piles pixels
+//           onto a few words makes a pair 2-4x slower.  A sampled histogram per image
+//           (image_mode_kernel) names the most frequent level a* of the render and b* of
+//           the warp; when together they cover >= 1/6 of the pixels, a thread whose 16
+//           pixels all have a == a* keeps them out of the joint histogram and counts
+//           their b values into a small per-warp-pair table instead (no return value, so
+//           equal lanes merge); likewise all b == b* -> a table over a; both -> one
+//           register counter.  The epilogue adds the tables to row a* / column b*.  Every
+//           count stays an exact integer; only where it is accumulated changes.
 //   P_U32X2 256 bins, two passes over the pixels, 128 render rows x 256 u32 per
 //           pass (128 KiB); no overflow logic, twice the L2->SM traffic.
 //   P_B64   64 bins (value >> 2), 8 replicated 64x64 u32 sub-histograms.
@@ -73,6 +84,13 @@ struct __align__(16) Smem {
   float term_tab[kTermTab];  // e(c) for small counts, filled per CTA with term() itself
   uint32_t ev_count;
   uint16_t ev_list[kEvCap];  // bin of every repaid crossing (+4096 each)
+};
+
+constexpr int kSkipCopies = 8;  // side tables: one per pair of consumer warps
+struct __align__(16) SmemSkip {   // follows Smem in the SKIPCAP builds
+  uint32_t n1[kSkipCopies][256];  // b-histogram of the uncounted pixels of all-(a == a*) threads
+  uint32_t n2[kSkipCopies][256];  // a-histogram of the uncounted pixels of all-(b == b*) threads
+  uint32_t nboth;                 // pixels of threads with all a == a* and all b == b*
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -256,9 +274,15 @@ __device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], c
 // pass.  B64: 64 rows of 64 words after folding the copies.
 template <int POLICY, bool SWZ, int NWARPS>
 __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const HistArgs& a,
-                                              bool dump, int warp, int lane) {
+                                              bool dump, int warp, int lane,
+                                              const SmemSkip* sk = nullptr, uint32_t skipT = 0xFFFFFFFFu) {
   constexpr int kConsumers = NWARPS * 32;
   if (POLICY == P_U16G) {
+    // skip mode (skipT = a* << 8 | b*): sk->n1[0] / n2[0] / nboth hold the folded side counts
+    const bool skip = sk != nullptr && skipT != 0xFFFFFFFFu;
+    const uint32_t astar = skip ? (skipT >> 8) & 0xFFu : 0x100u, bstar = skipT & 0xFFu;
+    const bool own_bstar = ((bstar >> 1) & 31u) == (uint32_t)lane;  // this lane holds column b* ...
+    const uint32_t i_bstar = ((bstar >> 6) << 1) | (bstar & 1u);     // ... in c[i_bstar]
     const uint32_t nev = min(sm.ev_count, (uint32_t)kEvCap);
     uint32_t col[8];
 #pragma unroll
@@ -281,6 +305,18 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
             for (int i = 0; i < 8; i++)
               if ((uint32_t)i == (((b >> 6) << 1) | (b & 1u))) c[i] += 4096u;
           }
+        }
+      }
+      if (skip) {  // the pixels that bypassed the joint histogram
+        if ((uint32_t)row == astar) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) c[i] += sk->n1[0][2 * (lane + 32 * (i >> 1)) + (i & 1)];
+        }
+        if (own_bstar) {
+          const uint32_t add = sk->n2[0][row] + ((uint32_t)row == astar ? sk->nboth : 0u);
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            if ((uint32_t)i == i_bstar) c[i] += add;
         }
       }
       uint32_t rs = 0;
@@ -401,11 +437,13 @@ __device__ __forceinline__ void ldg_words(uint32_t (&dst)[NW], const uint8_t* p)
 // NWARPS consumer warps.  With 16 of them a 17th warp is the dedicated TMA producer; with 32
 // (the 1024-thread CTA limit) thread 0 doubles as producer: after releasing chunk k it waits
 // until every warp has released it and refills that stage with chunk k + kStages.
-template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ>
+template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP>
 __global__ void __launch_bounds__(NWARPS == 32 ? 1024 : NWARPS * 32 + 32, 1)
 joint_hist_score_kernel(const HistArgs a) {
+  static_assert(!SKIPCAP || POLICY == P_U16G, "hot-bin skipping is built for the packed-u16 policy");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  SmemSkip& sk = *reinterpret_cast<SmemSkip*>(smem_raw + sizeof(Smem));  // SKIPCAP builds only
   constexpr int BINS = POLICY == P_B64 ? 64 : 256;
   constexpr int NPASS = POLICY == P_U32X2 ? 2 : 1;
   constexpr int kConsumers = NWARPS * 32;
@@ -430,6 +468,10 @@ joint_hist_score_kernel(const HistArgs a) {
     uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
     for (int i = tid; i < kHistWords / 4; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
     if (tid < 256) sm.HB[tid] = 0;
+    if (SKIPCAP) {
+      for (int i = tid; i < 2 * kSkipCopies * 256; i += kThreads) (&sk.n1[0][0])[i] = 0;
+      if (tid == 0) sk.nboth = 0;
+    }
     for (int i = tid; i < kTermTab; i += kThreads) sm.term_tab[i] = term((uint32_t)i, L);
     if (tid == 0) {
       sm.ev_count = 0;
@@ -441,6 +483,16 @@ joint_hist_score_kernel(const HistArgs a) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
+  // hot-bin skipping: the sampled modes of this pair's two images decide (CTA-uniform)
+  uint32_t skipT = 0xFFFFFFFFu;
+  if (SKIPCAP && a.img_mode != nullptr && a.bg && a.skip_mode != 0) {
+    const uint32_t ka = __ldg(a.img_mode + pr.x), kb = __ldg(a.img_mode + a.nrenders + pr.y);
+    if (a.skip_mode == 2 || ((unsigned long long)(ka >> 8) + (kb >> 8)) * 6ull >= a.sample_total)
+      skipT = ((ka & 0xFFu) << 8) | (kb & 0xFFu);
+  }
+  const bool skip = SKIPCAP && skipT != 0xFFFFFFFFu;
+  const uint32_t a4 = ((skipT >> 8) & 0xFFu) * 0x01010101u, b4 = (skipT & 0xFFu) * 0x01010101u;
+  uint32_t nboth = 0;
   __syncthreads();
 
   auto issue_chunk = [&](int k) {  // one elected thread: both images of chunk k -> stage k % kStages
@@ -499,9 +551,33 @@ joint_hist_score_kernel(const HistArgs a) {
         }
       }
       const int nvalid = off >= npix ? 0 : (int)min((uint32_t)PIX, npix - off);
-      if (nvalid == PIX && a.bg)
-        accum_fast<POLICY, SWZ, NW>(sm, r, w, pass, warp);
-      else if (nvalid > 0)
+      if (nvalid == PIX && a.bg) {
+        if (!skip) {
+          accum_fast<POLICY, SWZ, NW>(sm, r, w, pass, warp);
+        } else {
+          // all of this thread's pixels at a*, or all at b*?  Then they stay out of the joint
+          // histogram (see the header): side table over the other image's values instead.
+          uint32_t dr = 0, dw = 0;
+#pragma unroll
+          for (int j = 0; j < NW; j++) {
+            dr |= r[j] ^ a4;
+            dw |= w[j] ^ b4;
+          }
+          if (dr != 0u && dw != 0u) {
+            accum_fast<POLICY, SWZ, NW>(sm, r, w, pass, warp);
+          } else if (dr == 0u && dw == 0u) {
+            nboth += PIX;
+          } else {
+            const uint32_t (&x)[NW] = dr == 0u ? w : r;
+            const uint32_t base = smem_u32(dr == 0u ? sk.n1[warp & (kSkipCopies - 1)] : sk.n2[warp & (kSkipCopies - 1)]);
+#pragma unroll
+            for (int i = 0; i < PIX; i++) {
+              const uint32_t v = __byte_perm(x[i >> 2], 0u, 0x4440 + (i & 3));
+              asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + v * 4u) : "memory");
+            }
+          }
+        }
+      } else if (nvalid > 0)
         accum_slow<POLICY, SWZ, NW>(sm, r, w, nvalid, a.bg, pass, warp);
       if (USE_TMA) {
         __syncwarp();
@@ -526,8 +602,19 @@ joint_hist_score_kernel(const HistArgs a) {
       }
     }
     if (NPASS == 1) {
+      if (skip) {  // fold the side tables into copy 0
+        if (nboth) atomicAdd(&sk.nboth, nboth);
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+        for (int i = tid; i < 512; i += kConsumers) {
+          uint32_t* t0 = i < 256 ? &sk.n1[0][i] : &sk.n2[0][i - 256];
+          uint32_t sum = 0;
+#pragma unroll
+          for (int c = 0; c < kSkipCopies; c++) sum += t0[c * 256];
+          *t0 = sum;
+        }
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
-      rows_epilogue<POLICY, SWZ, NWARPS>(sm, 0, L, a, dump, warp, lane);
+      rows_epilogue<POLICY, SWZ, NWARPS>(sm, 0, L, a, dump, warp, lane, SKIPCAP ? &sk : nullptr, skipT);
     }
   }
   __syncthreads();
@@ -554,24 +641,110 @@ joint_hist_score_kernel(const HistArgs a) {
         finish_score(sm.sums[1], sm.sums[2], sm.sums[0], a.mode);
 }
 
-template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ>
+// ---- sampled per-image mode (hot-bin skipping) ----------------------------------------
+// One CTA per image: histogram of every 64th group of 16 pixels, then
+// img_mode[img] = sampled count of the most frequent level << 8 | that level (lowest level
+// among equals) and hot[0] / hot[1] = the largest such count over the renders / the warps
+// (read back by the host one search later to pick the SKIPCAP build).
+constexpr int kImThreads = 256;
+
+// 16 pixels (one uint4) into the warp's private histogram.  Flat runs -- the very images
+// this pass exists for -- would hammer one word, so 16 equal pixels are one add of 16, and
+// a warp whose lanes all hold the same flat value adds 512 once.
+__device__ __forceinline__ void im_count16(uint32_t* h, const uint4 v, bool valid) {
+  const uint32_t b0 = v.x & 0xFFu;
+  const bool flat = valid && v.x == b0 * 0x01010101u && v.y == v.x && v.z == v.x && v.w == v.x;
+  const uint32_t first = __shfl_sync(0xffffffffu, b0, 0);
+  if (__all_sync(0xffffffffu, flat && b0 == first)) {
+    if ((threadIdx.x & 31) == 0) atomicAdd(h + b0, 512u);
+    return;
+  }
+  if (!valid) return;
+  if (flat) {
+    atomicAdd(h + b0, 16u);
+    return;
+  }
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) atomicAdd(h + ((w[j] >> (8 * k)) & 0xFFu), 1u);
+}
+
+__global__ void __launch_bounds__(kImThreads)
+image_mode_kernel(const uint8_t* __restrict__ renders, size_t rpitch, int nr,
+                  const uint8_t* __restrict__ warps, size_t wpitch, uint32_t npix,
+                  uint32_t* __restrict__ img_mode, uint32_t* __restrict__ hot) {
+  __shared__ uint32_t s_h[kImThreads / 32][256];
+  __shared__ uint32_t s_best;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (kImThreads / 32) * 256; i += kImThreads) (&s_h[0][0])[i] = 0;
+  if (tid == 0) s_best = 0;
+  __syncthreads();
+  const int img = blockIdx.x;
+  const uint4* img4 = reinterpret_cast<const uint4*>(
+      img < nr ? renders + (size_t)img * rpitch : warps + (size_t)(img - nr) * wpitch);
+  const uint32_t nsamp = (npix / 16 + 63) / 64;
+  for (uint32_t i0 = 0; i0 < nsamp; i0 += 4 * kImThreads) {  // warp-uniform trip count, 4 loads in flight
+    uint4 v[4];
+    bool valid[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t i = i0 + u * kImThreads + tid;
+      valid[u] = i < nsamp && (size_t)i * 64 < npix / 16;
+      v[u] = valid[u] ? __ldg(img4 + (size_t)i * 64) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) im_count16(s_h[warp], v[u], valid[u]);
+  }
+  __syncthreads();
+  uint32_t c = 0;
+  for (int w = 0; w < kImThreads / 32; w++) c += s_h[w][tid];
+  atomicMax(&s_best, (c << 8) | (255u - (uint32_t)tid));  // largest count, lowest level among equals
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t cnt = s_best >> 8, level = 255u - (s_best & 0xFFu);
+    img_mode[img] = (cnt << 8) | level;
+    atomicMax(hot + (img < nr ? 0 : 1), cnt);
+  }
+}
+
+template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP = false>
 int launch_t(const HistArgs& a, cudaStream_t st) {
-  auto kern = joint_hist_score_kernel<POLICY, USE_TMA, NWARPS, SWZ>;
+  auto kern = joint_hist_score_kernel<POLICY, USE_TMA, NWARPS, SWZ, SKIPCAP>;
+  constexpr size_t smem = sizeof(Smem) + (SKIPCAP ? sizeof(SmemSkip) : 0);
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(Smem)) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return -1;
     configured = true;
   }
-  kern<<<a.npairs, NWARPS == 32 ? 1024 : NWARPS * 32 + 32, sizeof(Smem), st>>>(a);
+  kern<<<a.npairs, NWARPS == 32 ? 1024 : NWARPS * 32 + 32, smem, st>>>(a);
   return 1;
 }
 
 }  // namespace
 
+uint32_t image_mode_sample_total(uint32_t npix) { return ((npix / 16 + 63) / 64) * 16; }
+
+int launch_image_modes(const uint8_t* renders, size_t rpitch, int nr, const uint8_t* warps, size_t wpitch,
+                       int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st) {
+  if (nr + nw == 0) return 0;
+  cudaMemsetAsync(hot, 0, 2 * sizeof(uint32_t), st);
+  image_mode_kernel<<<nr + nw, kImThreads, 0, st>>>(renders, rpitch, nr, warps, wpitch, npix, img_mode, hot);
+  return 1;
+}
+
 int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
   if (a.npairs <= 0) return 0;
+  if (a.bins == 256 && a.skipcap && a.bg && a.img_mode != nullptr) {
+    switch (a.variant) {  // the packed-u16 builds that carry the side tables
+      case 0: return launch_t<P_U16G, true, 16, true, true>(a, st);
+      case 4: return launch_t<P_U16G, true, 32, false, true>(a, st);
+      case 5: return launch_t<P_U16G, true, 16, false, true>(a, st);
+      default: break;
+    }
+  }
   if (a.bins == 64)
     return (a.variant & 1) ? launch_t<P_B64, false, 16, false>(a, st)
                            : launch_t<P_B64, true, 16, false>(a, st);

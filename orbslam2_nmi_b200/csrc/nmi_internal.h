@@ -49,12 +49,26 @@ struct HistArgs {
   uint32_t length;  // kernel.cu:85: always W*H
   int bins, bg, mode, variant;
   float* scores;
+  // hot-bin skipping (hist.cu): per image, sampled count << 8 | level of its most frequent
+  // grey level (renders [0, nrenders), then the warps); sample_total = pixels sampled per
+  // image; skip_mode 0 never, 1 when a pair's two levels cover >= 1/6 of the samples,
+  // 2 always; skipcap = launch the build that carries the side tables.
+  const uint32_t* img_mode;
+  uint32_t sample_total;
+  int nrenders;
+  int skip_mode;
+  bool skipcap;
   // optional dumps (parity): when non-null, pair 0 of the launch writes them
   uint32_t* dumpJ;
   uint32_t* dumpHA;
   uint32_t* dumpHB;
 };
 int launch_joint_hist_score(const HistArgs& a, cudaStream_t st);  // returns launches, <0 on error
+// sampled per-image modes for HistArgs::img_mode; hot[0] / hot[1] = largest sampled count over
+// the renders / the warps.  Returns launches.
+int launch_image_modes(const uint8_t* renders, size_t rpitch, int nr, const uint8_t* warps, size_t wpitch,
+                       int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st);
+uint32_t image_mode_sample_total(uint32_t npix);
 int hist_configure();  // cudaFuncSetAttribute for the big-smem kernels; 0 on success
 
 // --- argmax.cu -------------------------------------------------------------

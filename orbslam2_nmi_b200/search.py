@@ -111,6 +111,10 @@ class NmiSearcher:
     def sync(self):
         check(self.lib.nmi_ctx_sync(self.h))
 
+    def set_hist_skip(self, mode: int):
+        """Hot-bin skipping of the histogram kernel: 0 never, 1 automatic, 2 always."""
+        check(self.lib.nmi_ctx_set_hist_skip(self.h, int(mode)))
+
     def decode(self, grid: Grid, key: int) -> SearchResult:
         r = Result()
         self.lib.nmi_decode_key(C.byref(grid), C.c_uint64(key), C.byref(r))

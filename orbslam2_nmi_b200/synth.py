@@ -131,6 +131,22 @@ def frame_textured(W: int, H: int, seed: int = 5) -> np.ndarray:
     return np.clip(np.rint(v), 0, 255).astype(np.uint8)
 
 
+def frame_sky(W: int, H: int, seed: int = 5, sky: float = 0.35) -> np.ndarray:
+    """Textured frame whose top `sky` fraction is saturated (255), like an over-exposed sky:
+    together with the render background (255) it piles a large share of all pixels onto one
+    joint-histogram bin -- the contention case real outdoor frames produce."""
+    f = frame_textured(W, H, seed)
+    f[: int(H * sky)] = 255
+    return f
+
+
+def frame_smooth(W: int, H: int, seed: int = 5) -> np.ndarray:
+    """Noise-free low-frequency texture: long runs of equal grey levels."""
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    v = 128 + 50 * np.sin(xx / 37.0) * np.cos(yy / 29.0) + 40 * np.sin((xx + yy) / 91.0)
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
 def default_grid(n_synth=(3, 3, 3), n_warp=(3, 3, 3)) -> Grid:
     """ETH_small.yaml:77-88 steps: 0.2/0.2/0.5 m, 0.02/0.02/0.05 rad."""
     return Grid.make(n_synth, n_warp, (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))

@@ -185,6 +185,44 @@ def test_point_sizes(searcher, oracle, size):
         assert res.best_index == oracle.argmax(scores)[0]
 
 
+@pytest.mark.parametrize("mode", [2, 1])
+@pytest.mark.parametrize("frame_kind,n_points,size", [
+    ("sky", 400, (96, 64)),        # saturated sky + mostly-background renders: one huge bin
+    ("constant", 20000, (96, 64)),  # every pixel has b == b*: the whole histogram is rebuilt
+    ("textured", 20000, (96, 64)),  # no dominant level (mode 2 forces the path anyway)
+    ("sky", 3000, (131, 67)),      # ragged: tail pixels, partial chunk
+])
+def test_hot_bin_skipping_is_exact(searcher, oracle, mode, frame_kind, n_points, size):
+    """Histogram option nmi_ctx_set_hist_skip: threads whose pixels all sit at the render's /
+    the warp's dominant grey level keep them out of the joint histogram (side tables, added
+    back in the epilogue) -- integer histograms must stay bit-exact, scores within 1e-5,
+    same winner."""
+    sc = synth.make_scene("tiny", n_points=n_points)
+    sc.W, sc.H = size
+    sc.cx, sc.cy = sc.W / 2.0 + 3.0, sc.H / 2.0 - 2.0
+    g = Grid.make((2, 2, 1), (2, 1, 2), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    frame = {"sky": synth.frame_sky, "constant": synth.frame_constant,
+             "textured": synth.frame_textured}[frame_kind](sc.W, sc.H)
+    searcher.set_scene(sc)
+    searcher.set_frame(frame)
+    scores, renders, warps = oracle.search_points(sc, sc.Twc, g, sc.xyzi, frame, keep_images=True)
+    searcher.set_hist_skip(mode)
+    try:
+        for _ in range(2):  # mode 1 picks the build with the side tables from the previous search's levels
+            res = searcher.search(sc.Twc, g, want_scores=True)
+            assert_scores_close(res.scores, scores)
+            assert res.best_index == oracle.argmax(scores)[0]
+        for (s, w) in [(0, 0), (3, 3), (1, 2)]:
+            J, HA, HB = oracle.joint_hist(renders[s], warps[w])
+            for v in (0, 5, 4):  # swizzled / plain / 32-warp builds of the packed-u16 policy
+                gJ, gHA, gHB, gs = searcher.get_hist(s, w, searcher.flags(variant=v))
+                assert np.array_equal(gJ, J), f"joint histogram differs (pair {s},{w}, variant {v})"
+                assert np.array_equal(gHA, HA) and np.array_equal(gHB, HB)
+                assert_scores_close([gs], [scores[w * g.n_synth + s]])
+    finally:
+        searcher.set_hist_skip(1)
+
+
 # ------------------------------------------------------------------ planted pose ----
 def test_planted_pose_recovered(searcher, oracle):
     sc = synth.make_scene("small")
