@@ -15,3 +15,6 @@ python tools/profile_run.py 0 > gpurun_out/prof_plain.log 2>&1 && \
 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"cull_|bin_kernel|tile_resolve|warp_kernel|argmax" -c 12 -f -o gpurun_out/prof_render python tools/profile_run.py 0 > gpurun_out/prof_ncu_render.log 2>&1 && \
 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"joint_hist" -c 1 -f -o gpurun_out/prof_hist python tools/profile_run.py 0 > gpurun_out/prof_ncu_hist.log 2>&1
 tail -1 gpurun_out/prof_ncu_render.log; tail -1 gpurun_out/prof_ncu_hist.log
+# histogram contention cases and the other BASELINE configs, for the record
+CASES="textured_40_0 textured_40_1 sky_40_0 sky_40_1 sky_12_0 sky_12_1 constant_40_0 constant_40_1" bash tools/gpu_stress.sh > gpurun_out/hist_stress.txt 2>&1
+python tools/run_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
