@@ -277,7 +277,7 @@ __device__ __forceinline__ Splat project_splat_point(const float4& p, const floa
 // pass of the counting sort).  MODE 2: single pass into fixed-capacity bins (capacity known
 // from the previous search; a bin that fills up raises the overflow flag).
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)  // <= 51 registers: five CTAs per SM hide the slot-atomic latency (measured)
 bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
            const uint32_t* __restrict__ counter, const float4* __restrict__ centres, int nviews,
            ViewConst vc, int ntx, int nt, uint32_t* __restrict__ counts,
