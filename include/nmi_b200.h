@@ -140,6 +140,7 @@ int nmi_decode_key(const nmi_grid *grid, uint64_t key, nmi_result *out);
 
 /* ---- the coarse-to-fine driver ------------------------------------------ */
 #define NMI_MAX_PREV_POSES 8
+#define NMI_MAX_LEVELS 8
 /* inputs of Tracking::RelocalizeWithNMIStrategy that live in Tracking's state  */
 typedef struct {
   float threshold;              /* NMI.Treshold -> mfNmiInitTresholf (Tracking.cc:157)   */
@@ -163,6 +164,14 @@ typedef struct {
   float prev_Twc[NMI_MAX_PREV_POSES][16];
   int n_evals;               /* total (render, warp) pairs scored                         */
   float gpu_ms;
+  /* per search that ran (first NMI_MAX_LEVELS): what the reference logs after each
+   * RelocalizeWithNMI (Tracking.cc:2103-2106) -- NmiKernel with its winner, LastNmiKernel->NMI */
+  int n_levels;
+  struct {
+    nmi_grid grid;
+    int32_t best_s[3], best_w[3];
+    float nmi, last_nmi;
+  } levels[NMI_MAX_LEVELS];
 } nmi_reloc_result;
 
 /* Grid choice at the top of RelocalizeWithNMIStrategy (Tracking.cc:2001-2069):

@@ -68,13 +68,21 @@ class RelocParams(C.Structure):
 MAX_PREV_POSES = 8
 
 
+MAX_LEVELS = 8
+
+
+class RelocLevel(C.Structure):
+    _fields_ = [("grid", Grid), ("best_s", C.c_int32 * 3), ("best_w", C.c_int32 * 3),
+                ("nmi", C.c_float), ("last_nmi", C.c_float)]
+
+
 class RelocResult(C.Structure):
     _fields_ = [("Twc", C.c_float * 16), ("relocalized", C.c_int), ("failed", C.c_int),
                 ("iterations", C.c_int), ("nmi", C.c_float), ("last_nmi", C.c_float),
                 ("threshold_used", C.c_float), ("final_grid", Grid), ("last_search_grid", Grid),
                 ("best_s", C.c_int32 * 3), ("best_w", C.c_int32 * 3), ("n_prev", C.c_int),
                 ("prev_Twc", (C.c_float * 16) * MAX_PREV_POSES), ("n_evals", C.c_int),
-                ("gpu_ms", C.c_float)]
+                ("gpu_ms", C.c_float), ("n_levels", C.c_int), ("levels", RelocLevel * MAX_LEVELS)]
 
 
 class Result(C.Structure):

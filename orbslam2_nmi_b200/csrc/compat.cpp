@@ -276,7 +276,9 @@ static std::string make_results_dir(std::string* log_path) {
   std::tm tmv{};
   localtime_r(&t, &tmv);
   std::ostringstream name;
-  name << nmi_prop_OUTPUT_LOC "/" << std::put_time(&tmv, "%d-%m-%Y_%Hh%Mm%Ss");
+  // allProperties.hpp's output location, overridable at run time ($NMI_OUTPUT_LOC)
+  const char* base = std::getenv("NMI_OUTPUT_LOC");
+  name << (base && *base ? base : nmi_prop_OUTPUT_LOC) << "/" << std::put_time(&tmv, "%d-%m-%Y_%Hh%Mm%Ss");
   fs::path dir(name.str());
   std::error_code ec;
   // localization.cpp:94-100: a relative location is taken under the working directory
@@ -473,6 +475,29 @@ nmi_reloc_result NmiObjects::relocalize(cv::Mat Twc, cv::Mat gray, const nmi_rel
   nmi_reloc_result out{};
   nmi_compat::check(nmi_relocalize(nmi_compat::context(), T, &start, &nmi_compat::flags(), &params, &out),
                     "NmiObjects::relocalize");
+  // the lines Tracking.cc:2103-2106 appends to _log.txt after every search
+  if (!logPath.empty()) {
+    for (int l = 0; l < out.n_levels; l++) {
+      NmiSearchKernel cur, last;
+      cur.setGrid(out.levels[l].grid);
+      cur.setBest(out.levels[l].best_s[0], out.levels[l].best_s[1], out.levels[l].best_s[2],
+                  out.levels[l].best_w[0], out.levels[l].best_w[1], out.levels[l].best_w[2], out.levels[l].nmi);
+      if (l == 0) {  // LastNmiKernel->reset() (Tracking.cc:1998): no winner yet, NMI 0
+        last.setGrid(out.levels[0].grid);
+        last.reset();
+      } else {
+        last.setGrid(out.levels[l - 1].grid);
+        last.setBest(out.levels[l - 1].best_s[0], out.levels[l - 1].best_s[1], out.levels[l - 1].best_s[2],
+                     out.levels[l - 1].best_w[0], out.levels[l - 1].best_w[1], out.levels[l - 1].best_w[2],
+                     out.levels[l - 1].nmi);
+      }
+      std::stringstream ss_log;
+      ss_log << "NmiKernel:\t" << cur;
+      ss_log << "\nLastNmiKernel:\t" << last;
+      ss_log << "\nKernel rate:\t" << (out.levels[l].nmi / out.levels[l].last_nmi) << "\n";
+      helperFunctions::log(ss_log, logPath);
+    }
+  }
   // leave the objects in the state the reference's loop would (kernel + winner + NMI)
   NmiKernel->setGrid(out.final_grid);
   NmiKernel->setBest(out.best_s[0], out.best_s[1], out.best_s[2], out.best_w[0], out.best_w[1],

@@ -75,6 +75,16 @@ int nmi_relocalize(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid* start_g
     std::memcpy(pose, moved, sizeof pose);
     out->relocalized = 1;  // SetNMIRelocalized(true) (:1978,:1982)
     out->iterations = i;
+    if (out->n_levels < NMI_MAX_LEVELS) {  // the state Tracking.cc:2103-2106 logs
+      auto& lv = out->levels[out->n_levels++];
+      lv.grid = kernel;
+      for (int k = 0; k < 3; ++k) {
+        lv.best_s[k] = r.best_s[k];
+        lv.best_w[k] = r.best_w[k];
+      }
+      lv.nmi = kernel_nmi;
+      lv.last_nmi = last_nmi;
+    }
 
     if (i > 1 && nmi_grid_is_middle(&kernel, r.best_s, r.best_w)) break;  // :2108-2110
     if (i > 1) {                                                         // :2112-2121

@@ -227,12 +227,16 @@ static int gpu_checks(const char* yaml, const char* frame_raw, const char* twc_t
               nk->bestWarpX, nk->bestWarpY, nk->bestWarpZ, nk->NMI);
   std::printf("NEWTWC");
   for (int i = 0; i < 16; i++) std::printf(" %.9g", newTwc.at<float>(i));
+  std::printf("\n");
+  std::fflush(stdout);  // relocalize() echoes its log lines through std::cout
   // ---- the multi-level driver ----
   nmi_reloc_params prm{};
   prm.threshold = objs.threshold();
   prm.max_iterations = nmi_prop_MAX_ITERATION_COUNT;
   nmi_reloc_result rr = objs.relocalize(Twc, gray, prm);
   std::printf("\nRELOC %d %d %d %.9g %.9g", rr.relocalized, rr.failed, rr.iterations, rr.nmi, rr.last_nmi);
+  EXPECT(rr.n_levels == rr.iterations && rr.levels[rr.n_levels - 1].nmi == rr.nmi);
+  std::printf("\nLOGPATH %s", objs.logPath.c_str());
   for (int i = 0; i < 16; i++) std::printf(" %.9g", rr.Twc[i]);
   std::stringstream ss;
   ss << *objs.NmiKernel;

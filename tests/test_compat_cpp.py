@@ -150,8 +150,11 @@ def _loaded_cloud(d):
 @pytest.mark.gpu
 def test_compat_reference_loop_on_gpu(exe, workdir, oracle):
     d, sc, frame = workdir
+    import os
+
     res = subprocess.run([str(exe), "gpu", str(d / "settings.yaml"), str(d / "frame.raw"), str(d / "twc.txt")],
-                         capture_output=True, text=True, cwd=d, timeout=600)
+                         capture_output=True, text=True, cwd=d, timeout=600,
+                         env=dict(os.environ, NMI_OUTPUT_LOC=str(d / "results")))
     assert res.returncode == 0 and "GPU OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
     out = {l.split(" ", 1)[0]: l.split()[1:] for l in res.stdout.splitlines() if l and l.split()[0].isupper()}
     g = Grid.make((2, 1, 2), (1, 2, 1), (0.2, 0.2, 0.5), (0.02, 0.03, 0.05))
@@ -171,3 +174,9 @@ def test_compat_reference_loop_on_gpu(exe, workdir, oracle):
     assert np.array_equal(new, oracle.apply_winner(sc.Twc, g, s, w))
     reloc = out["RELOC"]
     assert int(reloc[2]) >= 2  # at least two levels always run (Tracking.cc:2108 needs i > 1)
+    # _log.txt: one "NmiKernel / LastNmiKernel / Kernel rate" block per level (Tracking.cc:2103-2106)
+    log = Path(out["LOGPATH"][0]).read_text()
+    assert str(d / "results") in out["LOGPATH"][0]
+    assert log.count("\nNmiKernel:\tsX:") == int(reloc[2]) and log.count("\nLastNmiKernel:\tsX:") == int(reloc[2])
+    assert log.count("Kernel rate:\t") == int(reloc[2])
+    assert "Kernel rate:\tinf" in log  # first level: LastNmiKernel->NMI is 0 after reset()
