@@ -141,8 +141,12 @@ struct nmi_ctx {
   DevBuf<uint4> records;
 
   DevBuf<uint8_t> frame;
-  uint8_t* h_frame = nullptr;  // pinned staging for host frames
-  size_t h_frame_cap = 0;
+  // two pinned staging buffers for pageable host frames: frame k+1 is copied in while the
+  // H2D of frame k (and whatever follows it on the stream) is still in flight
+  unsigned char* h_frame[2] = {nullptr, nullptr};
+  size_t h_frame_cap[2] = {0, 0};
+  cudaEvent_t ev_frame[2] = {nullptr, nullptr};  // "the H2D out of staging buffer i is done"
+  int frame_slot = 0;
 
   DevBuf<unsigned long long> zbuf;
   size_t zbuf_clean = 0;  // elements known to hold ~0
@@ -614,7 +618,10 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
   c->img_mode.release(); c->hot.release(); c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
   c->one_score.release(); c->zero_pair.release();
-  if (c->h_frame) cudaFreeHost(c->h_frame);
+  for (int i = 0; i < 2; i++) {
+    if (c->h_frame[i]) cudaFreeHost(c->h_frame[i]);
+    if (c->ev_frame[i]) cudaEventDestroy(c->ev_frame[i]);
+  }
   if (c->h_params) cudaFreeHost(c->h_params);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->ev_params) cudaEventDestroy(c->ev_params);
@@ -822,12 +829,14 @@ int nmi_set_frame(nmi_ctx* c, const uint8_t* gray, int W, int H) {
     CK(cudaMemcpyAsync(c->frame.p, gray, c->P, cudaMemcpyHostToDevice, c->stream));
   } else {
     // pageable -> pinned staging so the H2D copy is a true async DMA on our stream
-    unsigned char* stage = c->h_frame;
-    if (int rc = ensure_pinned(&stage, &c->h_frame_cap, c->P)) return rc;
-    c->h_frame = stage;
-    CK(cudaStreamSynchronize(c->stream));  // previous upload of the staging buffer is done
-    memcpy(c->h_frame, gray, c->P);
-    CK(cudaMemcpyAsync(c->frame.p, c->h_frame, c->P, cudaMemcpyHostToDevice, c->stream));
+    const int slot = c->frame_slot;
+    c->frame_slot ^= 1;
+    if (!c->ev_frame[slot]) CK(cudaEventCreateWithFlags(&c->ev_frame[slot], cudaEventDisableTiming));
+    CK(cudaEventSynchronize(c->ev_frame[slot]));  // the upload that last used this buffer is done
+    if (int rc = ensure_pinned(&c->h_frame[slot], &c->h_frame_cap[slot], c->P)) return rc;
+    memcpy(c->h_frame[slot], gray, c->P);
+    CK(cudaMemcpyAsync(c->frame.p, c->h_frame[slot], c->P, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ev_frame[slot], c->stream));
   }
   c->has_frame = true;
   return NMI_OK;

@@ -15,7 +15,7 @@
 // B200 design: the whole 256x256 joint histogram of one evaluation lives in the
 // CTA's shared memory and never touches HBM; the marginals are its row / column
 // sums (integers, exact); only one float leaves the SM.  Both images are streamed
-// through a 3-stage shared-memory ring filled by the TMA engine
+// through a 4-stage shared-memory ring filled by the TMA engine
 // (cp.async.bulk + mbarrier complete_tx), issued by a dedicated producer warp,
 // so the 16 or 32 consumer warps spend their issue slots on shared-memory atomics.
 // The hot loop is branch-free: each thread fires all its atomics of a chunk back to

@@ -15,9 +15,8 @@
 //                  (depth bits << 32 | tie-break word) atomicMin into the per-view
 //                  z-buffer, with a plain-load early-z test in front;
 //   resolve        z-buffer -> u8 render (background 255) and reset to ~0.
-// Point clouds go through the binned TILE renderer further down (bin_count / scan /
-// bin_scatter / tile_resolve); the global z-buffer path above serves the mesh model and
-// oversized splats.
+// Point clouds go through the binned TILE renderer further down (bin_kernel / tile_resolve);
+// the global z-buffer path above serves the mesh model's resolve and splats wider than a tile.
 #include <climits>
 
 #include "nmi_internal.h"
@@ -228,16 +227,18 @@ project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict
 
 // ---- binned tile renderer (point clouds) ---------------------------------------------------
 // The classic tiled rasteriser, exact by construction:
-//   bin_count    every (survivor, view) pair is projected (fp32, bit-identical to the oracle)
-//                and counted into the 32x32-pixel tiles its s x s splat touches;
-//   (scan)       exclusive scan of the [view][tile] counts -> record offsets;
-//   bin_scatter  same projection again, one 16-byte record {i0|j0, depth bits, tag} per
-//                (splat, tile) written at its slot;
-//   tile_resolve one CTA per (view, tile): the tile's z-buffer lives in SHARED memory
-//                (depth + tag words), every record's fragments are resolved there with
-//                native 32-bit atomics -- pass 1 min depth, pass 2 min tag among the
-//                fragments at the minimum depth (== the packed 64-bit key minimum) -- and
-//                the CTA, sole owner of the tile, stores the finished u8 pixels directly.
+//   bin_kernel<2>  steady state, ONE pass: every (survivor, view) pair is projected (fp32,
+//                  bit-identical to the oracle) and one 16-byte record {i0|j0, depth bits, tag}
+//                  per (splat, 32x32 tile) is written into that [view][tile] bin.  Bins have a
+//                  fixed capacity taken from the previous search's fullest bin; a full bin
+//                  raises the overflow flag and the search is redone with the exact two-pass
+//                  counting sort: bin_kernel<0> counts, a scan turns the counts into offsets,
+//                  bin_kernel<1> projects again and writes the records at their slots;
+//   tile_resolve   one CTA per (view, tile): the tile's z-buffer lives in SHARED memory
+//                  (depth + tag words), every record's fragments are resolved there with
+//                  native 32-bit atomics -- pass 1 min depth, pass 2 min tag among the
+//                  fragments at the minimum depth (== the packed 64-bit key minimum) -- and
+//                  the CTA, sole owner of the tile, stores the finished u8 pixels directly.
 // No global z-buffer, no global atomics on pixels, no separate resolve pass.
 constexpr int kTile = 32;  // (bin_kernel shifts by 5)
 constexpr int kTileCells = kTile * kTile;
