@@ -223,6 +223,47 @@ def test_hot_bin_skipping_is_exact(searcher, oracle, mode, frame_kind, n_points,
         searcher.set_hist_skip(1)
 
 
+@pytest.mark.parametrize("case", range(14))
+def test_randomized_parity(searcher, oracle, case):
+    """Seeded random scenes / grids / flags / kernel options against the oracle: renders
+    bit-exact, scores within 1e-5, same winner."""
+    rng = np.random.default_rng(1000 + case)
+    sc = synth.make_scene("tiny", n_points=int(rng.integers(1, 6000)), seed=int(rng.integers(1 << 30)))
+    sc.W, sc.H = int(rng.integers(33, 150)), int(rng.integers(33, 110))
+    sc.cx, sc.cy = sc.W / 2.0 + rng.uniform(-6, 6), sc.H / 2.0 + rng.uniform(-6, 6)
+    sc.point_size = float(rng.integers(1, 5))
+    nS = tuple(int(v) for v in rng.integers(1, 4, size=3))
+    nW = tuple(int(v) for v in rng.integers(1, 4, size=3))
+    g = Grid.make(nS, nW, (0.2, 0.25, 0.4), (0.02, 0.03, 0.04))
+    kind = ["textured", "uniform", "constant", "sky", "smooth"][int(rng.integers(5))]
+    frame = {"textured": synth.frame_textured, "uniform": synth.frame_uniform, "constant": synth.frame_constant,
+             "sky": synth.frame_sky, "smooth": synth.frame_smooth}[kind](sc.W, sc.H)
+    bins = int(rng.choice([256, 256, 64]))
+    bg = bool(rng.integers(2))
+    mode = int(rng.choice([capi.SCORE_SUC, capi.SCORE_ENMI]))
+    variant = int(rng.choice([0, 1, 2, 5])) if bins == 256 else int(rng.integers(2))
+    skip = int(rng.integers(3))
+    searcher.set_scene(sc)
+    searcher.set_frame(frame)
+    searcher.set_hist_skip(skip)
+    try:
+        scores, renders, warps = oracle.search_points(sc, sc.Twc, g, sc.xyzi, frame, bins=bins, bg=bg,
+                                                      mode=mode, keep_images=True)
+        for _ in range(2):
+            res = searcher.search(sc.Twc, g, searcher.flags(bins=bins, score=mode, bg=bg, variant=variant),
+                                  want_scores=True)
+            for v in range(g.n_synth):
+                assert np.array_equal(searcher.get_render(v), renders[v]), f"render {v}"
+            for w in range(g.n_warp):
+                assert np.array_equal(searcher.get_warp(w), warps[w]), f"warp {w}"
+            assert_scores_close(res.scores, scores)
+            want, wmax = oracle.argmax(scores)
+            if want >= 0:
+                assert res.best_index == want
+    finally:
+        searcher.set_hist_skip(1)
+
+
 # ------------------------------------------------------------------ planted pose ----
 def test_planted_pose_recovered(searcher, oracle):
     sc = synth.make_scene("small")
