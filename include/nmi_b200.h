@@ -206,6 +206,19 @@ int nmi_warp_ptr(nmi_ctx *ctx, const nmi_grid *grid, int wx, int wy, int wz,
 int nmi_eval_pair(nmi_ctx *ctx, const void *warped_dev, unsigned int handle,
                   int W, int H, const nmi_flags *flags, float *score_host);
 
+/* Same evaluation with the integer histograms left on the device, the layout
+ * histogram256all fills (NMI.cuh:63-71): J[render * bins + camera], HA = render,
+ * HB = camera.  Any of J_dev / HA_dev / HB_dev / score_host may be NULL.       */
+int nmi_eval_pair_dev(nmi_ctx *ctx, const void *warped_dev, unsigned int handle,
+                      int W, int H, const nmi_flags *flags, uint32_t *J_dev,
+                      uint32_t *HA_dev, uint32_t *HB_dev, float *score_host);
+/* Adopt an externally produced render as the current render handle -- e.g. the
+ * reference's GL texture mapped through cuda_gl_interop (kernel.cu:53-59) and
+ * copied out of its cudaArray.  W*H u8 on the device, `pitch_bytes` between rows;
+ * bottom_up != 0: first row is the bottom one (GL), flipped like NMI.cu:82 does. */
+int nmi_import_render(nmi_ctx *ctx, const void *render_dev, size_t pitch_bytes,
+                      int W, int H, int bottom_up, unsigned int *handle);
+
 /* ---- host-side helpers of the search driver ----------------------------- */
 /* Rendering::calculateTranslation (rendering.hpp:644-665)                    */
 void nmi_cell_translation(const float Twc[16], const nmi_grid *grid, int sx,

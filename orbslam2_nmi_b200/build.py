@@ -20,7 +20,7 @@ LIBDIR = ROOT / "orbslam2_nmi_b200" / "_lib"
 LIB = LIBDIR / "libnmi_b200.so"
 ORACLE_LIB = ROOT / "oracle" / "_build" / "libnmi_oracle.so"
 
-CU_SOURCES = ["capi.cu", "project.cu", "mesh.cu", "warp.cu", "hist.cu", "argmax.cu", "host_math.cpp", "driver.cpp", "compat.cpp"]
+CU_SOURCES = ["capi.cu", "project.cu", "mesh.cu", "warp.cu", "hist.cu", "argmax.cu", "host_math.cpp", "driver.cpp", "compat.cpp", "compat_nmi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

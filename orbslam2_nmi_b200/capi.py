@@ -120,6 +120,8 @@ SYMBOLS = [
     ("nmi_warp_cells", C.c_int, [_P, C.POINTER(Grid)]),
     ("nmi_warp_ptr", C.c_int, [_P, C.POINTER(Grid), C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     ("nmi_eval_pair", C.c_int, [_P, _P, C.c_uint, C.c_int, C.c_int, C.POINTER(Flags), _P]),
+    ("nmi_eval_pair_dev", C.c_int, [_P, _P, C.c_uint, C.c_int, C.c_int, C.POINTER(Flags), _P, _P, _P, _P]),
+    ("nmi_import_render", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint)]),
     ("nmi_cell_translation", None, [_P, C.POINTER(Grid), C.c_int, C.c_int, C.c_int, _P]),
     ("nmi_cell_homography_inv", None, [C.POINTER(Camera), C.POINTER(Grid), C.c_int, C.c_int, C.c_int, _P]),
     ("nmi_apply_winner", None, [_P, C.POINTER(Grid), _P, _P, _P]),

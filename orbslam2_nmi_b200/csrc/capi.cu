@@ -28,6 +28,7 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
                           unsigned long long* zbuf, size_t P, uint32_t max_points, cudaStream_t st);
 
 void launch_scan_counts(uint32_t* block_counts, uint32_t nblocks, uint32_t* counter, cudaStream_t st);
+void launch_copy_rows(const uint8_t* src, size_t src_pitch, uint8_t* dst, int W, int H, bool flip, cudaStream_t st);
 void launch_bin_points(int mode, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
                        const float4* centres, int nviews, const ViewConst& vc, uint32_t* counts,
                        const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t bin_cap,
@@ -978,8 +979,10 @@ int nmi_warp_ptr(nmi_ctx* c, const nmi_grid* g, int wx, int wy, int wz, void** d
   return NMI_OK;
 }
 
+// One evaluation.  J / HA / HB: optional DEVICE destinations of the integer histograms
+// (bins*bins, bins, bins u32); when only some are wanted the rest land in context scratch.
 static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped, uint32_t npix,
-                       const nmi_flags* f, bool dump, float* score_host) {
+                       const nmi_flags* f, uint32_t* J, uint32_t* HA, uint32_t* HB, float* score_host) {
   HistArgs a{};
   a.renders = render;
   a.warps = warped;
@@ -994,12 +997,12 @@ static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped,
   a.mode = f->score_mode;
   a.variant = f->variant;
   a.scores = c->one_score.p;
-  if (dump) {
-    CK(c->dumpJ.reserve(65536));
-    CK(c->dumpH.reserve(512));
-    a.dumpJ = c->dumpJ.p;
-    a.dumpHA = c->dumpH.p;
-    a.dumpHB = c->dumpH.p + 256;
+  if (J || HA || HB) {
+    if (!J) CK(c->dumpJ.reserve(65536));
+    if (!HA || !HB) CK(c->dumpH.reserve(512));
+    a.dumpJ = J ? J : c->dumpJ.p;
+    a.dumpHA = HA ? HA : c->dumpH.p;
+    a.dumpHB = HB ? HB : c->dumpH.p + 256;
   }
   if (c->hist_skip != 0 && f->bins == 256 && f->bg && ((uintptr_t)render % 16) == 0 &&
       ((uintptr_t)warped % 16) == 0) {
@@ -1040,7 +1043,36 @@ int nmi_eval_pair(nmi_ctx* c, const void* warped_dev, unsigned int handle, int W
     CK(cudaMemcpyAsync(c->one_warp.p, wp, c->P, cudaMemcpyDeviceToDevice, c->stream));
     wp = c->one_warp.p;
   }
-  return eval_images(c, c->one_render.p, wp, (uint32_t)c->P, f, false, score_host);
+  return eval_images(c, c->one_render.p, wp, (uint32_t)c->P, f, nullptr, nullptr, nullptr, score_host);
+}
+
+int nmi_eval_pair_dev(nmi_ctx* c, const void* warped_dev, unsigned int handle, int W, int H,
+                      const nmi_flags* f, uint32_t* J_dev, uint32_t* HA_dev, uint32_t* HB_dev,
+                      float* score_host) {
+  REQUIRE(c && warped_dev, NMI_ERR_INVALID, "null argument");
+  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags");
+  REQUIRE(c->has_cam && W == c->cam.W && H == c->cam.H, NMI_ERR_INVALID, "size != camera size");
+  REQUIRE(handle == 1 && c->one_render.p, NMI_ERR_STATE, "unknown render handle");
+  REQUIRE(c->P / 4096 + 2 < 2048, NMI_ERR_INVALID, "image too large for the histogram kernel");
+  CK(cudaSetDevice(c->device));
+  CK(c->one_warp.reserve(c->pitch));
+  CK(cudaMemcpyAsync(c->one_warp.p, warped_dev, c->P, cudaMemcpyDeviceToDevice, c->stream));
+  return eval_images(c, c->one_render.p, c->one_warp.p, (uint32_t)c->P, f, J_dev, HA_dev, HB_dev, score_host);
+}
+
+int nmi_import_render(nmi_ctx* c, const void* render_dev, size_t pitch_bytes, int W, int H, int bottom_up,
+                      unsigned int* handle) {
+  REQUIRE(c && render_dev && handle, NMI_ERR_INVALID, "null argument");
+  REQUIRE(c->has_cam && W == c->cam.W && H == c->cam.H, NMI_ERR_INVALID, "size != camera size");
+  REQUIRE(pitch_bytes >= (size_t)W, NMI_ERR_INVALID, "pitch smaller than a row");
+  CK(cudaSetDevice(c->device));
+  CK(c->one_render.reserve(c->pitch));
+  launch_copy_rows(static_cast<const uint8_t*>(render_dev), pitch_bytes, c->one_render.p, W, H,
+                   bottom_up != 0, c->stream);
+  CK(cudaGetLastError());
+  c->has_search = false;  // nmi_get_render(0) now returns the imported image
+  *handle = 1;
+  return NMI_OK;
 }
 
 // ---- parity read-backs ------------------------------------------------------
@@ -1104,9 +1136,11 @@ int nmi_get_hist(nmi_ctx* c, int s, int w, const nmi_flags* f, uint32_t* J, uint
               w - c->w_begin < c->nwl,
           NMI_ERR_INVALID, "pair not on this rank");
   CK(cudaSetDevice(c->device));
+  CK(c->dumpJ.reserve(65536));
+  CK(c->dumpH.reserve(512));
   const int rc = eval_images(c, c->renders.p + (size_t)(s - c->v_begin) * c->pitch,
                              c->warps.p + (size_t)(w - c->w_begin) * c->pitch, (uint32_t)c->P, f,
-                             true, score);
+                             c->dumpJ.p, c->dumpH.p, c->dumpH.p + 256, score);
   if (rc) return rc;
   const size_t nb = (size_t)f->bins;
   CK(cudaMemcpy(J, c->dumpJ.p, nb * nb * sizeof(uint32_t), cudaMemcpyDeviceToHost));

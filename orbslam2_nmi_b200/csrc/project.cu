@@ -33,6 +33,16 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return r;
 }
 
+// W x H u8 image with an arbitrary row pitch -> packed rows, optionally bottom-up -> top-down
+// (an externally produced render: a GL texture's first row is the bottom one)
+__global__ void copy_rows_kernel(const uint8_t* __restrict__ src, size_t src_pitch, uint8_t* __restrict__ dst,
+                                 int W, int H, bool flip) {
+  const int y = blockIdx.y;
+  const uint8_t* s = src + (size_t)(flip ? H - 1 - y : y) * src_pitch;
+  uint8_t* d = dst + (size_t)y * W;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) d[x] = s[x];
+}
+
 __global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -587,6 +597,11 @@ void launch_bin_points(int mode, const float4* cpts, const uint32_t* ctag, const
   else
     bin_kernel<2><<<grid, block, smem, st>>>(cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts,
                                              offsets, rec, rec_cap, bin_cap, overflow);
+}
+
+void launch_copy_rows(const uint8_t* src, size_t src_pitch, uint8_t* dst, int W, int H, bool flip, cudaStream_t st) {
+  if (W <= 0 || H <= 0) return;
+  copy_rows_kernel<<<dim3((unsigned)((W + 255) / 256), (unsigned)H), 256, 0, st>>>(src, src_pitch, dst, W, H, flip);
 }
 
 int tiles_per_view(int W, int H) { return ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile); }

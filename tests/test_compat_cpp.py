@@ -180,3 +180,40 @@ def test_compat_reference_loop_on_gpu(exe, workdir, oracle):
     assert log.count("\nNmiKernel:\tsX:") == int(reloc[2]) and log.count("\nLastNmiKernel:\tsX:") == int(reloc[2])
     assert log.count("Kernel rate:\t") == int(reloc[2])
     assert "Kernel rate:\tinf" in log  # first level: LastNmiKernel->NMI is 0 after reset()
+
+
+@pytest.mark.gpu
+def test_nmi_cuh_secondary_exports(tmp_path, oracle):
+    """NMI.cuh:60-78 -- histogram256all + the three kernels, called like kernel.cu:63-100 does,
+    with the render in a cudaArray (bottom-up rows, flipped like NMI.cu:82)."""
+    import shutil
+
+    lib = build.build_cuda()
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = tmp_path / "test_nmi_cuh"
+    cmd = [nvcc, "-ccbin", "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-std=c++17",
+           "-gencode", "arch=compute_100a,code=sm_100a", "-I", str(ROOT / "include"),
+           str(ROOT / "tests" / "cpp" / "test_nmi_cuh.cu"), "-L", str(lib.parent), "-lnmi_b200",
+           f"-Xlinker=-rpath,{lib.parent}", "-o", str(exe)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    sc = synth.make_scene("tiny", n_points=5000)
+    sc.W, sc.H = 150, 70  # not a multiple of 16 pixels per row
+    sc.cx, sc.cy = 75.0, 35.0
+    g = Grid.make((1, 1, 1), (1, 1, 1), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    _, render = oracle.render_points(sc, sc.Twc, oracle.cell_translation(sc.Twc, g, 0, 0, 0), sc.xyzi)
+    warped = synth.frame_textured(sc.W, sc.H, seed=9)
+    render[::-1].copy().tofile(tmp_path / "render_bottom_up.raw")  # GL row order
+    warped.tofile(tmp_path / "warped.raw")
+    res = subprocess.run([str(exe), str(sc.W), str(sc.H), str(tmp_path / "render_bottom_up.raw"),
+                          str(tmp_path / "warped.raw"), str(tmp_path / "hist.bin")],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "NMICUH OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+    out = np.fromfile(tmp_path / "hist.bin", dtype=np.uint32)
+    J, HA, HB = oracle.joint_hist(render, warped)
+    assert np.array_equal(out[:65536].reshape(256, 256), J.reshape(256, 256))
+    assert np.array_equal(out[65536:65536 + 256], HA) and np.array_equal(out[65536 + 256:], HB)
+    want = oracle.score_f32(J, HA, HB, sc.W * sc.H)
+    got = [float(v) for v in res.stdout.split("SCORE")[1].split()[:2]]
+    assert got[0] == got[1]
+    assert abs(got[0] - want) <= 1e-5 * abs(want)
