@@ -120,9 +120,10 @@ def cpu_baseline_run(scene, frame, threads: int, sample=((4, 4, 4), (4, 4, 4))):
 
     g = synth.default_grid(*sample)
     t0 = time.perf_counter()
-    oracle.search_points(scene, scene.Twc, g, scene.xyzi, frame, threads=threads)
+    scores, _, _ = oracle.search_points(scene, scene.Twc, g, scene.xyzi, frame, threads=threads)
     dt = time.perf_counter() - t0
     n = g.n_pose
+    cpu_baseline_run.last_scores = scores  # the checker's answer, for the parity line of the N=1 run
     return n / dt, dt, f"{n}-pose grid {sample[0]}x{sample[1]} at full 1920x1080 / 10M points ({dt:.1f} s)"
 
 
@@ -255,6 +256,20 @@ def run_gpu(args):
         threads = os.cpu_count() or 1
         v, dt, sample = cpu_baseline_run(scene, frame, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        # the oracle just scored the whole workload: check the GPU's 4096 scores against it
+        # (outside every timed region; the checker is never on the measured path)
+        from oracle import oracle_py as oracle
+
+        want = cpu_baseline_run.last_scores
+        got = searcher.search(scene.Twc, grid, flags, want_scores=True)
+        rel = np.abs(got.scores.astype(np.float64) - want) / np.maximum(np.abs(want.astype(np.float64)), 1e-30)
+        cpu["parity"] = {"poses": int(want.size), "max_rel_err": float(rel.max()),
+                         "same_winner": bool(got.best_index == oracle.argmax(want)[0]),
+                         "tolerance": 1e-5}
+        t1 = time.perf_counter()
+        oracle.search_points(scene, scene.Twc, synth.default_grid((1, 1, 1), (1, 1, 1)), scene.xyzi, frame,
+                             threads=1)
+        cpu["single_eval_ms_1core"] = 1e3 * (time.perf_counter() - t1)  # one evaluation, one core
 
     if rank == 0:
         P = scene.W * scene.H

@@ -156,6 +156,8 @@ struct nmi_ctx {
   // hot-bin skipping of the histogram kernel (hist.cu): sampled mode per image; hot[0..1] =
   // largest mode count over the renders / warps, copied to h_feedback[5..6] after every
   // search so the NEXT search knows whether to launch the build with the side tables
+  DevBuf<float> term_tab;      // entropy term of every count 0..term_tab_len (4 B per pixel)
+  uint32_t term_tab_len = 0;
   DevBuf<uint32_t> img_mode, hot;
   int hist_skip = 1;  // 0 never, 1 automatic, 2 always ($NMI_HIST_SKIP, nmi_ctx_set_hist_skip)
   cudaEvent_t ev_hot = nullptr;
@@ -279,6 +281,16 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
     CK(c->records.reserve(want));
   }
   CK(cudaMemsetAsync(c->bin_total.p, 0, 4 * sizeof(uint32_t), c->stream));
+  return NMI_OK;
+}
+
+// entropy-term table of the histogram kernel: depends on the image size only
+int ensure_term_table(nmi_ctx* c, uint32_t length) {
+  if (c->term_tab.p && c->term_tab_len == length) return NMI_OK;
+  CK(c->term_tab.reserve((size_t)length + 1));
+  launch_term_table(c->term_tab.p, length, c->stream);
+  CK(cudaGetLastError());
+  c->term_tab_len = length;
   return NMI_OK;
 }
 
@@ -539,6 +551,8 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   a.mode = f->score_mode;
   a.variant = f->variant;
   a.scores = scores_dev ? scores_dev : c->scores.p;
+  if (int rc = ensure_term_table(c, (uint32_t)c->P)) return rc;
+  a.term_tab = c->term_tab.p;
   if (use_skip) {
     a.img_mode = c->img_mode.p;
     a.sample_total = image_mode_sample_total((uint32_t)c->P);
@@ -617,7 +631,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   c->bin_total.release(); c->records.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
-  c->img_mode.release(); c->hot.release(); c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
+  c->img_mode.release(); c->hot.release(); c->term_tab.release(); c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
   c->one_score.release(); c->zero_pair.release();
   for (int i = 0; i < 2; i++) {
     if (c->h_frame[i]) cudaFreeHost(c->h_frame[i]);
@@ -997,6 +1011,8 @@ static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped,
   a.mode = f->score_mode;
   a.variant = f->variant;
   a.scores = c->one_score.p;
+  if (int rc = ensure_term_table(c, npix)) return rc;
+  a.term_tab = c->term_tab.p;
   if (J || HA || HB) {
     if (!J) CK(c->dumpJ.reserve(65536));
     if (!HA || !HB) CK(c->dumpH.reserve(512));

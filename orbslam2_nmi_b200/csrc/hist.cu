@@ -132,15 +132,21 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 // ---- entropy pieces (NMI.cu:240-266) ---------------------------------------
+// log2f: correctly rounded (double log2, rounded once), the same value the CPU oracle uses --
+// two different <= 1 ulp libm log2f disagree enough to move a low SUC score by several 1e-5
+// (oracle/nmi_oracle.c: log2f_cr).  The double-precision call is paid once per image size:
+// term_table_kernel tabulates e(c) for every possible count 0..L.
+__device__ __forceinline__ float log2f_cr(float p) { return (float)log2((double)p); }
 __device__ __forceinline__ float term(uint32_t c, float L) {
   if (c == 0) return 0.0f;
   const float p = __fdiv_rn((float)c, L);
-  return __fmul_rn(p, log2f(p));
+  return __fmul_rn(p, log2f_cr(p));
 }
 // Same value as term(c, L): small counts (the vast majority of non-empty bins) are looked up in
 // the per-CTA table that was filled with term() itself, so the result is bit-identical.
-__device__ __forceinline__ float term_t(const float* tab, uint32_t c, float L) {
-  return c < (uint32_t)kTermTab ? tab[c] : term(c, L);
+__device__ __forceinline__ float term_t(const float* tab, const float* __restrict__ gtab, uint32_t c, float L) {
+  if (c < (uint32_t)kTermTab) return tab[c];   // shared-memory copy of the first entries
+  return gtab != nullptr ? __ldg(gtab + c) : term(c, L);  // full table (L2), else compute
 }
 // Pairwise tree of NMI.cu:270-287 / :295-338 for n = 32*K values, lane l holding
 // x[l + 32k]: strides 16K..32 fold k, strides 16..1 are shuffles. Result in lane 0.
@@ -326,8 +332,8 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
         rs += c[2 * k] + c[2 * k + 1];
         col[2 * k] += c[2 * k];
         col[2 * k + 1] += c[2 * k + 1];
-        vl[k] = term_t(sm.term_tab, c[2 * k], L);
-        vh[k] = term_t(sm.term_tab, c[2 * k + 1], L);
+        vl[k] = term_t(sm.term_tab, a.term_tab, c[2 * k], L);
+        vh[k] = term_t(sm.term_tab, a.term_tab, c[2 * k + 1], L);
         if (dump) {
           a.dumpJ[row * 256 + 2 * (lane + 32 * k)] = c[2 * k];
           a.dumpJ[row * 256 + 2 * (lane + 32 * k) + 1] = c[2 * k + 1];
@@ -361,7 +367,7 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
         const uint32_t c = sm.hist[lr * 256 + lane + 32 * k];
         rs += c;
         col[k] += c;
-        v[k] = term_t(sm.term_tab, c, L);
+        v[k] = term_t(sm.term_tab, a.term_tab, c, L);
         if (dump) a.dumpJ[row * 256 + lane + 32 * k] = c;
       }
       rs = warp_sum(rs);
@@ -392,7 +398,7 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
         const uint32_t c = sm.hist[row * 64 + lane + 32 * k];
         rs += c;
         col[k] += c;
-        v[k] = term_t(sm.term_tab, c, L);
+        v[k] = term_t(sm.term_tab, a.term_tab, c, L);
         if (dump) a.dumpJ[row * 64 + lane + 32 * k] = c;
       }
       rs = warp_sum(rs);
@@ -472,7 +478,11 @@ joint_hist_score_kernel(const HistArgs a) {
       for (int i = tid; i < 2 * kSkipCopies * 256; i += kThreads) (&sk.n1[0][0])[i] = 0;
       if (tid == 0) sk.nboth = 0;
     }
-    for (int i = tid; i < kTermTab; i += kThreads) sm.term_tab[i] = term((uint32_t)i, L);
+    // e(c) for c < kTermTab: from the per-image-size table of term_table_kernel, or computed here
+    if (a.term_tab != nullptr)
+      for (int i = tid; i < kTermTab && (uint32_t)i <= a.length; i += kThreads) sm.term_tab[i] = __ldg(a.term_tab + i);
+    else
+      for (int i = tid; i < kTermTab; i += kThreads) sm.term_tab[i] = term((uint32_t)i, L);
     if (tid == 0) {
       sm.ev_count = 0;
       for (int s = 0; s < kStages; s++) {
@@ -626,7 +636,7 @@ joint_hist_score_kernel(const HistArgs a) {
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const int i = lane + 32 * k;
-      v[k] = warp == 0 ? sm.rowE[i] : term(warp == 1 ? sm.HA[i] : sm.HB[i], L);
+      v[k] = warp == 0 ? sm.rowE[i] : term_t(sm.term_tab, a.term_tab, warp == 1 ? sm.HA[i] : sm.HB[i], L);
     }
     const float s = tree_lanes<K>(v);
     if (lane == 0) sm.sums[warp] = s;
@@ -639,6 +649,12 @@ joint_hist_score_kernel(const HistArgs a) {
   if (tid == 0)
     a.scores[a.out_index ? a.out_index[blockIdx.x] : blockIdx.x] =
         finish_score(sm.sums[1], sm.sums[2], sm.sums[0], a.mode);
+}
+
+// e(c) for every count 0..length (counts cannot exceed the pixel count)
+__global__ void term_table_kernel(float* __restrict__ tab, uint32_t length) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= length) tab[i] = term(i, (float)length);
 }
 
 // ---- sampled per-image mode (hot-bin skipping) ----------------------------------------
@@ -724,6 +740,10 @@ int launch_t(const HistArgs& a, cudaStream_t st) {
 }
 
 }  // namespace
+
+void launch_term_table(float* tab, uint32_t length, cudaStream_t st) {
+  term_table_kernel<<<(length + 256) / 256, 256, 0, st>>>(tab, length);
+}
 
 uint32_t image_mode_sample_total(uint32_t npix) { return ((npix / 16 + 63) / 64) * 16; }
 

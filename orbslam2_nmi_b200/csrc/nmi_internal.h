@@ -49,6 +49,8 @@ struct HistArgs {
   uint32_t length;  // kernel.cu:85: always W*H
   int bins, bg, mode, variant;
   float* scores;
+  // optional: e(c) = (c/length) log2(c/length) for c = 0..length, from launch_term_table
+  const float* term_tab;
   // hot-bin skipping (hist.cu): per image, sampled count << 8 | level of its most frequent
   // grey level (renders [0, nrenders), then the warps); sample_total = pixels sampled per
   // image; skip_mode 0 never, 1 when a pair's two levels cover >= 1/6 of the samples,
@@ -69,6 +71,7 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st);  // returns lau
 int launch_image_modes(const uint8_t* renders, size_t rpitch, int nr, const uint8_t* warps, size_t wpitch,
                        int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st);
 uint32_t image_mode_sample_total(uint32_t npix);
+void launch_term_table(float* tab, uint32_t length, cudaStream_t st);
 int hist_configure();  // cudaFuncSetAttribute for the big-smem kernels; 0 on success
 
 // --- argmax.cu -------------------------------------------------------------
