@@ -394,6 +394,26 @@ def test_full_size_search_matches_oracle(searcher, oracle):
         assert np.array_equal(searcher.get_render(v), img), f"render {v}"
 
 
+def test_full_size_mesh_matches_oracle(searcher, oracle):
+    """BASELINE configs[2] shape at full size (848x480 frame, 2 M triangles, 64 bins) on a small
+    grid: renders bit-exact, scores within 1e-5, same winner."""
+    c = synth.CONFIGS["C3"]
+    sc = synth.make_scene("C3", n_points=10)
+    verts, tris = synth.make_mesh(1000, 1000)
+    g = Grid.make((3, 2, 1), (2, 1, 2), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    frame = synth.frame_textured(c["W"], c["H"])
+    searcher.set_camera(c["W"], c["H"], c["fx"], c["fy"], c["cx"], c["cy"], synth.ZN, synth.ZF, 3.0)
+    searcher.set_mesh(verts, tris)
+    searcher.set_frame(frame)
+    res = searcher.search(synth.prior_pose(), g, searcher.flags(bins=64), want_scores=True)
+    sc.Twc = synth.prior_pose()
+    scores, renders, _ = oracle.search_mesh(sc, sc.Twc, g, verts, tris, frame, bins=64, keep_images=True)
+    for v in range(g.n_synth):
+        assert np.array_equal(searcher.get_render(v), renders[v]), f"mesh render {v}"
+    assert_scores_close(res.scores, scores)
+    assert res.best_index == oracle.argmax(scores)[0]
+
+
 # ------------------------------------------------------------ multi-level driver ----
 @pytest.mark.parametrize("threshold,dist", [(0.05, (0, 0, 0)), (0.9, (0, 0, 0)), (0.3, (30.0, 0, 0))])
 def test_relocalize_matches_oracle_driver(searcher, oracle, threshold, dist):
