@@ -394,6 +394,27 @@ def test_full_size_search_matches_oracle(searcher, oracle):
         assert np.array_equal(searcher.get_render(v), img), f"render {v}"
 
 
+def test_full_size_relocalize_matches_oracle_driver(searcher, oracle):
+    """The level driver on the C2 scene (1920x1080, 10 M points, the reference's 3^6 grid): its
+    stop rules compare score ratios against 1.001 (Tracking.cc:2112-2121), so they are the
+    most sensitive consumer of the score bits -- same levels, same decisions, same pose."""
+    sc = synth.make_scene("C2")
+    g0 = synth.default_grid()
+    t = oracle.cell_translation(sc.Twc, g0, 2, 0, 1)
+    _, img = oracle.render_points(sc, sc.Twc, t, sc.xyzi)
+    frame = synth.frame_from_render(img, seed=11)
+    searcher.set_scene(sc)
+    searcher.set_frame(frame)
+    got = searcher.relocalize(sc.Twc, g0, threshold=0.02)
+    rc, want = oracle.relocalize_points(sc, sc.Twc, g0, sc.xyzi, frame, 0.02)
+    assert rc == 0
+    assert (got.iterations, got.relocalized, got.failed) == (want.iterations, want.relocalized, want.failed)
+    assert list(got.best_s) == list(want.best_s) and list(got.best_w) == list(want.best_w)
+    assert np.array_equal(np.array(got.Twc[:]), np.array(want.Twc[:]))
+    assert got.nmi == pytest.approx(want.nmi, rel=SCORE_RTOL)
+    assert got.n_levels == got.iterations
+
+
 def test_full_size_mesh_matches_oracle(searcher, oracle):
     """BASELINE configs[2] shape at full size (848x480 frame, 2 M triangles, 64 bins) on a small
     grid: renders bit-exact, scores within 1e-5, same winner."""
