@@ -142,6 +142,13 @@ struct nmi_ctx {
   DevBuf<uint4> records;
 
   DevBuf<uint8_t> frame;
+  // the same frame as a gather-capable array + point-sampled border-0 texture for the warp
+  // kernel ($NMI_WARP_TEX=0 keeps the plain-load kernel); refreshed lazily before a warp launch
+  cudaArray_t frame_arr = nullptr;
+  cudaTextureObject_t frame_tex = 0;
+  int frame_arr_w = 0, frame_arr_h = 0;
+  bool frame_tex_dirty = true;
+  bool use_warp_tex = true;
   // two pinned staging buffers for pageable host frames: frame k+1 is copied in while the
   // H2D of frame k (and whatever follows it on the stream) is still in flight
   unsigned char* h_frame[2] = {nullptr, nullptr};
@@ -281,6 +288,39 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
     CK(c->records.reserve(want));
   }
   CK(cudaMemsetAsync(c->bin_total.p, 0, 4 * sizeof(uint32_t), c->stream));
+  return NMI_OK;
+}
+
+// Frame -> texture for the warp kernel; enqueued on `st` right before the warp launch.
+int ensure_frame_texture(nmi_ctx* c, cudaStream_t st, cudaTextureObject_t* tex) {
+  *tex = 0;
+  if (!c->use_warp_tex) return NMI_OK;
+  if (!c->frame_arr || c->frame_arr_w != c->cam.W || c->frame_arr_h != c->cam.H) {
+    if (c->frame_tex) cudaDestroyTextureObject(c->frame_tex);
+    if (c->frame_arr) cudaFreeArray(c->frame_arr);
+    c->frame_tex = 0;
+    c->frame_arr = nullptr;
+    const cudaChannelFormatDesc desc = cudaCreateChannelDesc<unsigned char>();
+    CK(cudaMallocArray(&c->frame_arr, &desc, (size_t)c->cam.W, (size_t)c->cam.H, cudaArrayTextureGather));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->frame_arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder;  // BORDER_CONSTANT 0 (image.cpp:123)
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    CK(cudaCreateTextureObject(&c->frame_tex, &rd, &td, nullptr));
+    c->frame_arr_w = c->cam.W;
+    c->frame_arr_h = c->cam.H;
+    c->frame_tex_dirty = true;
+  }
+  if (c->frame_tex_dirty) {
+    CK(cudaMemcpy2DToArrayAsync(c->frame_arr, 0, 0, c->frame.p, (size_t)c->cam.W, (size_t)c->cam.W,
+                                (size_t)c->cam.H, cudaMemcpyDeviceToDevice, st));
+    c->frame_tex_dirty = false;
+  }
+  *tex = c->frame_tex;
   return NMI_OK;
 }
 
@@ -505,7 +545,9 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   // latency-bound) on a second stream; both only need the uploaded parameters
   CK(cudaEventRecord(c->ev_fork, c->stream));
   CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-  launch_warp(c->frame.p, c->cam.W, c->cam.H, d_minv, nwl, c->warps.p, c->pitch, c->stream2);
+  cudaTextureObject_t frame_tex = 0;
+  if (int rc = ensure_frame_texture(c, c->stream2, &frame_tex)) return rc;
+  launch_warp(c->frame.p, frame_tex, c->cam.W, c->cam.H, d_minv, nwl, c->warps.p, c->pitch, c->stream2);
   c->launches++;
   CK(cudaEventRecord(c->ev_join, c->stream2));
   if (int rc = cull_model(c, vc, Twc, margin)) return rc;
@@ -614,6 +656,7 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   CK(c->zero_pair.reserve(1));
   CK(cudaMemset(c->zero_pair.p, 0, sizeof(int2)));
   c->timed = true;
+  if (const char* e = getenv("NMI_WARP_TEX")) c->use_warp_tex = atoi(e) != 0;
   if (const char* e = getenv("NMI_HIST_SKIP")) {
     const int m = atoi(e);
     if (m >= 0 && m <= 2) c->hist_skip = m;
@@ -642,6 +685,8 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (c->ev_params) cudaEventDestroy(c->ev_params);
   if (c->ev_feedback) cudaEventDestroy(c->ev_feedback);
   if (c->ev_hot) cudaEventDestroy(c->ev_hot);
+  if (c->frame_tex) cudaDestroyTextureObject(c->frame_tex);
+  if (c->frame_arr) cudaFreeArray(c->frame_arr);
   if (c->h_feedback) cudaFreeHost(c->h_feedback);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -853,6 +898,7 @@ int nmi_set_frame(nmi_ctx* c, const uint8_t* gray, int W, int H) {
     CK(cudaMemcpyAsync(c->frame.p, c->h_frame[slot], c->P, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev_frame[slot], c->stream));
   }
+  c->frame_tex_dirty = true;
   c->has_frame = true;
   return NMI_OK;
 }
@@ -864,6 +910,7 @@ int nmi_set_frame_device(nmi_ctx* c, const void* gray_dev, int W, int H) {
   CK(cudaSetDevice(c->device));
   CK(c->frame.reserve(c->pitch));
   CK(cudaMemcpyAsync(c->frame.p, gray_dev, c->P, cudaMemcpyDeviceToDevice, c->stream));
+  c->frame_tex_dirty = true;
   c->has_frame = true;
   return NMI_OK;
 }
@@ -972,7 +1019,9 @@ int nmi_warp_cells(nmi_ctx* c, const nmi_grid* g) {
     nmi_cell_homography_inv(&c->cam, g, wx, wy, wz, hm + 9 * (size_t)w);
   }
   CK(cudaMemcpyAsync(c->params.p, c->h_params, bytes, cudaMemcpyHostToDevice, c->stream));
-  launch_warp(c->frame.p, c->cam.W, c->cam.H, reinterpret_cast<const float*>(c->params.p), nW,
+  cudaTextureObject_t frame_tex = 0;
+  if (int rc = ensure_frame_texture(c, c->stream, &frame_tex)) return rc;
+  launch_warp(c->frame.p, frame_tex, c->cam.W, c->cam.H, reinterpret_cast<const float*>(c->params.p), nW,
               c->warps.p, c->pitch, c->stream);
   CK(cudaGetLastError());
   c->has_search = false;

@@ -34,8 +34,10 @@ void launch_resolve(unsigned long long* zbuf, const uint8_t* val, int nviews, si
                     cudaStream_t st);
 
 // --- warp.cu ---------------------------------------------------------------
-void launch_warp(const uint8_t* src, int W, int H, const float* minv /*nW x 9, device*/,
-                 int nW, uint8_t* dst, size_t pitch, cudaStream_t st);
+// tex != 0: the frame as a point-sampled, border-0 u8 texture over a gather-capable array
+// (same pixels as src); the kernel then fetches the four bilinear taps with one gather
+void launch_warp(const uint8_t* src, cudaTextureObject_t tex, int W, int H,
+                 const float* minv /*nW x 9, device*/, int nW, uint8_t* dst, size_t pitch, cudaStream_t st);
 
 // --- hist.cu ---------------------------------------------------------------
 struct HistArgs {
