@@ -37,6 +37,13 @@ extern "C" {
 #define NMI_ERR_STATE 3     /* camera / model / frame not set yet            */
 #define NMI_ERR_NO_WINNER 4 /* every score < 0: the reference's max-vector   */
                             /* is empty (helperFunctions.cpp:50-103)         */
+#define NMI_ERR_RETRY 5     /* a rank's enqueued search was incomplete (its   */
+                            /* splat-record bins filled up): redo the level  */
+/* Key an enqueued search leaves instead of a winner when its renders are
+ * incomplete.  Above every real key in signed and unsigned order (its score
+ * word is a NaN pattern, which never wins find_max_elements), so the
+ * max-allreduce hands it to every rank and all ranks redo the level together. */
+#define NMI_KEY_RETRY 0x7FFFFFFFFFFFFFFFull
 
 #define NMI_SCORE_ENMI 0 /* kernel.cuh:22  (H(A)+H(B))/H(A,B)                */
 #define NMI_SCORE_SUC 1  /* kernel.cuh:23  2(1-H(A,B)/(H(A)+H(B))) (default) */
@@ -135,8 +142,11 @@ int nmi_search_enqueue(nmi_ctx *ctx, const float Twc[16], const nmi_grid *grid,
 /* Pose-grid partitioner: axis 0 = synthetic views, 1 = warps.    */
 int nmi_partition(const nmi_grid *grid, int rank, int world, int *axis,
                   int *begin, int *end);
-/* find_max_elements' answer from a (reduced) key.                            */
+/* find_max_elements' answer from a (reduced) key.  NMI_ERR_RETRY for
+ * NMI_KEY_RETRY, NMI_ERR_NO_WINNER when the low word is 0.                    */
 int nmi_decode_key(const nmi_grid *grid, uint64_t key, nmi_result *out);
+/* Stream-synchronise, then copy the (reduced) 8-byte key at key_dev to *key.  */
+int nmi_read_key(nmi_ctx *ctx, const void *key_dev, uint64_t *key);
 
 /* ---- the coarse-to-fine driver ------------------------------------------ */
 #define NMI_MAX_PREV_POSES 8
@@ -185,6 +195,33 @@ void nmi_grid_from_motion(const nmi_grid *initial, const float dist[3],
 int nmi_relocalize(nmi_ctx *ctx, const float Twc[16], const nmi_grid *start_grid,
                    const nmi_flags *flags, const nmi_reloc_params *params,
                    nmi_reloc_result *out);
+
+/* The same driver with the per-level grid search supplied by the caller: `search`
+ * stands where Tracking::RelocalizeWithNMI (src/Tracking.cc:1851-1985) stands in the
+ * reference -- score the grid around `Twc`, fill *out with the winner (best_s, best_w,
+ * best_score; gpu_ms optional) and return NMI_OK, or an error code that aborts the
+ * driver.  nmi_relocalize and nmi_relocalize_sharded are this driver over nmi_search
+ * and over the sharded search below.                                              */
+typedef int (*nmi_level_search_fn)(void *user, const float Twc[16],
+                                   const nmi_grid *grid, nmi_result *out);
+int nmi_relocalize_with(nmi_level_search_fn search, void *user, const float Twc[16],
+                        const nmi_grid *start_grid, const nmi_reloc_params *params,
+                        nmi_reloc_result *out);
+
+/* Multi-GPU coarse-to-fine search (BASELINE config 4): every rank runs
+ * this driver with the same arguments; each level is one nmi_search_enqueue of the
+ * rank's slice followed by `exchange`, which must max-reduce the u64 at key_dev over
+ * all ranks, in place, on `stream` (one ncclAllReduce(ncclUint64 / ncclInt64, ncclMax,
+ * 8 bytes); torch.distributed.all_reduce in the harness) and return 0.  All ranks
+ * then decode the same winner, resize the grid identically and go on; no other
+ * data moves between GPUs.  A rank whose splat-record bins filled up publishes
+ * NMI_KEY_RETRY and every rank redoes that level once with exact sizing.
+ * key_dev: 8 bytes of device memory on the context's GPU (the collective's buffer). */
+typedef int (*nmi_exchange_fn)(void *user, void *key_dev, void *stream);
+int nmi_relocalize_sharded(nmi_ctx *ctx, const float Twc[16], const nmi_grid *start_grid,
+                           const nmi_flags *flags, const nmi_reloc_params *params,
+                           int rank, int world, void *key_dev,
+                           nmi_exchange_fn exchange, void *user, nmi_reloc_result *out);
 
 /* ---- stage-level entry points (the reference's own call granularity) ---- */
 /* Rendering::renderToTextureOnGPU(calculateTranslation(sx,sy,sz))

@@ -93,6 +93,12 @@ class Result(C.Structure):
 # every symbol include/nmi_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 _F16 = C.POINTER(C.c_float)
+# nmi_level_search_fn / nmi_exchange_fn (include/nmi_b200.h)
+LEVEL_SEARCH_FN = C.CFUNCTYPE(C.c_int, _P, _F16, C.POINTER(Grid), C.POINTER(Result))
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, _P, _P, _P)
+NMI_ERR_NO_WINNER = 4
+NMI_ERR_RETRY = 5
+NMI_KEY_RETRY = 0x7FFFFFFFFFFFFFFF
 SYMBOLS = [
     ("nmi_ctx_create", C.c_int, [C.c_int, C.POINTER(_P)]),
     ("nmi_ctx_destroy", None, [_P]),
@@ -114,6 +120,11 @@ SYMBOLS = [
     ("nmi_grid_from_motion", None, [C.POINTER(Grid), _P, _P, C.c_int, C.POINTER(Grid)]),
     ("nmi_relocalize", C.c_int, [_P, _P, C.POINTER(Grid), C.POINTER(Flags), C.POINTER(RelocParams),
                                  C.POINTER(RelocResult)]),
+    ("nmi_relocalize_with", C.c_int, [LEVEL_SEARCH_FN, _P, _P, C.POINTER(Grid), C.POINTER(RelocParams),
+                                      C.POINTER(RelocResult)]),
+    ("nmi_relocalize_sharded", C.c_int, [_P, _P, C.POINTER(Grid), C.POINTER(Flags), C.POINTER(RelocParams),
+                                         C.c_int, C.c_int, _P, EXCHANGE_FN, _P, C.POINTER(RelocResult)]),
+    ("nmi_read_key", C.c_int, [_P, _P, C.POINTER(C.c_uint64)]),
     ("nmi_render_at", C.c_int, [_P, _P, _P, C.POINTER(C.c_uint)]),
     ("nmi_render_cell", C.c_int, [_P, _P, C.POINTER(Grid), C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_uint)]),

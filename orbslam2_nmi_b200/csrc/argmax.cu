@@ -17,7 +17,8 @@ constexpr int kArgThreads = 1024;
 
 __global__ void __launch_bounds__(kArgThreads)
 argmax_kernel(const float* __restrict__ scores, const uint32_t* __restrict__ list, int n_list,
-              uint32_t n_total, unsigned long long* __restrict__ key) {
+              uint32_t n_total, unsigned long long* __restrict__ key,
+              const uint32_t* __restrict__ retry_flag) {
   __shared__ float s_max[32];
   __shared__ uint32_t s_idx[32];
   __shared__ float s_m;
@@ -55,16 +56,20 @@ argmax_kernel(const float* __restrict__ scores, const uint32_t* __restrict__ lis
     uint32_t x = s_idx[lane];
 #pragma unroll
     for (int d = 16; d >= 1; d /= 2) x = min(x, __shfl_xor_sync(0xffffffffu, x, d));
-    if (lane == 0)
-      *key = ((unsigned long long)__float_as_uint(m) << 32) | (unsigned long long)(0xFFFFFFFFu - x);
+    if (lane == 0) {
+      // incomplete renders (record bins overflowed): publish the retry key, never a winner
+      const bool retry = retry_flag != nullptr && *retry_flag != 0;
+      *key = retry ? NMI_KEY_RETRY
+                   : ((unsigned long long)__float_as_uint(m) << 32) | (unsigned long long)(0xFFFFFFFFu - x);
+    }
   }
 }
 
 }  // namespace
 
 void launch_argmax(const float* scores, const uint32_t* index_list, int n_list, uint32_t n_total,
-                   unsigned long long* key, cudaStream_t st) {
-  argmax_kernel<<<1, kArgThreads, 0, st>>>(scores, index_list, n_list, n_total, key);
+                   unsigned long long* key, const uint32_t* retry_flag, cudaStream_t st) {
+  argmax_kernel<<<1, kArgThreads, 0, st>>>(scores, index_list, n_list, n_total, key, retry_flag);
 }
 
 }  // namespace nmi

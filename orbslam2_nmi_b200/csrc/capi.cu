@@ -136,6 +136,7 @@ struct nmi_ctx {
   cudaEvent_t ev_feedback = nullptr;
   bool feedback_pending = false;
   bool force_conservative = false;
+  bool conservative_once = false;  // an enqueued search overflowed: size the next one exactly
   // binned tile renderer scratch (point clouds)
   DevBuf<uint32_t> bin_offsets, bin_cursor;  // [views of a group * tiles]
   DevBuf<uint32_t> bin_total;                // [0] records of the group, [1] overflow flag
@@ -242,7 +243,7 @@ int vc_point_size(const nmi_camera& cam) {
 // synchronous entry point turns into an error (never a silently wrong render).
 int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   const size_t tiles = (size_t)tiles_per_view(c->cam.W, c->cam.H);
-  const bool fb = c->h_feedback && !c->force_conservative && c->feedback_pending &&
+  const bool fb = c->h_feedback && !c->force_conservative && !c->conservative_once && c->feedback_pending &&
                   cudaEventQuery(c->ev_feedback) == cudaSuccess && c->h_feedback[4] > 0 &&
                   c->h_feedback[2] == 0;
   CK(c->bin_total.reserve(4));
@@ -606,11 +607,15 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   REQUIRE(nl >= 0, NMI_ERR_CUDA, "histogram kernel configuration failed");
   c->launches += nl;
   if (c->timed) CK(cudaEventRecord(c->ev[5], c->stream));
-  launch_argmax(a.scores, d_index, (int)npl, (uint32_t)nP, key_dev ? key_dev : c->key.p, c->stream);
+  // an enqueued (multi-GPU) search whose record bins filled up publishes NMI_KEY_RETRY instead
+  // of a winner taken from incomplete renders
+  launch_argmax(a.scores, d_index, (int)npl, (uint32_t)nP, key_dev ? key_dev : c->key.p,
+                key_dev && tiled ? c->bin_total.p + 1 : nullptr, c->stream);
   c->launches++;
   if (c->timed) CK(cudaEventRecord(c->ev[6], c->stream));
   CK(cudaGetLastError());
 
+  c->conservative_once = false;
   c->has_search = true;
   c->grid = *g;
   c->nvl = nvl;
@@ -707,7 +712,7 @@ int nmi_ctx_sync(nmi_ctx* c) {
   REQUIRE(c, NMI_ERR_INVALID, "null ctx");
   CK(cudaStreamSynchronize(c->stream));
   if (c->feedback_pending && c->h_feedback && c->h_feedback[2] != 0) {
-    c->force_conservative = true;  // the next search uses the pose-independent sizing
+    c->conservative_once = true;  // the next search uses the pose-independent sizing
     set_error("tile renderer record buffer overflow in an enqueued search: its renders are incomplete; "
               "re-enqueue it");
     c->h_feedback[2] = 0;
@@ -945,6 +950,19 @@ int nmi_search(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fla
   out->gpu_ms = ms;
   if (rc == NMI_ERR_NO_WINNER) set_error("every score is negative: no winner");
   return rc;
+}
+
+int nmi_read_key(nmi_ctx* c, const void* key_dev, uint64_t* key) {
+  REQUIRE(c && key_dev && key, NMI_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(key, key_dev, sizeof *key, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  // a local overflow is also visible in the pinned feedback words: size the next search exactly
+  if (c->feedback_pending && c->h_feedback && c->h_feedback[2] != 0) {
+    c->conservative_once = true;
+    c->h_feedback[2] = 0;
+  }
+  return NMI_OK;
 }
 
 int nmi_search_enqueue(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_flags* f,

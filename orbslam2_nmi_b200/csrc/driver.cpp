@@ -35,9 +35,9 @@ void nmi_grid_from_motion(const nmi_grid* initial, const float dist[3], const fl
   }
 }
 
-int nmi_relocalize(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid* start_grid,
-                   const nmi_flags* flags, const nmi_reloc_params* prm, nmi_reloc_result* out) {
-  if (!ctx || !Twc_in || !start_grid || !flags || !prm || !out) {
+int nmi_relocalize_with(nmi_level_search_fn search, void* user, const float Twc_in[16],
+                        const nmi_grid* start_grid, const nmi_reloc_params* prm, nmi_reloc_result* out) {
+  if (!search || !Twc_in || !start_grid || !prm || !out) {
     nmi::set_error("nmi_relocalize: null argument");
     return NMI_ERR_INVALID;
   }
@@ -63,7 +63,7 @@ int nmi_relocalize(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid* start_g
 
     // ---- RelocalizeWithNMI: one batched grid search around `pose` ----
     nmi_result r{};
-    const int rc = nmi_search(ctx, pose, &kernel, flags, &r, nullptr);
+    const int rc = search(user, pose, &kernel, &r);
     if (rc != NMI_OK) return rc;  // NMI_ERR_NO_WINNER is the reference's UB case: surface it
     out->gpu_ms += r.gpu_ms;
     out->n_evals += kernel.nS[0] * kernel.nS[1] * kernel.nS[2] * kernel.nW[0] * kernel.nW[1] * kernel.nW[2];
@@ -128,6 +128,72 @@ int nmi_relocalize(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid* start_g
     out->best_w[k] = best.best_w[k];
   }
   return NMI_OK;
+}
+
+namespace {
+
+struct SingleSearch {
+  nmi_ctx* ctx;
+  const nmi_flags* flags;
+};
+int single_level(void* user, const float Twc[16], const nmi_grid* grid, nmi_result* out) {
+  const SingleSearch* s = static_cast<const SingleSearch*>(user);
+  return nmi_search(s->ctx, Twc, grid, s->flags, out, nullptr);
+}
+
+// One level of the multi-GPU driver: this rank's slice, then the 8-byte max-allreduce of the
+// packed key on the context's stream, then every rank decodes the same winner.
+struct ShardedSearch {
+  nmi_ctx* ctx;
+  const nmi_flags* flags;
+  int rank, world;
+  void* key_dev;
+  nmi_exchange_fn exchange;
+  void* user;
+};
+int sharded_level(void* user, const float Twc[16], const nmi_grid* grid, nmi_result* out) {
+  const ShardedSearch* s = static_cast<const ShardedSearch*>(user);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (int rc = nmi_search_enqueue(s->ctx, Twc, grid, s->flags, s->rank, s->world, s->key_dev, nullptr)) return rc;
+    if (s->exchange(s->user, s->key_dev, nmi_ctx_stream(s->ctx)) != 0) {
+      nmi::set_error("nmi_relocalize_sharded: the exchange callback failed");
+      return NMI_ERR_CUDA;
+    }
+    uint64_t key = 0;
+    if (int rc = nmi_read_key(s->ctx, s->key_dev, &key)) return rc;
+    const int rc = nmi_decode_key(grid, key, out);
+    // some rank's record bins filled up: all ranks saw NMI_KEY_RETRY and redo the level (the
+    // rank concerned sizes its bins exactly this time)
+    if (rc != NMI_ERR_RETRY) {
+      if (rc == NMI_ERR_NO_WINNER) nmi::set_error("every score is negative: no winner");
+      return rc;
+    }
+  }
+  nmi::set_error("nmi_relocalize_sharded: a rank's splat-record buffer overflowed twice");
+  return NMI_ERR_CUDA;
+}
+
+}  // namespace
+
+int nmi_relocalize(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid* start_grid,
+                   const nmi_flags* flags, const nmi_reloc_params* prm, nmi_reloc_result* out) {
+  if (!ctx || !flags) {
+    nmi::set_error("nmi_relocalize: null argument");
+    return NMI_ERR_INVALID;
+  }
+  SingleSearch s{ctx, flags};
+  return nmi_relocalize_with(single_level, &s, Twc_in, start_grid, prm, out);
+}
+
+int nmi_relocalize_sharded(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid* start_grid,
+                           const nmi_flags* flags, const nmi_reloc_params* prm, int rank, int world,
+                           void* key_dev, nmi_exchange_fn exchange, void* user, nmi_reloc_result* out) {
+  if (!ctx || !flags || !key_dev || !exchange || world < 1 || rank < 0 || rank >= world) {
+    nmi::set_error("nmi_relocalize_sharded: bad argument");
+    return NMI_ERR_INVALID;
+  }
+  ShardedSearch s{ctx, flags, rank, world, key_dev, exchange, user};
+  return nmi_relocalize_with(sharded_level, &s, Twc_in, start_grid, prm, out);
 }
 
 }  // extern "C"

@@ -208,6 +208,11 @@ int nmi_decode_key(const nmi_grid* g, uint64_t key, nmi_result* out) {
   const uint32_t hi = static_cast<uint32_t>(key >> 32), lo = static_cast<uint32_t>(key);
   std::memcpy(&out->best_score, &hi, 4);
   out->key = key;
+  if (key == NMI_KEY_RETRY) {
+    out->best_index = -1;
+    for (int k = 0; k < 3; ++k) out->best_s[k] = out->best_w[k] = -1;
+    return NMI_ERR_RETRY;
+  }
   if (lo == 0) {
     out->best_index = -1;
     for (int k = 0; k < 3; ++k) out->best_s[k] = out->best_w[k] = -1;

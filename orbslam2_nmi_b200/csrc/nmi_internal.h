@@ -79,7 +79,7 @@ int hist_configure();  // cudaFuncSetAttribute for the big-smem kernels; 0 on su
 // --- argmax.cu -------------------------------------------------------------
 // key = (bits(max(0, scores)) << 32) | (0xFFFFFFFF - lowest index with score == max)
 void launch_argmax(const float* scores, const uint32_t* index_list, int n_list, uint32_t n_total,
-                   unsigned long long* key, cudaStream_t st);
+                   unsigned long long* key, const uint32_t* retry_flag, cudaStream_t st);
 
 // --- host_math.cpp ----------------------------------------------------------
 void make_view_const(const nmi_camera& cam, const float Twc[16], ViewConst* vc);

@@ -67,3 +67,40 @@ def sharded_search(searcher, Twc, grid: Grid, flags: Flags, key_tensor, rank: in
         allreduce_key(key_tensor)
     (stream or torch.cuda.current_stream()).synchronize()
     return searcher.decode(grid, int(key_tensor.item()))
+
+
+def relocalize_sharded(searcher, Twc, grid: Grid, flags: Flags | None, key_tensor, rank: int, world: int,
+                       **kw):
+    """BASELINE config 4: the coarse-to-fine driver with every level sharded over the ranks of
+    the default process group (csrc/driver.cpp nmi_relocalize_sharded).  The exchange step is one
+    8-byte MAX all_reduce of `key_tensor` (int64, on the searcher's GPU) per level, enqueued by
+    NCCL on the searcher's own stream right behind the argmax kernel."""
+    import torch
+
+    assert key_tensor.is_cuda and key_tensor.numel() == 1 and key_tensor.dtype == torch.int64
+
+    def exchange(key_dev: int, stream: int):
+        assert key_dev == key_tensor.data_ptr()
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=key_tensor.device)):
+            allreduce_key(key_tensor)
+
+    return searcher.relocalize_sharded(Twc, grid, flags, rank, world, key_tensor.data_ptr(), exchange, **kw)
+
+
+def relocalize_sharded_host(level_scores, Twc, grid: Grid, rank: int, world: int, reduce_max, **kw):
+    """The same driver with the per-rank scoring supplied by the caller -- the host-side logic
+    of the multi-GPU level driver without a GPU (CPU tests: gloo, world_size 2).
+    level_scores(Twc, grid, indices) -> scores of this rank's linear indices;
+    reduce_max(int key) -> int is the exchange step."""
+
+    def level(T, g):
+        idx = shard_indices(g, rank, world)
+        full = np.full(g.n_pose, -1.0, dtype=np.float32)
+        full[idx] = np.asarray(level_scores(T, g, idx), dtype=np.float32)
+        key = int(reduce_max(local_key_from_scores(full, idx)))
+        r = _search.decode_key(g, key)
+        if r.best_index < 0:
+            return 4  # NMI_ERR_NO_WINNER
+        return r.best_s, r.best_w, r.best_score
+
+    return _search.relocalize_with(level, Twc, grid, **kw)

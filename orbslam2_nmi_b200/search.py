@@ -131,6 +131,33 @@ class NmiSearcher:
                                       C.byref(out)))
         return out
 
+    def relocalize_sharded(self, Twc, grid: Grid, flags: Flags | None, rank: int, world: int, key_dev: int,
+                           exchange, threshold=0.1, max_iterations=4, dist=(0.0, 0.0, 0.0),
+                           rot=(0.0, 0.0, 0.0)):
+        """nmi_relocalize_sharded: the level driver with every level sharded over `world` ranks;
+        `exchange(key_dev, stream)` max-reduces the 8-byte key in place on that stream."""
+        Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
+        flags = flags or self.flags()
+        prm = capi.RelocParams(threshold, max_iterations, (C.c_float * 3)(*dist), (C.c_float * 3)(*rot))
+        out = capi.RelocResult()
+        failure = []
+
+        def _cb(_user, kdev, stream):
+            try:
+                exchange(kdev, stream)
+                return 0
+            except BaseException as e:  # never unwind through the C frame
+                failure.append(e)
+                return 1
+
+        cb = capi.EXCHANGE_FN(_cb)
+        rc = self.lib.nmi_relocalize_sharded(self.h, ptr(Twc), C.byref(grid), C.byref(flags), C.byref(prm),
+                                             rank, world, C.c_void_p(key_dev), cb, None, C.byref(out))
+        if failure:
+            raise failure[0]
+        check(rc)
+        return out
+
     # -- stage-level API (reference call granularity) ------------------------------
     def render_cell(self, Twc, grid: Grid, sx, sy, sz) -> int:
         Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
@@ -236,6 +263,41 @@ def grid_from_motion(initial: Grid, dist, rot, not_initialized=False) -> Grid:
     d = np.asarray(dist, dtype=np.float32)
     r = np.asarray(rot, dtype=np.float32)
     capi.load().nmi_grid_from_motion(C.byref(initial), ptr(d), ptr(r), int(not_initialized), C.byref(out))
+    return out
+
+
+def relocalize_with(level_search, Twc, grid: Grid, threshold=0.1, max_iterations=4, dist=(0.0, 0.0, 0.0),
+                    rot=(0.0, 0.0, 0.0)):
+    """nmi_relocalize_with: the coarse-to-fine driver (host logic only, no GPU needed) over a
+    caller-supplied level search  level_search(Twc[4x4], grid) -> (best_s, best_w, best_score)
+    or an integer error code."""
+    Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
+    prm = capi.RelocParams(threshold, max_iterations, (C.c_float * 3)(*dist), (C.c_float * 3)(*rot))
+    out = capi.RelocResult()
+    failure = []
+
+    def _cb(_user, twc_p, grid_p, res_p):
+        try:
+            T = np.array([twc_p[i] for i in range(16)], dtype=np.float32).reshape(4, 4)
+            r = level_search(T, grid_p.contents.copy())
+            if isinstance(r, int):
+                return r
+            bs, bw, score = r
+            res = res_p.contents
+            for k in range(3):
+                res.best_s[k] = int(bs[k])
+                res.best_w[k] = int(bw[k])
+            res.best_score = float(score)
+            return 0
+        except BaseException as e:
+            failure.append(e)
+            return capi.NMI_ERR_INVALID
+
+    cb = capi.LEVEL_SEARCH_FN(_cb)
+    rc = capi.load().nmi_relocalize_with(cb, None, ptr(Twc), C.byref(grid), C.byref(prm), C.byref(out))
+    if failure:
+        raise failure[0]
+    check(rc)
     return out
 
 

@@ -557,3 +557,107 @@ def test_record_buffer_guess_overflow_is_recovered(searcher, oracle):
         for s in range(g.n_synth):
             assert np.array_equal(searcher.get_render(s), renders[s])
         assert_scores_close(res.scores, scores)
+
+
+# ------------------------------------------- sharded coarse-to-fine driver (C4) ----
+def _two_rank_reloc(nmi_lib, sc, frame, g0, Twc, world=2, prime=None, **kw):
+    """`world` contexts on cuda:0, one thread each, run nmi_relocalize_sharded as ranks 0..world-1;
+    the exchange step (an NCCL max-allreduce in production) is a barrier + max over the ranks'
+    device keys."""
+    import threading
+
+    import torch
+
+    from orbslam2_nmi_b200.search import NmiSearcher
+
+    searchers = [NmiSearcher(0) for _ in range(world)]
+    keys = [torch.zeros(1, dtype=torch.int64, device="cuda:0") for _ in range(world)]
+    torch.cuda.synchronize()
+    barrier = threading.Barrier(world)
+    seen = [[] for _ in range(world)]
+    local = [0] * world
+    out, err = [None] * world, [None] * world
+
+    def run(rank):
+        try:
+            s = searchers[rank]
+            s.set_scene(sc)
+            s.set_frame(frame)
+            if prime is not None:
+                prime(s)
+
+            def exchange(key_dev, stream):
+                torch.cuda.ExternalStream(stream, device="cuda:0").synchronize()
+                local[rank] = int(keys[rank].item())
+                barrier.wait(timeout=120)
+                m = max(local)
+                barrier.wait(timeout=120)
+                seen[rank].append((local[rank], m))
+                keys[rank].fill_(m)
+                torch.cuda.synchronize()
+
+            out[rank] = s.relocalize_sharded(Twc, g0, None, rank, world, keys[rank].data_ptr(), exchange, **kw)
+        except BaseException as e:  # noqa: BLE001
+            err[rank] = e
+            barrier.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    for s in searchers:
+        s.close()
+    for e in err:
+        if e is not None:
+            raise e
+    return out, seen
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_relocalize_sharded_matches_oracle_driver(nmi_lib, oracle, world):
+    """nmi_relocalize_sharded on `world` ranks (every level sharded by nmi_partition, one 8-byte max
+    exchange per level) takes the oracle's single-process decisions and ends on the same pose."""
+    sc = synth.make_scene("tiny")
+    g0 = Grid.make((3, 3, 1), (3, 1, 1), (0.4, 0.4, 0.5), (0.04, 0.02, 0.05))
+    t = oracle.cell_translation(sc.Twc, g0, 2, 0, 0)
+    _, img = oracle.render_points(sc, sc.Twc, t, sc.xyzi)
+    frame = synth.frame_from_render(img, seed=3)
+    outs, seen = _two_rank_reloc(nmi_lib, sc, frame, g0, sc.Twc, world=world, threshold=0.05)
+    rc, want = oracle.relocalize_points(sc, sc.Twc, g0, sc.xyzi, frame, 0.05)
+    assert rc == 0
+    for rank, got in enumerate(outs):
+        assert (got.iterations, got.relocalized, got.failed) == (want.iterations, want.relocalized, want.failed)
+        assert got.n_evals == want.n_evals
+        assert list(got.best_s) == list(want.best_s) and list(got.best_w) == list(want.best_w)
+        assert np.array_equal(np.array(got.Twc[:]), np.array(want.Twc[:]))
+        assert got.nmi == pytest.approx(want.nmi, rel=SCORE_RTOL)
+        assert list(got.final_grid.stepT) == list(want.final_grid.stepT)
+        assert len(seen[rank]) == got.iterations  # one exchange per level, no retries
+    if world > 1:  # the ranks really held different local winners at some level
+        assert any(len({k for k, _ in lv}) > 1 for lv in zip(*seen))
+
+
+def test_relocalize_sharded_retries_a_level_when_a_rank_overflows(nmi_lib, oracle):
+    """A rank whose splat-record bins (sized from ITS previous search) fill up publishes
+    NMI_KEY_RETRY; the max exchange hands it to every rank and all redo the level once."""
+    sc = synth.make_scene("small")
+    g0 = Grid.make((2, 2, 1), (2, 1, 1), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    frame = synth.frame_textured(sc.W, sc.H, seed=9)
+    away = sc.Twc.copy()
+    away[:3, 3] += np.array([500.0, 0.0, 0.0], dtype=np.float32)  # nothing in view -> tiny bins next time
+
+    def prime(s):
+        s.search(away, g0)
+        s.search(away, g0)
+
+    outs, seen = _two_rank_reloc(nmi_lib, sc, frame, g0, sc.Twc, world=2, prime=prime, threshold=0.0,
+                                 max_iterations=1)
+    rc, want = oracle.relocalize_points(sc, sc.Twc, g0, sc.xyzi, frame, 0.0, max_iterations=1)
+    assert rc == 0
+    for rank, got in enumerate(outs):
+        assert [m for _, m in seen[rank]][0] == capi.NMI_KEY_RETRY   # first attempt: retry key everywhere
+        assert len(seen[rank]) == 2 and seen[rank][1][1] != capi.NMI_KEY_RETRY
+        assert list(got.best_s) == list(want.best_s) and list(got.best_w) == list(want.best_w)
+        assert got.nmi == pytest.approx(want.nmi, rel=SCORE_RTOL)
+        assert np.array_equal(np.array(got.Twc[:]), np.array(want.Twc[:]))
