@@ -644,12 +644,12 @@ def test_relocalize_sharded_retries_a_level_when_a_rank_overflows(nmi_lib, oracl
     sc = synth.make_scene("small")
     g0 = Grid.make((2, 2, 1), (2, 1, 1), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
     frame = synth.frame_textured(sc.W, sc.H, seed=9)
-    away = sc.Twc.copy()
-    away[:3, 3] += np.array([500.0, 0.0, 0.0], dtype=np.float32)  # nothing in view -> tiny bins next time
+    low = sc.Twc.copy()
+    low[2, 3] -= 9.0  # 6 m above the ground: ~6x fewer splats per tile -> far too small bins next time
 
     def prime(s):
-        s.search(away, g0)
-        s.search(away, g0)
+        s.search(low, g0)
+        s.search(low, g0)
 
     outs, seen = _two_rank_reloc(nmi_lib, sc, frame, g0, sc.Twc, world=2, prime=prime, threshold=0.0,
                                  max_iterations=1)
