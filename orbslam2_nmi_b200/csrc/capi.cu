@@ -135,6 +135,12 @@ struct nmi_ctx {
   uint32_t bin_cap = 0;  // > 0: this search bins in a single pass into bins of that capacity
   cudaEvent_t ev_feedback = nullptr;
   bool feedback_pending = false;
+  // fullest bins of the last searches: the single-pass bin capacity covers the fullest of them,
+  // so a driver that alternates between coarse and fine levels (or a tracker whose pose jumps
+  // back) does not overflow the bins sized by the one search before
+  static constexpr int kFullestHist = 16;
+  uint32_t fullest_hist[kFullestHist] = {};
+  int fullest_pos = 0;
   bool force_conservative = false;
   bool conservative_once = false;  // an enqueued search overflowed: size the next one exactly
   // binned tile renderer scratch (point clouds)
@@ -249,8 +255,14 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   CK(c->bin_total.reserve(4));
   c->bin_cap = 0;
   // (a) single pass: every bin gets the capacity of the previous search's fullest bin (+25 %)
+  if (!c->feedback_pending)  // new model / camera: the history belongs to the old one
+    for (uint32_t& v : c->fullest_hist) v = 0;
   if (fb && c->h_feedback[3] > 0 && nviews <= kMaxViewsPerLaunch) {
-    size_t cap = (size_t)c->h_feedback[3] + c->h_feedback[3] / 4 + 32;
+    c->fullest_hist[c->fullest_pos] = c->h_feedback[3];
+    c->fullest_pos = (c->fullest_pos + 1) % nmi_ctx::kFullestHist;
+    uint32_t fullest = 0;
+    for (uint32_t v : c->fullest_hist) fullest = v > fullest ? v : fullest;
+    size_t cap = (size_t)fullest + fullest / 4 + 32;
     cap = (cap + 7) / 8 * 8;
     const size_t want = tiles * (size_t)nviews * cap;
     if (want <= (4ull << 30) / sizeof(uint4) && want < 0xFFFFFFFFull) {

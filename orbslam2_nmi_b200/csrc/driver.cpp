@@ -6,7 +6,10 @@
 // (the reference runs nS*nW separate evaluations), re-centred on the previous winner
 // with NmiSearchKernel::resizeKernel's step-halving rule (nmiSearchKernel.cpp:104-141).
 // The accept / reject logic is kept decision for decision.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "nmi_internal.h"
@@ -153,15 +156,31 @@ struct ShardedSearch {
 };
 int sharded_level(void* user, const float Twc[16], const nmi_grid* grid, nmi_result* out) {
   const ShardedSearch* s = static_cast<const ShardedSearch*>(user);
+  static const bool trace = getenv("NMI_TRACE_LEVELS") != nullptr;  // host-side cost of a level, to stderr
+  using clk = std::chrono::steady_clock;
+  auto us = [](clk::time_point a, clk::time_point b) {
+    return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
+  };
   for (int attempt = 0; attempt < 2; ++attempt) {
+    const auto t0 = clk::now();
     if (int rc = nmi_search_enqueue(s->ctx, Twc, grid, s->flags, s->rank, s->world, s->key_dev, nullptr)) return rc;
+    const auto t1 = clk::now();
     if (s->exchange(s->user, s->key_dev, nmi_ctx_stream(s->ctx)) != 0) {
       nmi::set_error("nmi_relocalize_sharded: the exchange callback failed");
       return NMI_ERR_CUDA;
     }
+    const auto t2 = clk::now();
     uint64_t key = 0;
     if (int rc = nmi_read_key(s->ctx, s->key_dev, &key)) return rc;
+    const auto t3 = clk::now();
     const int rc = nmi_decode_key(grid, key, out);
+    float ms[8];
+    if (nmi_get_timings(s->ctx, ms, nullptr) == NMI_OK) out->gpu_ms = ms[6];  // this rank's device time
+    if (trace)
+      fprintf(stderr, "[nmi level] rank %d/%d grid %dx%dx%d x %dx%dx%d: enqueue %ld us, exchange call %ld us, "
+                      "wait %ld us, device %.3f ms (cull %.3f render %.3f hist %.3f)\n",
+              s->rank, s->world, grid->nS[0], grid->nS[1], grid->nS[2], grid->nW[0], grid->nW[1], grid->nW[2],
+              us(t0, t1), us(t1, t2), us(t2, t3), ms[6], ms[0], ms[1], ms[4]);
     // some rank's record bins filled up: all ranks saw NMI_KEY_RETRY and redo the level (the
     // rank concerned sizes its bins exactly this time)
     if (rc != NMI_ERR_RETRY) {
@@ -193,7 +212,13 @@ int nmi_relocalize_sharded(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid*
     return NMI_ERR_INVALID;
   }
   ShardedSearch s{ctx, flags, rank, world, key_dev, exchange, user};
-  return nmi_relocalize_with(sharded_level, &s, Twc_in, start_grid, prm, out);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = nmi_relocalize_with(sharded_level, &s, Twc_in, start_grid, prm, out);
+  if (getenv("NMI_TRACE_LEVELS"))
+    fprintf(stderr, "[nmi driver] rank %d/%d: %d levels, %ld us in nmi_relocalize_sharded\n", rank, world,
+            out->iterations,
+            (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count());
+  return rc;
 }
 
 }  // extern "C"

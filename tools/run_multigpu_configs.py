@@ -81,7 +81,8 @@ def main():
         med = float(np.median(ms))
         emit(config="C4 coarse-to-fine 3-level search, level 0 = 8^3 x 4^3 = 32768 poses, levels sharded over the "
                     "ranks, one 8-byte NCCL max-allreduce per level", n_gpus=world, levels=out.iterations,
-             evals=out.n_evals, search_ms=med, search_ms_all=ms, evals_per_s=out.n_evals / med * 1e3,
+             evals=out.n_evals, search_ms=med, rank0_device_ms=out.gpu_ms,
+             level_grids=[[list(out.levels[i].grid.nS), list(out.levels[i].grid.nW)] for i in range(out.n_levels)], search_ms_all=ms, evals_per_s=out.n_evals / med * 1e3,
              nmi=out.nmi, best_s=list(out.best_s), best_w=list(out.best_w), pose_t=[out.Twc[3], out.Twc[7], out.Twc[11]],
              timing="wall clock around nmi_relocalize_sharded, max over ranks", scaling="strong")
 
