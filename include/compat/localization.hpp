@@ -45,6 +45,13 @@ class NmiObjects {
   // Tracking::RelocalizeWithNMIStrategy (Tracking.cc:1987-2179) on a pose.
   nmi_reloc_result relocalize(cv::Mat Twc, cv::Mat gray, const nmi_reloc_params& params,
                               bool not_initialized = false);
+  // The same on `world` GPUs, one process and one NmiObjects per GPU: every level's
+  // grid is sharded by nmi_partition and `exchange` max-reduces the 8-byte winner key at key_dev
+  // over the ranks on the given stream (ncclAllReduce(key_dev, key_dev, 1, ncclUint64, ncclMax,
+  // comm, stream)).  Every rank returns the same result.
+  nmi_reloc_result relocalizeSharded(cv::Mat Twc, cv::Mat gray, const nmi_reloc_params& params, int rank,
+                                     int world, void* key_dev, nmi_exchange_fn exchange, void* user,
+                                     bool not_initialized = false);
   float threshold() const { return threshold_; }  // NMI.Treshold (Tracking.cc:157)
 
  private:

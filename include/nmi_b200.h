@@ -145,6 +145,9 @@ int nmi_partition(const nmi_grid *grid, int rank, int world, int *axis,
 /* find_max_elements' answer from a (reduced) key.  NMI_ERR_RETRY for
  * NMI_KEY_RETRY, NMI_ERR_NO_WINNER when the low word is 0.                    */
 int nmi_decode_key(const nmi_grid *grid, uint64_t key, nmi_result *out);
+/* 8 bytes of device memory owned by the context, for hosts that have no allocator
+ * of their own at hand (the exchange buffer of nmi_relocalize_sharded).          */
+void *nmi_ctx_key_buffer(nmi_ctx *ctx);
 /* Stream-synchronise, then copy the (reduced) 8-byte key at key_dev to *key.  */
 int nmi_read_key(nmi_ctx *ctx, const void *key_dev, uint64_t *key);
 
@@ -216,7 +219,8 @@ int nmi_relocalize_with(nmi_level_search_fn search, void *user, const float Twc[
  * then decode the same winner, resize the grid identically and go on; no other
  * data moves between GPUs.  A rank whose splat-record bins filled up publishes
  * NMI_KEY_RETRY and every rank redoes that level once with exact sizing.
- * key_dev: 8 bytes of device memory on the context's GPU (the collective's buffer). */
+ * key_dev: 8 bytes of device memory on the context's GPU (the collective's buffer);
+ * NULL = nmi_ctx_key_buffer(ctx).                                                   */
 typedef int (*nmi_exchange_fn)(void *user, void *key_dev, void *stream);
 int nmi_relocalize_sharded(nmi_ctx *ctx, const float Twc[16], const nmi_grid *start_grid,
                            const nmi_flags *flags, const nmi_reloc_params *params,

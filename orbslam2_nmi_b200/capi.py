@@ -125,6 +125,7 @@ SYMBOLS = [
     ("nmi_relocalize_sharded", C.c_int, [_P, _P, C.POINTER(Grid), C.POINTER(Flags), C.POINTER(RelocParams),
                                          C.c_int, C.c_int, _P, EXCHANGE_FN, _P, C.POINTER(RelocResult)]),
     ("nmi_read_key", C.c_int, [_P, _P, C.POINTER(C.c_uint64)]),
+    ("nmi_ctx_key_buffer", _P, [_P]),
     ("nmi_render_at", C.c_int, [_P, _P, _P, C.POINTER(C.c_uint)]),
     ("nmi_render_cell", C.c_int, [_P, _P, C.POINTER(Grid), C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_uint)]),

@@ -178,6 +178,7 @@ struct nmi_ctx {
   bool hot_pending = false;
   uint32_t hot_total = 0;  // pixels sampled per image when h_feedback[5..6] were written
   DevBuf<unsigned long long> key;
+  DevBuf<unsigned long long> xkey;  // nmi_ctx_key_buffer(): exchange buffer of the sharded driver
   DevBuf<unsigned char> params;  // device copy of the per-search parameter block
   unsigned char* h_params = nullptr;
   size_t h_params_cap = 0;
@@ -962,6 +963,11 @@ int nmi_search(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fla
   out->gpu_ms = ms;
   if (rc == NMI_ERR_NO_WINNER) set_error("every score is negative: no winner");
   return rc;
+}
+
+void* nmi_ctx_key_buffer(nmi_ctx* c) {
+  if (!c || cudaSetDevice(c->device) != cudaSuccess || c->xkey.reserve(1) != cudaSuccess) return nullptr;
+  return c->xkey.p;
 }
 
 int nmi_read_key(nmi_ctx* c, const void* key_dev, uint64_t* key) {

@@ -464,6 +464,12 @@ cv::Mat NmiObjects::searchGrid(cv::Mat Twc, cv::Mat gray) {
 
 nmi_reloc_result NmiObjects::relocalize(cv::Mat Twc, cv::Mat gray, const nmi_reloc_params& params,
                                         bool not_initialized) {
+  return relocalizeSharded(Twc, gray, params, 0, 1, nullptr, nullptr, nullptr, not_initialized);
+}
+
+nmi_reloc_result NmiObjects::relocalizeSharded(cv::Mat Twc, cv::Mat gray, const nmi_reloc_params& params,
+                                               int rank, int world, void* key_dev, nmi_exchange_fn exchange,
+                                               void* user, bool not_initialized) {
   myImage->loadOriginal(gray);
   NmiKernel->reset();      // Tracking.cc:1997
   LastNmiKernel->reset();  // Tracking.cc:1998
@@ -473,8 +479,13 @@ nmi_reloc_result NmiObjects::relocalize(cv::Mat Twc, cv::Mat gray, const nmi_rel
   float T[16];
   mat_to_twc(Twc, T);
   nmi_reloc_result out{};
-  nmi_compat::check(nmi_relocalize(nmi_compat::context(), T, &start, &nmi_compat::flags(), &params, &out),
-                    "NmiObjects::relocalize");
+  if (exchange == nullptr)
+    nmi_compat::check(nmi_relocalize(nmi_compat::context(), T, &start, &nmi_compat::flags(), &params, &out),
+                      "NmiObjects::relocalize");
+  else
+    nmi_compat::check(nmi_relocalize_sharded(nmi_compat::context(), T, &start, &nmi_compat::flags(), &params,
+                                             rank, world, key_dev, exchange, user, &out),
+                      "NmiObjects::relocalizeSharded");
   // the lines Tracking.cc:2103-2106 appends to _log.txt after every search
   if (!logPath.empty()) {
     for (int l = 0; l < out.n_levels; l++) {

@@ -207,9 +207,14 @@ int nmi_relocalize(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid* start_g
 int nmi_relocalize_sharded(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid* start_grid,
                            const nmi_flags* flags, const nmi_reloc_params* prm, int rank, int world,
                            void* key_dev, nmi_exchange_fn exchange, void* user, nmi_reloc_result* out) {
-  if (!ctx || !flags || !key_dev || !exchange || world < 1 || rank < 0 || rank >= world) {
+  if (!ctx || !flags || !exchange || world < 1 || rank < 0 || rank >= world) {
     nmi::set_error("nmi_relocalize_sharded: bad argument");
     return NMI_ERR_INVALID;
+  }
+  if (!key_dev) key_dev = nmi_ctx_key_buffer(ctx);  // the context's own 8-byte exchange buffer
+  if (!key_dev) {
+    nmi::set_error("nmi_relocalize_sharded: no key buffer");
+    return NMI_ERR_CUDA;
   }
   ShardedSearch s{ctx, flags, rank, world, key_dev, exchange, user};
   const auto t0 = std::chrono::steady_clock::now();

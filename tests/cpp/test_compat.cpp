@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -236,6 +237,19 @@ static int gpu_checks(const char* yaml, const char* frame_raw, const char* twc_t
   nmi_reloc_result rr = objs.relocalize(Twc, gray, prm);
   std::printf("\nRELOC %d %d %d %.9g %.9g", rr.relocalized, rr.failed, rr.iterations, rr.nmi, rr.last_nmi);
   EXPECT(rr.n_levels == rr.iterations && rr.levels[rr.n_levels - 1].nmi == rr.nmi);
+  {
+    // the sharded driver as rank 0 of 1: the exchange step has nothing to combine, and the
+    // result must be the single-GPU driver's, decision for decision
+    int calls = 0;
+    const nmi_exchange_fn same = [](void* user, void* key_dev, void* stream) -> int {
+      ++*static_cast<int*>(user);
+      return key_dev != nullptr && stream != nullptr ? 0 : 1;
+    };
+    nmi_reloc_result rs = objs.relocalizeSharded(Twc, gray, prm, 0, 1, nullptr, same, &calls);
+    EXPECT(calls == rs.iterations && rs.iterations == rr.iterations);
+    EXPECT(rs.relocalized == rr.relocalized && rs.failed == rr.failed && rs.nmi == rr.nmi);
+    EXPECT(std::memcmp(rs.Twc, rr.Twc, sizeof rs.Twc) == 0);
+  }
   std::printf("\nLOGPATH %s", objs.logPath.c_str());
   for (int i = 0; i < 16; i++) std::printf(" %.9g", rr.Twc[i]);
   std::stringstream ss;
