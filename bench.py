@@ -127,6 +127,26 @@ def cpu_baseline_run(scene, frame, threads: int, sample=((4, 4, 4), (4, 4, 4))):
     return n / dt, dt, f"{n}-pose grid {sample[0]}x{sample[1]} at full 1920x1080 / 10M points ({dt:.1f} s)"
 
 
+def reference_gpu_kernels(render, warped, iters: int = 20):
+    """The reference's OWN CUDA routine -- CUDAF::NMIWithCuda_noMask from oracle/_ref (NMI.cu +
+    kernel.cu compiled unmodified for sm_100a, oracle/Makefile.ref) -- timed per evaluation on
+    this GPU with the pair resident: what the reference pays per pose for a7-a10 alone (render and
+    warp excluded; its GL / NPP stages cannot run here).  Part of the baseline leg; None when the
+    library was not built or no GPU is visible."""
+    try:
+        from oracle import ref_py  # test infrastructure: baseline leg only
+
+        if not ref_py.available():
+            return None
+        ms, score = ref_py.time_per_eval(render, warped, iters)
+        return {"value": 1e3 / ms, "unit": UNIT, "ms_per_eval": ms, "kind": "reference",
+                "sample": f"{iters} calls of CUDAF::NMIWithCuda_noMask on one resident {render.shape[1]}x{render.shape[0]} pair "
+                          "(histogram + entropy + score only; renders and warps supplied)",
+                "score": float(score), "build": ref_py.describe()}
+    except Exception as e:  # a baseline that cannot run must not take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement on the box's host cores (bounded sample)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -145,12 +165,26 @@ def run_reference(args):
         vals.append(v)
         total += dt
     value = float(np.mean(vals))
+    ref_gpu = None
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            from oracle import oracle_py as oracle
+
+            g1 = synth.default_grid((1, 1, 1), (1, 1, 1))
+            _, renders, warps = oracle.search_points(scene, scene.Twc, g1, scene.xyzi, frame, keep_images=True,
+                                                     threads=threads)
+            ref_gpu = reference_gpu_kernels(renders[0], warps[0])
+    except Exception as e:
+        ref_gpu = {"unavailable": f"{type(e).__name__}: {e}"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32+f32",
         "data": "synthetic", "config": {"workload": WORKLOAD, "note": "each step is one whole 4096-pose C2 search on the host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "reference_gpu_kernels": ref_gpu},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -270,6 +304,8 @@ def run_gpu(args):
         oracle.search_points(scene, scene.Twc, synth.default_grid((1, 1, 1), (1, 1, 1)), scene.xyzi, frame,
                              threads=1)
         cpu["single_eval_ms_1core"] = 1e3 * (time.perf_counter() - t1)  # one evaluation, one core
+        # the reference's own CUDA kernels on this GPU, on the pair (render 0, warp 0) of that search
+        cpu["reference_gpu_kernels"] = reference_gpu_kernels(searcher.get_render(0), searcher.get_warp(0))
 
     if rank == 0:
         P = scene.W * scene.H

@@ -69,6 +69,12 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.orc_score_f32.restype = C.c_float
     lib.orc_score_f64.argtypes = [P, P, P, C.c_int, C.c_uint32, C.c_int]
     lib.orc_score_f64.restype = C.c_double
+    lib.orc_score_stages_f32.argtypes = [P, P, P, C.c_int, C.c_uint32, C.c_int, P, P, P, P, P]
+    lib.orc_score_stages_f32.restype = C.c_float
+    lib.orc_tree_f32.argtypes = [P, C.c_int]
+    lib.orc_tree_f32.restype = C.c_float
+    lib.orc_finish_f32.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
+    lib.orc_finish_f32.restype = C.c_float
     lib.orc_eval_one.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.orc_eval_one.restype = C.c_float
     lib.orc_argmax.argtypes = [P, C.c_size_t, P]
@@ -193,6 +199,28 @@ def joint_hist(render, warped, bins=256, bg=True):
 
 def score_f32(J, HA, HB, length, mode=SUC):
     return float(load().orc_score_f32(_p(J), _p(HA), _p(HB), J.shape[0], int(length), mode))
+
+
+def score_stages_f32(J, HA, HB, length, mode=SUC):
+    """-> dict(ea, eb, ej, mid, sums[3], score): the score computation stage by stage."""
+    bins = J.shape[0]
+    ea = np.zeros(bins, np.float32); eb = np.zeros(bins, np.float32)
+    ej = np.zeros((bins, bins), np.float32); mid = np.zeros(bins, np.float32)
+    sums = np.zeros(3, np.float32)
+    J = np.ascontiguousarray(J, np.uint32); HA = np.ascontiguousarray(HA, np.uint32)
+    HB = np.ascontiguousarray(HB, np.uint32)
+    s = load().orc_score_stages_f32(_p(J), _p(HA), _p(HB), bins, int(length), mode,
+                                    _p(ea), _p(eb), _p(ej), _p(mid), _p(sums))
+    return dict(ea=ea, eb=eb, ej=ej, mid=mid, sums=sums, score=float(s))
+
+
+def tree_f32(x):
+    x = np.ascontiguousarray(x, np.float32)
+    return float(load().orc_tree_f32(_p(x), x.size))
+
+
+def finish_f32(sa, sb, sab, mode=SUC):
+    return float(load().orc_finish_f32(float(sa), float(sb), float(sab), mode))
 
 
 def score_f64(J, HA, HB, length, mode=SUC):

@@ -1,0 +1,104 @@
+"""ctypes access to oracle/_ref/libnmi_ref.so -- the reference's OWN CUDA NMI routine
+(Thirdparty/CUDA_Functions/NMI.cu + kernel.cu, compiled unmodified for sm_100a by
+oracle/Makefile.ref in the build container; see oracle/ref_harness.cu and
+oracle/ref_shim/refshim.h for what is supplied around it).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/ and by bench.py's baseline leg, never by the
+product.  Needs a GPU to run (the reference has no CPU path); `/root/reference` is needed
+only to BUILD the library, never at run time."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "_ref" / "libnmi_ref.so"
+REF_SOURCES = Path("/root/reference/Thirdparty/CUDA_Functions")
+
+_lib = None
+
+
+def build(force: bool = False) -> Path | None:
+    """Compile the reference sources where they lie; None when /root/reference is absent."""
+    if not (REF_SOURCES / "NMI.cu").exists():
+        return LIB_PATH if LIB_PATH.exists() else None
+    if force and LIB_PATH.exists():
+        LIB_PATH.unlink()
+    subprocess.run(["make", "-C", str(HERE), "-f", "Makefile.ref"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+def available() -> bool:
+    return LIB_PATH.exists()
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} not built (python -m orbslam2_nmi_b200.build, needs /root/reference)")
+        lib = C.CDLL(str(LIB_PATH))   # RTLD_LOCAL: its CUDAF::NMIWithCuda_noMask never meets ours
+        P = C.c_void_p
+        lib.nmiref_score.argtypes = [P, P, C.c_int, C.c_int, P]
+        lib.nmiref_stages.argtypes = [P, P, C.c_int, C.c_int] + [P] * 9
+        lib.nmiref_time.argtypes = [P, P, C.c_int, C.c_int, C.c_int, P, P]
+        lib.nmiref_describe.restype = C.c_char_p
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _gl_rows(render_topdown):
+    """Our renders are top-down; the GL colour texture the reference samples is bottom-up
+    (it flips the row itself, NMI.cu:82)."""
+    r = np.ascontiguousarray(render_topdown, dtype=np.uint8)
+    return np.ascontiguousarray(r[::-1])
+
+
+def describe() -> str:
+    return load().nmiref_describe().decode()
+
+
+def score(render_topdown, warped) -> float:
+    """CUDAF::NMIWithCuda_noMask (kernel.cu:49-114) on one pair, as Tracking calls it."""
+    r = _gl_rows(render_topdown)
+    w = np.ascontiguousarray(warped, dtype=np.uint8)
+    H, W = r.shape
+    out = np.zeros(1, np.float32)
+    rc = load().nmiref_score(_p(r), _p(w), W, H, _p(out))
+    if rc:
+        raise RuntimeError(f"nmiref_score: CUDA error {rc}")
+    return float(out[0])
+
+
+def stages(render_topdown, warped) -> dict:
+    """kernel.cu:57-100 stage by stage with every intermediate read back."""
+    r = _gl_rows(render_topdown)
+    w = np.ascontiguousarray(warped, dtype=np.uint8)
+    H, W = r.shape
+    J = np.zeros((256, 256), np.uint32); h1 = np.zeros(256, np.uint32); h2 = np.zeros(256, np.uint32)
+    e1 = np.zeros(256, np.float32); e2 = np.zeros(256, np.float32); ej = np.zeros((256, 256), np.float32)
+    mid = np.zeros(256, np.float32); sums = np.zeros(3, np.float32); raw = np.zeros(1, np.float32)
+    rc = load().nmiref_stages(_p(r), _p(w), W, H, _p(J), _p(h1), _p(h2), _p(e1), _p(e2), _p(ej),
+                              _p(mid), _p(sums), _p(raw))
+    if rc:
+        raise RuntimeError(f"nmiref_stages: CUDA error {rc}")
+    return dict(J=J, HA=h1, HB=h2, ea=e1, eb=e2, ej=ej, mid=mid, sums=sums, raw_score=float(raw[0]))
+
+
+def time_per_eval(render_topdown, warped, iters: int = 20):
+    """(ms per NMIWithCuda_noMask call, last score) with the pair resident on the device."""
+    r = _gl_rows(render_topdown)
+    w = np.ascontiguousarray(warped, dtype=np.uint8)
+    H, W = r.shape
+    ms = C.c_double(0.0); s = C.c_float(0.0)
+    rc = load().nmiref_time(_p(r), _p(w), W, H, int(iters), C.byref(ms), C.byref(s))
+    if rc:
+        raise RuntimeError(f"nmiref_time: CUDA error {rc}")
+    return ms.value, s.value

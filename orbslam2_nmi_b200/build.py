@@ -4,6 +4,8 @@
 Outputs (git-ignored, but shipped to the GPU box by gpurun):
   orbslam2_nmi_b200/_lib/libnmi_b200.so     the product (C ABI, include/nmi_b200.h)
   oracle/_build/libnmi_oracle.so            test infrastructure (never loaded by the product)
+  oracle/_ref/libnmi_ref.so                 the reference's own NMI.cu + kernel.cu for sm_100a (checker;
+                                            built only where /root/reference exists)
 """
 from __future__ import annotations
 
@@ -84,6 +86,28 @@ def build_oracle(force: bool = False) -> Path:
     return ORACLE_LIB
 
 
+REF_LIB = ROOT / "oracle" / "_ref" / "libnmi_ref.so"
+REF_CUF = Path("/root/reference/Thirdparty/CUDA_Functions")
+
+
+def build_reference(force: bool = False):
+    """The reference's own NMI.cu + kernel.cu, compiled unmodified from /root/reference for sm_100a
+    (oracle/Makefile.ref) -- a checker for the GPU tests, never loaded by the product.  Only
+    possible where /root/reference exists (the build container); the GPU box uses the prebuilt
+    oracle/_ref/libnmi_ref.so.  Returns the path, or None when it can neither be built nor found."""
+    if not (REF_CUF / "NMI.cu").exists():
+        return REF_LIB if REF_LIB.exists() else None
+    args = ["make", "-C", str(ROOT / "oracle"), "-f", "Makefile.ref", f"NVCC={_nvcc()}"]
+    if force:
+        args.append("-B")
+    res = subprocess.run(args, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("reference (oracle/_ref) build failed")
+    return REF_LIB
+
+
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose=True))
     print(build_oracle(force="--force" in sys.argv))
+    print(build_reference(force="--force" in sys.argv))

@@ -180,6 +180,22 @@ class NmiSearcher:
                                      C.byref(flags), ptr(s)))
         return float(s[0])
 
+    def import_render(self, render_dev: int, pitch_bytes: int, bottom_up: bool = False) -> int:
+        """Adopt a device image as the current render (kernel.cu:53-59's mapped GL texture)."""
+        h = C.c_uint(0)
+        check(self.lib.nmi_import_render(self.h, render_dev, pitch_bytes, self.cam.W, self.cam.H,
+                                         int(bottom_up), C.byref(h)))
+        return h.value
+
+    def eval_pair_dev(self, warped_dev: int, handle: int, J_dev: int, HA_dev: int, HB_dev: int,
+                      flags: Flags | None = None) -> float:
+        """NMIWithCuda_noMask with the integer histograms left on the device (NMI.cuh:63-71 layout)."""
+        flags = flags or self.flags()
+        s = np.zeros(1, dtype=np.float32)
+        check(self.lib.nmi_eval_pair_dev(self.h, warped_dev, handle, self.cam.W, self.cam.H,
+                                         C.byref(flags), J_dev, HA_dev, HB_dev, ptr(s)))
+        return float(s[0])
+
     # -- parity read-backs -------------------------------------------------------
     def get_render(self, s: int) -> np.ndarray:
         out = np.empty((self.cam.H, self.cam.W), dtype=np.uint8)
