@@ -139,7 +139,14 @@ def reference_gpu_kernels(render, warped, iters: int = 20):
         if not ref_py.available():
             return None
         ms, score = ref_py.time_per_eval(render, warped, iters)
+        st = ref_py.stages(render, warped)
+        sa, sb, sab = (float(x) for x in st["sums"])
+        # its three-block last kernel reads the other blocks' totals unsynchronised (NMI.cu:340-362):
+        # `score` is what it returned, `score_from_its_totals` the formula over its own three sums
+        race_free = float(np.float32(2.0) * (np.float32(1.0) - (np.float32(-sab) / (np.float32(-sa) + np.float32(-sb))))) \
+            if (sa or sb or sab) else 0.0
         return {"value": 1e3 / ms, "unit": UNIT, "ms_per_eval": ms, "kind": "reference",
+                "score_from_its_totals": race_free,
                 "sample": f"{iters} calls of CUDAF::NMIWithCuda_noMask on one resident {render.shape[1]}x{render.shape[0]} pair "
                           "(histogram + entropy + score only; renders and warps supplied)",
                 "score": float(score), "build": ref_py.describe()}

@@ -102,3 +102,64 @@ def time_per_eval(render_topdown, warped, iters: int = 20):
     if rc:
         raise RuntimeError(f"nmiref_time: CUDA error {rc}")
     return ms.value, s.value
+
+
+# ---------------------------------------------------------------- host-side reference (CPU) ----
+# oracle/_ref/libnmi_ref_host.so: Thirdparty/Localization/{nmiSearchKernel,helperFunctions}.cpp,
+# compiled unmodified with g++ (oracle/Makefile.ref) + oracle/ref_host_harness.cpp.  Runs anywhere.
+HOST_LIB_PATH = HERE / "_ref" / "libnmi_ref_host.so"
+_hlib = None
+
+
+def host_available() -> bool:
+    return HOST_LIB_PATH.exists()
+
+
+def load_host() -> C.CDLL:
+    global _hlib
+    if _hlib is None:
+        if not HOST_LIB_PATH.exists():
+            raise RuntimeError(f"{HOST_LIB_PATH} not built (needs /root/reference at build time)")
+        lib = C.CDLL(str(HOST_LIB_PATH))
+        P = C.c_void_p
+        lib.nmirefh_find_max.argtypes = [P] * 6
+        lib.nmirefh_resize.argtypes = [P] * 6
+        lib.nmirefh_format.argtypes = [P] * 6 + [C.c_float, C.c_char_p, C.c_int]
+        _hlib = lib
+    return _hlib
+
+
+def _i3(v):
+    return np.ascontiguousarray(v, dtype=np.int32).reshape(3).copy()
+
+
+def _f3(v):
+    return np.ascontiguousarray(v, dtype=np.float32).reshape(3).copy()
+
+
+def find_max(rating_linear, nS, nW):
+    """helperFunctions::find_max_elements on the rating array (linear order wz,wy,wx,sz,sy,sx).
+    -> (count of maximal elements, best_s, best_w, score) with element [0] of its vector."""
+    r = np.ascontiguousarray(rating_linear, dtype=np.float32)
+    s, w = _i3(nS), _i3(nW)
+    assert r.size == int(np.prod(s)) * int(np.prod(w))
+    bs, bw = np.full(3, -1, np.int32), np.full(3, -1, np.int32)
+    sc = np.zeros(1, np.float32)
+    n = load_host().nmirefh_find_max(_p(r), _p(s), _p(w), _p(bs), _p(bw), _p(sc))
+    return n, tuple(int(x) for x in bs), tuple(int(x) for x in bw), float(sc[0])
+
+
+def resize(nS, nW, stepT, stepR, best_s, best_w):
+    """NmiSearchKernel::isMiddle (before) and ::resizeKernel -> (is_middle, nS, nW, stepT, stepR)."""
+    s, w, t, r = _i3(nS), _i3(nW), _f3(stepT), _f3(stepR)
+    bs, bw = _i3(best_s), _i3(best_w)
+    mid = load_host().nmirefh_resize(_p(s), _p(w), _p(t), _p(r), _p(bs), _p(bw))
+    return bool(mid), tuple(int(x) for x in s), tuple(int(x) for x in w), t, r
+
+
+def format_kernel(nS, nW, stepT, stepR, best_s, best_w, nmi) -> str:
+    """operator<<(std::ostream&, const NmiSearchKernel&): the _log.txt line."""
+    s, w, t, r, bs, bw = _i3(nS), _i3(nW), _f3(stepT), _f3(stepR), _i3(best_s), _i3(best_w)
+    buf = C.create_string_buffer(1024)
+    load_host().nmirefh_format(_p(s), _p(w), _p(t), _p(r), _p(bs), _p(bw), C.c_float(nmi), buf, 1024)
+    return buf.value.decode()

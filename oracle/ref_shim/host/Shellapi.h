@@ -1,0 +1,2 @@
+/* stand-in for "Shellapi.h", absent on this machine: see refshim_host.h (test infrastructure only) */
+#include "./refshim_host.h"

@@ -1,0 +1,2 @@
+/* stand-in for "opencv2/opencv.hpp", absent on this machine: see refshim_host.h (test infrastructure only) */
+#include "../refshim_host.h"

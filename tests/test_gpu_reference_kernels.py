@@ -128,6 +128,13 @@ def test_search_pairs_against_reference_kernels(searcher, oracle, ref, config, n
             ref_scores[w * g.n_synth + s] = rs
     # the pose the reference's own scores select is the pose we select
     assert oracle.argmax(ref_scores)[0] == res.best_index
+    # ... and the reference's own find_max_elements (helperFunctions.cpp:50-103, element [0] as
+    # src/Tracking.cc:1952 takes it) over either rating array names the cell our argmax kernel did
+    if ref.host_available():
+        for rating in (ref_scores, res.scores):
+            count, bs, bw, sc = ref.find_max(rating, nS, nW)
+            assert count >= 1 and (bs, bw) == (res.best_s, res.best_w)
+            assert np.float32(sc) == np.float32(res.best_score)
 
 
 def _eval_images(searcher, render, warped):
