@@ -171,6 +171,11 @@ def _pairs():
     yield "constant_320x240", np.full((240, 320), 255, np.uint8), np.full((240, 320), 128, np.uint8)
     f = synth.frame_textured(1920, 1080, seed=5)
     yield "c2_size_1920x1080", synth.frame_from_render(f, seed=11, gamma=0.9, noise=20.0), f
+    # nearly independent full-size images: SUC = 2(1 - x) with x ~ 0.99 amplifies any disagreement of
+    # the entropy sums (the case that moved the score by 5e-5 between two <= 1 ulp log2f's)
+    g2 = np.ascontiguousarray(synth.frame_textured(1920, 1080, seed=77)[::-1, ::-1])
+    yield "c2_size_low_score_a", g2, f
+    yield "c2_size_low_score_b", np.roll(synth.frame_textured(1920, 1080, seed=78), 611, axis=1), f
 
 
 @pytest.mark.parametrize("name", [n for n, _, _ in _pairs()])
