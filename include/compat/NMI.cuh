@@ -43,7 +43,7 @@ namespace nmi_compat_detail {
 __device__ __forceinline__ float entropy_term(uint count, int length) {  // NMI.cu:240-266
   if (count == 0) return 0.0f;
   const float p = __fdiv_rn((float)count, (float)length);
-  return __fmul_rn(p, (float)log2((double)p));  // correctly rounded log2f, like csrc/hist.cu
+  return __fmul_rn(p, log2f(p));  // libdevice log2f, what NMI.cu:248 calls (see csrc/hist.cu)
 }
 // sum of 256 floats in the order of NMI.cu:270-287: strides 128, 64, ..., 1.  128 threads.
 __device__ __forceinline__ float tree256(const float* in, float* scratch) {

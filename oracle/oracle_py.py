@@ -71,6 +71,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.orc_score_f64.restype = C.c_double
     lib.orc_score_stages_f32.argtypes = [P, P, P, C.c_int, C.c_uint32, C.c_int, P, P, P, P, P]
     lib.orc_score_stages_f32.restype = C.c_float
+    lib.orc_log2f.argtypes = [C.c_float]
+    lib.orc_log2f.restype = C.c_float
     lib.orc_tree_f32.argtypes = [P, C.c_int]
     lib.orc_tree_f32.restype = C.c_float
     lib.orc_finish_f32.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int]
@@ -212,6 +214,10 @@ def score_stages_f32(J, HA, HB, length, mode=SUC):
     s = load().orc_score_stages_f32(_p(J), _p(HA), _p(HB), bins, int(length), mode,
                                     _p(ea), _p(eb), _p(ej), _p(mid), _p(sums))
     return dict(ea=ea, eb=eb, ej=ej, mid=mid, sums=sums, score=float(s))
+
+
+def log2f(x):
+    return float(load().orc_log2f(float(x)))
 
 
 def tree_f32(x):

@@ -132,15 +132,18 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 // ---- entropy pieces (NMI.cu:240-266) ---------------------------------------
-// log2f: correctly rounded (double log2, rounded once), the same value the CPU oracle uses --
-// two different <= 1 ulp libm log2f disagree enough to move a low SUC score by several 1e-5
-// (oracle/nmi_oracle.c: log2f_cr).  The double-precision call is paid once per image size:
-// term_table_kernel tabulates e(c) for every possible count 0..L.
-__device__ __forceinline__ float log2f_cr(float p) { return (float)log2((double)p); }
+// log2f is the one libm call on the path.  SUC of two nearly independent images is 2(1 - x) with
+// x ~ 0.99: one fp32 step of x is 1.8e-5 of a 0.007 score, so "within 1e-5 of the reference" means
+// the same bits, and that needs the reference's own logarithm: CUDA's libdevice log2f, the function
+// its ComputeEntropyKernel calls (NMI.cu:248).  Measured against the reference's kernels compiled
+// for this GPU (oracle/_ref, tests/test_gpu_reference_kernels.py): every term and every score
+// bit-identical.  The CPU oracle carries a transcription of the same routine
+// (oracle/nmi_oracle.c: log2f_cuda).  term_table_kernel tabulates e(c) for every possible count
+// 0..L once per image size, so the histogram kernel itself never evaluates a logarithm.
 __device__ __forceinline__ float term(uint32_t c, float L) {
   if (c == 0) return 0.0f;
   const float p = __fdiv_rn((float)c, L);
-  return __fmul_rn(p, log2f_cr(p));
+  return __fmul_rn(p, log2f(p));
 }
 // Same value as term(c, L): small counts (the vast majority of non-empty bins) are looked up in
 // the per-CTA table that was filled with term() itself, so the result is bit-identical.
