@@ -83,6 +83,7 @@ struct __align__(16) Smem {
   float sums[4];
   float term_tab[kTermTab];  // e(c) for small counts, filled per CTA with term() itself
   uint32_t ev_count;
+  uint32_t rowmask[8];       // fast epilogue: rows that hold a repaid crossing (bit = render level)
   uint16_t ev_list[kEvCap];  // bin of every repaid crossing (+4096 each)
 };
 
@@ -281,10 +282,15 @@ __device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], c
 // ---- epilogue over the rows of one pass --------------------------------------
 // U16G: one pass, 256 rows of 128 packed words.  U32X2: 128 rows of 256 words per
 // pass.  B64: 64 rows of 64 words after folding the copies.
-template <int POLICY, bool SWZ, int NWARPS>
+// ZERO (packed-u16 only): every word is cleared right after it has been read, so a persistent
+// CTA finds an empty histogram for its next evaluation without a separate clearing pass.
+// COLS = false / rowmask != nullptr (packed-u16 only): the fast epilogue below has taken the column
+// sums and the rows without repaid crossings; only the rows named in rowmask are left for this one.
+template <int POLICY, bool SWZ, int NWARPS, bool ZERO = false, bool COLS = true>
 __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const HistArgs& a,
                                               bool dump, int warp, int lane,
-                                              const SmemSkip* sk = nullptr, uint32_t skipT = 0xFFFFFFFFu) {
+                                              const SmemSkip* sk = nullptr, uint32_t skipT = 0xFFFFFFFFu,
+                                              const uint32_t* rowmask = nullptr) {
   constexpr int kConsumers = NWARPS * 32;
   if (POLICY == P_U16G) {
     // skip mode (skipT = a* << 8 | b*): sk->n1[0] / n2[0] / nboth hold the folded side counts
@@ -297,11 +303,14 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
 #pragma unroll
     for (int i = 0; i < 8; i++) col[i] = 0;
     for (int row = warp; row < 256; row += NWARPS) {
+      if (rowmask != nullptr && ((rowmask[row >> 5] >> (row & 31)) & 1u) == 0u) continue;
       uint32_t c[8];  // c[2k+h] = J[row][2(lane+32k)+h]
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         // word of bins (row, 2(lane+32k)) / (row, 2(lane+32k)+1), bank swizzle undone
-        const uint32_t wv = sm.hist[u16g_word<SWZ>(((uint32_t)row << 8) | (2u * (lane + 32 * k)))];
+        const uint32_t wi = u16g_word<SWZ>(((uint32_t)row << 8) | (2u * (lane + 32 * k)));
+        const uint32_t wv = sm.hist[wi];
+        if (ZERO) sm.hist[wi] = 0u;
         c[2 * k] = wv & 0xFFFFu;
         c[2 * k + 1] = wv >> 16;
       }
@@ -333,8 +342,10 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         rs += c[2 * k] + c[2 * k + 1];
-        col[2 * k] += c[2 * k];
-        col[2 * k + 1] += c[2 * k + 1];
+        if (COLS) {
+          col[2 * k] += c[2 * k];
+          col[2 * k + 1] += c[2 * k + 1];
+        }
         vl[k] = term_t(sm.term_tab, a.term_tab, c[2 * k], L);
         vh[k] = term_t(sm.term_tab, a.term_tab, c[2 * k + 1], L);
         if (dump) {
@@ -352,10 +363,12 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
         sm.HA[row] = rs;
       }
     }
+    if (COLS) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      atomicAdd(&sm.HB[2 * (lane + 32 * k)], col[2 * k]);
-      atomicAdd(&sm.HB[2 * (lane + 32 * k) + 1], col[2 * k + 1]);
+      for (int k = 0; k < 4; k++) {
+        atomicAdd(&sm.HB[2 * (lane + 32 * k)], col[2 * k]);
+        atomicAdd(&sm.HB[2 * (lane + 32 * k) + 1], col[2 * k + 1]);
+      }
     }
   } else if (POLICY == P_U32X2) {
     uint32_t col[8];
@@ -416,6 +429,117 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
   }
 }
 
+// ---- fast epilogue: packed-u16, swizzled layout, 16 consumer warps --------------------------
+// The warp-per-row epilogue above costs ~12 us per evaluation (ncu on 4096 evaluations of two-chunk
+// images: ~175 instructions per row, 80 % of all instructions executed) -- 8 % of the kernel at
+// C2 -- because every row pays 15 dependent shuffles for the trees and the row sum, and all 32
+// lanes repeat the address and bookkeeping work.  Here a row belongs to TWO THREADS and the reference's
+// tree (NMI.cu:270-287: strides 128, 64, ..., 1 over b) is walked depth-first in registers:
+// with b = 2m + h, the last stride (1) joins the h = 0 and h = 1 halves of the packed words, the
+// one before (2) joins even and odd word index m -- thread A of the row takes the even words,
+// thread B the odd ones -- and strides 4..128 are bits 1..6 of m, the recursion below, deepest
+// first.  fp32 addition is commutative, the pairing is the reference's: same bits.
+// Bank conflicts: lanes 0-15 are the A threads of 16 consecutive rows, lanes 16-31 the B threads of
+// the same rows.  The swizzle puts word m of row a in bank (m ^ a) & 31, so the A lanes read an
+// aligned block of 16 distinct banks; B walks its subtree with bit 4 of m flipped (children swapped
+// at one level -- same sums) and lands in the other block.  One wavefront per load.
+// Rows that hold a repaid crossing (+4096 per event, rare) are left to the warp-per-row code, which
+// knows how to add them; the marginal over the camera image comes from a column pass in which 32
+// lanes read 32 consecutive words of one row (again one wavefront), plus 4096 per event.
+// Entropy term from the tables only (the fast epilogue runs only when the per-image-size table
+// exists): the first kTermTab entries sit in shared memory, the rest in global memory.  Keeps a
+// leaf at a dozen instructions.  (Measured and dropped: a 4096-entry shared-memory table -- all
+// a field can hold once every crossing is repaid -- and immediate-offset addressing of bits 5-6;
+// both shorten the epilogue on small images and make the C2 kernel 1-4 % slower.)
+__device__ __forceinline__ float term_lut(const float* tab, const float* __restrict__ gtab, uint32_t c) {
+  return c < (uint32_t)kTermTab ? tab[c] : __ldg(gtab + c);
+}
+// subtree over the words wx ^ {bits BIT..6}: splits on bit BIT first, bit 6 deepest
+template <int BIT, uint32_t M>
+__device__ __forceinline__ void row_subtree(const uint32_t* hist, uint32_t wx, const float* tab,
+                                            const float* __restrict__ gtab, uint32_t& rs, float& lo, float& hi) {
+  if constexpr (BIT == 7) {
+    const uint32_t wv = hist[wx ^ M];
+    const uint32_t cl = wv & 0xFFFFu, ch = wv >> 16;
+    rs += cl + ch;
+    lo = term_lut(tab, gtab, cl);
+    hi = term_lut(tab, gtab, ch);
+  } else {
+    float l0, h0, l1, h1;
+    row_subtree<BIT + 1, M>(hist, wx, tab, gtab, rs, l0, h0);
+    row_subtree<BIT + 1, (M | (1u << BIT))>(hist, wx, tab, gtab, rs, l1, h1);
+    lo = __fadd_rn(l0, l1);
+    hi = __fadd_rn(h0, h1);
+  }
+}
+
+// Call with all 512 consumer threads after the barrier that ends the pixel loop; sm.rowmask must be
+// zero on entry and is left set (the caller clears it if the CTA goes on to another pair).
+// Leaves sm.rowE, sm.HA, sm.HB complete once the callers' next barrier has passed.
+template <bool ZERO>
+__device__ __forceinline__ void rows_epilogue_fast(Smem& sm, float L, const HistArgs& a, int warp, int lane) {
+  constexpr int NWARPS = 16, kConsumers = NWARPS * 32;
+  const int tid = warp * 32 + lane;
+  const uint32_t nev = min(sm.ev_count, (uint32_t)kEvCap);
+  if (nev != 0u) {  // CTA-uniform
+    for (uint32_t e = tid; e < nev; e += kConsumers) {
+      const uint32_t t = sm.ev_list[e];
+      atomicOr(&sm.rowmask[t >> 13], 1u << ((t >> 8) & 31u));
+      atomicAdd(&sm.HB[t & 0xFFu], 4096u);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+  }
+  // rows: thread pair (lane, lane + 16) owns row 16 * warp + (lane & 15)
+  {
+    const uint32_t row = (uint32_t)warp * 16u + ((uint32_t)lane & 15u);
+    const uint32_t pb = (uint32_t)lane >> 4;
+    const uint32_t rowx = ((row << 7) ^ row) ^ (pb ? 17u : 0u);  // u16g_word<true>(row << 8); B: odd words, bit 4 swapped
+    uint32_t rs = 0;
+    // bits 1..3 of m: eight subtrees visited depth-first (bit 1 is the split nearest the root, so
+    // the visiting order counts q = bits 3..1 bit-reversed) and folded like a binary counter --
+    // a rolled loop, so the code stays a few hundred instructions; bits 4..6: unrolled recursion
+    float s0l = 0.f, s0h = 0.f, s1l = 0.f, s1h = 0.f, s2l = 0.f, s2h = 0.f, lo = 0.f, hi = 0.f;
+#pragma unroll 1
+    for (uint32_t j = 0; j < 8u; j++) {
+      const uint32_t q = ((j & 1u) << 2) | (j & 2u) | (j >> 2);
+      row_subtree<4, 0u>(sm.hist, rowx ^ (q << 1), sm.term_tab, a.term_tab, rs, lo, hi);
+      if (j & 1u) {
+        lo = __fadd_rn(s0l, lo); hi = __fadd_rn(s0h, hi);
+        if (j & 2u) {
+          lo = __fadd_rn(s1l, lo); hi = __fadd_rn(s1h, hi);
+          if (j & 4u) { lo = __fadd_rn(s2l, lo); hi = __fadd_rn(s2h, hi); }
+          else { s2l = lo; s2h = hi; }
+        } else { s1l = lo; s1h = hi; }
+      } else { s0l = lo; s0h = hi; }
+    }
+    const float lo2 = __shfl_down_sync(0xffffffffu, lo, 16);
+    const float hi2 = __shfl_down_sync(0xffffffffu, hi, 16);
+    const uint32_t rs2 = __shfl_down_sync(0xffffffffu, rs, 16);
+    if (pb == 0u && ((sm.rowmask[row >> 5] >> (row & 31u)) & 1u) == 0u) {
+      sm.rowE[row] = __fadd_rn(__fadd_rn(lo, lo2), __fadd_rn(hi, hi2));  // strides 2, 2, then 1
+      sm.HA[row] = rs + rs2;
+    }
+  }
+  if (nev != 0u)  // the few rows with repaid crossings, warp per row
+    rows_epilogue<P_U16G, true, NWARPS, false, false>(sm, 0, L, a, false, warp, lane, nullptr, 0xFFFFFFFFu, sm.rowmask);
+  if (ZERO) asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // every row has been read
+  // columns: thread = (word index, quarter of the rows)
+  {
+    const uint32_t cw = (uint32_t)tid & 127u, r0 = ((uint32_t)tid >> 7) * 64u;
+    uint32_t slo = 0, shi = 0;
+#pragma unroll 16
+    for (uint32_t r = r0; r < r0 + 64u; r++) {
+      const uint32_t idx = ((r << 7) ^ r) ^ cw;
+      const uint32_t wv = sm.hist[idx];
+      if (ZERO) sm.hist[idx] = 0u;
+      slo += wv & 0xFFFFu;
+      shi += wv >> 16;
+    }
+    atomicAdd(&sm.HB[2u * cw], slo);
+    atomicAdd(&sm.HB[2u * cw + 1u], shi);
+  }
+}
+
 template <int NW>
 __device__ __forceinline__ void load_words(uint32_t (&dst)[NW], const uint8_t* p) {
   if (NW % 4 == 0) {
@@ -446,10 +570,11 @@ __device__ __forceinline__ void ldg_words(uint32_t (&dst)[NW], const uint8_t* p)
 // NWARPS consumer warps.  With 16 of them a 17th warp is the dedicated TMA producer; with 32
 // (the 1024-thread CTA limit) thread 0 doubles as producer: after releasing chunk k it waits
 // until every warp has released it and refills that stage with chunk k + kStages.
-template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP>
+template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP, bool FASTEP = false>
 __global__ void __launch_bounds__(NWARPS == 32 ? 1024 : NWARPS * 32 + 32, 1)
 joint_hist_score_kernel(const HistArgs a) {
   static_assert(!SKIPCAP || POLICY == P_U16G, "hot-bin skipping is built for the packed-u16 policy");
+  static_assert(!FASTEP || (POLICY == P_U16G && SWZ && NWARPS == 16 && !SKIPCAP), "fast epilogue: packed-u16, swizzled, 16 warps");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   SmemSkip& sk = *reinterpret_cast<SmemSkip*>(smem_raw + sizeof(Smem));  // SKIPCAP builds only
@@ -477,6 +602,7 @@ joint_hist_score_kernel(const HistArgs a) {
     uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
     for (int i = tid; i < kHistWords / 4; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
     if (tid < 256) sm.HB[tid] = 0;
+    if (tid < 8) sm.rowmask[tid] = 0;
     if (SKIPCAP) {
       for (int i = tid; i < 2 * kSkipCopies * 256; i += kThreads) (&sk.n1[0][0])[i] = 0;
       if (tid == 0) sk.nboth = 0;
@@ -627,7 +753,10 @@ joint_hist_score_kernel(const HistArgs a) {
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
-      rows_epilogue<POLICY, SWZ, NWARPS>(sm, 0, L, a, dump, warp, lane, SKIPCAP ? &sk : nullptr, skipT);
+      if (FASTEP && !dump && a.term_tab != nullptr)
+        rows_epilogue_fast<false>(sm, L, a, warp, lane);
+      else
+        rows_epilogue<POLICY, SWZ, NWARPS>(sm, 0, L, a, dump, warp, lane, SKIPCAP ? &sk : nullptr, skipT);
     }
   }
   __syncthreads();
@@ -652,6 +781,189 @@ joint_hist_score_kernel(const HistArgs a) {
   if (tid == 0)
     a.scores[a.out_index ? a.out_index[blockIdx.x] : blockIdx.x] =
         finish_score(sm.sums[1], sm.sums[2], sm.sums[0], a.mode);
+}
+
+// ---- persistent build of the default configuration -------------------------------------
+// Packed-u16 histogram, TMA ring, 16 consumer warps + producer warp, one CTA per SM that walks
+// the pair schedule with stride gridDim.x.  The fixed cost per evaluation, measured as 4096
+// evaluations of two-chunk images (tools/exp_hist_overhead.py): one CTA per pair with the
+// warp-per-row epilogue 0.40 ms (14 us per evaluation -- 80 % of the instructions of such a launch
+// are the epilogue's), with the fast epilogue 0.26 ms, persistent with the fast epilogue 0.22 ms.
+// At C2 (254 chunks per image) that is 4.73 -> 4.55 ms per 4096 evaluations.  Here the CTA is set
+// up once; the producer warp runs ahead into the NEXT pair's first kStages chunks while the
+// consumers are still in the epilogue of the current one (the ring is idle then), the epilogue
+// clears each histogram word as it reads it, and the only per-pair state left to reset is 1 KiB
+// of marginals, the row mask and the event counter.
+// The ring's stage / phase arithmetic runs on a chunk counter that never restarts (kk), so the
+// mbarriers need no re-initialisation between pairs.  The schedule is static (pair i on CTA
+// i mod gridDim.x): the builds with the side tables, whose pairs differ a lot in cost, stay on
+// one CTA per pair and the hardware's dynamic block scheduler.
+template <bool SWZ, bool SKIPCAP>
+__global__ void __launch_bounds__(16 * 32 + 32, 1)
+joint_hist_score_persistent_kernel(const HistArgs a) {
+  constexpr int NWARPS = 16;
+  constexpr int kConsumers = NWARPS * 32;
+  constexpr int kThreads = kConsumers + 32;
+  constexpr int PIX = kChunk / kConsumers;  // 16 pixels per thread and chunk
+  constexpr int NW = PIX / 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  SmemSkip& sk = *reinterpret_cast<SmemSkip*>(smem_raw + sizeof(Smem));  // SKIPCAP builds only
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t npix = a.npix;
+  const int nchunks = (int)((npix + kChunk - 1) / kChunk);
+  const float L = (float)a.length;
+
+  // ---- once per CTA ----
+  {
+    uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+    for (int i = tid; i < kHistWords / 4; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 256) sm.HB[tid] = 0;
+    if (tid < 8) sm.rowmask[tid] = 0;
+    if (SKIPCAP) {
+      for (int i = tid; i < 2 * kSkipCopies * 256; i += kThreads) (&sk.n1[0][0])[i] = 0;
+      if (tid == 0) sk.nboth = 0;
+    }
+    if (a.term_tab != nullptr)
+      for (int i = tid; i < kTermTab && (uint32_t)i <= a.length; i += kThreads) sm.term_tab[i] = __ldg(a.term_tab + i);
+    else
+      for (int i = tid; i < kTermTab; i += kThreads) sm.term_tab[i] = term((uint32_t)i, L);
+    if (tid == 0) {
+      sm.ev_count = 0;
+      for (int s = 0; s < kStages; s++) {
+        mbar_init(&sm.full[s], 1);
+        mbar_init(&sm.empty[s], NWARPS);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  __syncthreads();
+
+  if (warp == NWARPS) {
+    // ===== producer warp: one TMA ring across all of this CTA's pairs =====
+    if (lane == 0) {
+      int kk = 0;
+      for (int pi = blockIdx.x; pi < a.npairs; pi += gridDim.x) {
+        const int2 pr = a.pairs[pi];
+        const uint8_t* rimg = a.renders + (size_t)pr.x * a.render_pitch;
+        const uint8_t* wimg = a.warps + (size_t)pr.y * a.warp_pitch;
+        for (int k = 0; k < nchunks; k++, kk++) {
+          const int st = kk % kStages;
+          if (kk >= kStages) mbar_wait(&sm.empty[st], ((kk / kStages) - 1) & 1);
+          const uint32_t off = (uint32_t)k * kChunk;
+          uint32_t bytes = npix - off;
+          bytes = bytes > (uint32_t)kChunk ? (uint32_t)kChunk : ((bytes + 15u) & ~15u);
+          mbar_expect_tx(&sm.full[st], 2 * bytes);
+          tma_load_1d(sm.rbuf[st], rimg + off, bytes, &sm.full[st]);
+          tma_load_1d(sm.wbuf[st], wimg + off, bytes, &sm.full[st]);
+        }
+      }
+    }
+    return;  // the consumers synchronise among themselves with named barrier 1 from here on
+  }
+
+  // ===== consumers =====
+  int kk = 0;
+  for (int pi = blockIdx.x; pi < a.npairs; pi += gridDim.x) {
+    const int2 pr = a.pairs[pi];
+    const bool dump = a.dumpJ != nullptr && pi == 0;
+    // hot-bin skipping: the sampled modes of this pair's two images decide (CTA-uniform)
+    uint32_t skipT = 0xFFFFFFFFu;
+    if (SKIPCAP && a.img_mode != nullptr && a.bg && a.skip_mode != 0) {
+      const uint32_t ka = __ldg(a.img_mode + pr.x), kb = __ldg(a.img_mode + a.nrenders + pr.y);
+      if (a.skip_mode == 2 || ((unsigned long long)(ka >> 8) + (kb >> 8)) * 6ull >= a.sample_total)
+        skipT = ((ka & 0xFFu) << 8) | (kb & 0xFFu);
+    }
+    const bool skip = SKIPCAP && skipT != 0xFFFFFFFFu;
+    const uint32_t a4 = ((skipT >> 8) & 0xFFu) * 0x01010101u, b4 = (skipT & 0xFFu) * 0x01010101u;
+    uint32_t nboth = 0;
+
+    for (int k = 0; k < nchunks; k++, kk++) {
+      const int st = kk % kStages;
+      const uint32_t off = (uint32_t)k * kChunk + (uint32_t)tid * PIX;
+      uint32_t r[NW], w[NW];
+      mbar_wait(&sm.full[st], (kk / kStages) & 1);
+      load_words<NW>(r, sm.rbuf[st] + tid * PIX);
+      load_words<NW>(w, sm.wbuf[st] + tid * PIX);
+      const int nvalid = off >= npix ? 0 : (int)min((uint32_t)PIX, npix - off);
+      if (nvalid == PIX && a.bg) {
+        if (!skip) {
+          accum_fast<P_U16G, SWZ, NW>(sm, r, w, 0, warp);
+        } else {
+          uint32_t dr = 0, dw = 0;
+#pragma unroll
+          for (int j = 0; j < NW; j++) {
+            dr |= r[j] ^ a4;
+            dw |= w[j] ^ b4;
+          }
+          if (dr != 0u && dw != 0u) {
+            accum_fast<P_U16G, SWZ, NW>(sm, r, w, 0, warp);
+          } else if (dr == 0u && dw == 0u) {
+            nboth += PIX;
+          } else {
+            const uint32_t (&x)[NW] = dr == 0u ? w : r;
+            const uint32_t base = smem_u32(dr == 0u ? sk.n1[warp & (kSkipCopies - 1)] : sk.n2[warp & (kSkipCopies - 1)]);
+#pragma unroll
+            for (int i = 0; i < PIX; i++) {
+              const uint32_t v = __byte_perm(x[i >> 2], 0u, 0x4440 + (i & 3));
+              asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + v * 4u) : "memory");
+            }
+          }
+        }
+      } else if (nvalid > 0) {
+        accum_slow<P_U16G, SWZ, NW>(sm, r, w, nvalid, a.bg, 0, warp);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[st]);
+    }
+
+    if (skip) {  // fold the side tables into copy 0
+      if (nboth) atomicAdd(&sk.nboth, nboth);
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+      for (int i = tid; i < 512; i += kConsumers) {
+        uint32_t* t0 = i < 256 ? &sk.n1[0][i] : &sk.n2[0][i - 256];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int c = 0; c < kSkipCopies; c++) sum += t0[c * 256];
+        *t0 = sum;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B1: every increment of this pair has landed
+    if (SWZ && !SKIPCAP && !dump && a.term_tab != nullptr)
+      rows_epilogue_fast<true>(sm, L, a, warp, lane);
+    else
+      rows_epilogue<P_U16G, SWZ, NWARPS, true>(sm, 0, L, a, dump, warp, lane, SKIPCAP ? &sk : nullptr, skipT);
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B2: rows read and cleared, marginals complete
+    if (warp < 3) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int i = lane + 32 * k;
+        v[k] = warp == 0 ? sm.rowE[i] : term_t(sm.term_tab, a.term_tab, warp == 1 ? sm.HA[i] : sm.HB[i], L);
+      }
+      const float s = tree_lanes<8>(v);
+      if (lane == 0) sm.sums[warp] = s;
+    } else {
+      // what the next pair's pixel loop must find empty (the marginals are still being read)
+      if (tid == 3 * 32) sm.ev_count = 0;
+      if (tid >= 4 * 32 && tid < 4 * 32 + 8) sm.rowmask[tid - 4 * 32] = 0;
+      if (SKIPCAP) {
+        for (int i = tid - 3 * 32; i < 2 * kSkipCopies * 256; i += kConsumers - 3 * 32) (&sk.n1[0][0])[i] = 0;
+        if (tid == 3 * 32) sk.nboth = 0;
+      }
+    }
+    if (dump && tid < 256) {
+      a.dumpHA[tid] = sm.HA[tid];
+      a.dumpHB[tid] = sm.HB[tid];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B3: totals done, marginals free again
+    if (tid == 0)
+      a.scores[a.out_index ? a.out_index[pi] : pi] = finish_score(sm.sums[1], sm.sums[2], sm.sums[0], a.mode);
+    if (tid < 256) sm.HB[tid] = 0;  // the next epilogue's column sums start from zero (ordered by its B1)
+  }
 }
 
 // e(c) for every count 0..length (counts cannot exceed the pixel count)
@@ -728,9 +1040,9 @@ image_mode_kernel(const uint8_t* __restrict__ renders, size_t rpitch, int nr,
   }
 }
 
-template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP = false>
+template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP = false, bool FASTEP = false>
 int launch_t(const HistArgs& a, cudaStream_t st) {
-  auto kern = joint_hist_score_kernel<POLICY, USE_TMA, NWARPS, SWZ, SKIPCAP>;
+  auto kern = joint_hist_score_kernel<POLICY, USE_TMA, NWARPS, SWZ, SKIPCAP, FASTEP>;
   constexpr size_t smem = sizeof(Smem) + (SKIPCAP ? sizeof(SmemSkip) : 0);
   static bool configured = false;
   if (!configured) {
@@ -739,6 +1051,25 @@ int launch_t(const HistArgs& a, cudaStream_t st) {
     configured = true;
   }
   kern<<<a.npairs, NWARPS == 32 ? 1024 : NWARPS * 32 + 32, smem, st>>>(a);
+  return 1;
+}
+
+template <bool SWZ, bool SKIPCAP>
+int launch_persistent(const HistArgs& a, cudaStream_t st) {
+  auto kern = joint_hist_score_persistent_kernel<SWZ, SKIPCAP>;
+  constexpr size_t smem = sizeof(Smem) + (SKIPCAP ? sizeof(SmemSkip) : 0);
+  static int sms[64] = {0};  // per device: one CTA per SM (the histogram takes most of an SM's shared memory)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return -1;
+    sms[dev] = n;
+  }
+  const int nsm = sms[dev];
+  kern<<<a.npairs < nsm ? a.npairs : nsm, 16 * 32 + 32, smem, st>>>(a);
   return 1;
 }
 
@@ -762,7 +1093,7 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
   if (a.npairs <= 0) return 0;
   if (a.bins == 256 && a.skipcap && a.bg && a.img_mode != nullptr) {
     switch (a.variant) {  // the packed-u16 builds that carry the side tables
-      case 0: return launch_t<P_U16G, true, 16, true, true>(a, st);
+      case 0: case 8: case 9: return launch_t<P_U16G, true, 16, true, true>(a, st);
       case 4: return launch_t<P_U16G, true, 32, false, true>(a, st);
       case 5: return launch_t<P_U16G, true, 16, false, true>(a, st);
       default: break;
@@ -779,7 +1110,12 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
     case 5: return launch_t<P_U16G, true, 16, false>(a, st);
     case 6: return launch_t<P_U16G, true, 32, true>(a, st);
     case 7: return launch_t<P_U32X2, true, 32, false>(a, st);
-    default: return launch_t<P_U16G, true, 16, true>(a, st);  // variant 0: TMA ring, bank swizzle
+    case 8: return launch_t<P_U16G, true, 16, true>(a, st);  // variant 0's configuration: one CTA per pair, warp-per-row epilogue
+    case 9:  // one CTA per pair, fast epilogue
+      return a.term_tab != nullptr ? launch_t<P_U16G, true, 16, true, false, true>(a, st)
+                                   : launch_t<P_U16G, true, 16, true>(a, st);
+    default:  // variant 0: TMA ring, bank swizzle, persistent CTAs with the fast epilogue
+      return launch_persistent<true, false>(a, st);
   }
 }
 
