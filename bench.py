@@ -341,7 +341,7 @@ def run_gpu(args):
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(P + 256 * 1024), "d2h_bytes_per_step": 8},
             "gpu_launches": int(sum(launches)) * 2,  # device-timed loop + e2e loop
-            "roofline": {"bound": "hbm", "kernel": "joint_hist_score_kernel",
+            "roofline": {"bound": "hbm", "kernel": "joint_hist_score_persistent_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": hist_bytes,
