@@ -349,7 +349,7 @@ def run_gpu(args):
                          "smem_atomics_per_s": per_rank_pairs * P / (hist_ms * 1e-3),
                          "search_algorithmic_GBps": search_bytes / (mean_stage["total"] * 1e-3) / 1e9,
                          "note": "HBM is the contract's denominator; the kernel's measured limiter is the "
-                                 "shared-memory data pipe (ncu l1tex__data_pipe_lsu_wavefronts 88 % of peak, "
+                                 "shared-memory data pipe (ncu l1tex__data_pipe_lsu_wavefronts 91 % of peak, "
                                  "3.75 wavefronts per warp-level ATOMS = random bank collisions; DRAM traffic is "
                                  "8 % of the algorithmic bytes): profiles/r01_hist_ncu_summary.txt"},
             "stage_ms": mean_stage,
