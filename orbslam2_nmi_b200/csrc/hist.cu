@@ -1,4 +1,6 @@
-// hist.cu -- fused joint histogram + entropy + NMI score, one CTA per evaluation.
+// hist.cu -- fused joint histogram + entropy + NMI score; one CTA holds one evaluation at a time
+// (default build: one persistent CTA per SM walking the pair schedule, see
+// joint_hist_score_persistent_kernel; the other builds launch one CTA per evaluation).
 //
 // Replaces, per (render, warped frame) pair, the reference's six launches
 //   histogram256Kernel + mergeHistogram256Kernel + mergeJointHistogram256Kernel
@@ -18,6 +20,8 @@
 // through a 4-stage shared-memory ring filled by the TMA engine
 // (cp.async.bulk + mbarrier complete_tx), issued by a dedicated producer warp,
 // so the 16 or 32 consumer warps spend their issue slots on shared-memory atomics.
+// The epilogue of the default build walks the reference's summation trees depth-first in
+// registers, two threads per histogram row (rows_epilogue_fast).
 // The hot loop is branch-free: each thread fires all its atomics of a chunk back to
 // back (independent ATOMS in flight) and only afterwards inspects the returned values.
 //
