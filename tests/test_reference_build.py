@@ -48,8 +48,9 @@ def test_reference_kernels_are_in_the_fatbin(ref_lib):
 
 def test_nothing_from_the_reference_is_in_the_repo():
     """The recipe compiles the sources where they lie; only build outputs land in oracle/_ref/ (git-ignored)."""
-    tracked = subprocess.run(["git", "ls-files"], cwd=ROOT, capture_output=True, text=True).stdout.split()
-    assert not [f for f in tracked if f.startswith("oracle/_ref/")]
+    res = subprocess.run(["git", "ls-files"], cwd=ROOT, capture_output=True, text=True)
+    if res.returncode == 0:   # a snapshot without .git (the GPU box) has nothing to list
+        assert not [f for f in res.stdout.split() if f.startswith("oracle/_ref/")]
     mk = (ROOT / "oracle" / "Makefile.ref").read_text()
     assert "$(CUF)/NMI.cu" in mk and "$(CUF)/kernel.cu" in mk
     assert "oracle/_ref/" in (ROOT / ".gitignore").read_text()
