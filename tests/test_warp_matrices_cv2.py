@@ -1,0 +1,76 @@
+"""Row a5 against OpenCV's own arithmetic: the warp matrices of Image::Image (image.cpp:76-108)
+rebuilt with cv2's gemm / invert (the functions `cv::Mat operator*` and `.inv()` call) and inverted
+the way cv::cuda::warpPerspective does before it hands float coefficients to its kernel.  The
+oracle's and the product's inverse homographies have to agree with that to the last float bit or
+the one next to it (OpenCV's gemm and 3x3 inverse may order their double additions differently)."""
+import numpy as np
+import pytest
+
+from orbslam2_nmi_b200 import synth
+from orbslam2_nmi_b200.capi import Grid
+
+cv2 = pytest.importorskip("cv2")
+
+
+def image_ctor_matrices(sc, g):
+    """image.cpp:76-108, statement by statement, on cv2 doubles."""
+    K = np.array([[sc.fx, 0, sc.cx], [0, sc.fy, sc.cy], [0, 0, 1]], np.float64)
+    Kinv = cv2.invert(K)[1]
+    nx, ny, nz = g.nW[0], g.nW[1], g.nW[2]
+    sx, sy, sz = (np.float32(g.stepR[k]) for k in range(3))   # float members (image.hpp)
+    out = {}
+    thz = np.float64(np.float32(-((nz - 1) // 2 if nz >= 1 else 0)) * sz)   # -(n-1)/2*step: int division, float product
+    for i in range(nz):
+        Rz = np.array([[np.cos(thz), -np.sin(thz), 0], [np.sin(thz), np.cos(thz), 0], [0, 0, 1]], np.float64)
+        thy = np.float64(np.float32(-((ny - 1) // 2)) * sy)
+        for j in range(ny):
+            Ry = np.array([[np.cos(thy), 0, np.sin(thy)], [0, 1, 0], [-np.sin(thy), 0, np.cos(thy)]], np.float64)
+            thx = np.float64(np.float32(-((nx - 1) // 2)) * sx)
+            for k in range(nx):
+                Rx = np.array([[1, 0, 0], [0, np.cos(thx), -np.sin(thx)], [0, np.sin(thx), np.cos(thx)]], np.float64)
+                R = cv2.gemm(cv2.gemm(Rz, Ry, 1, None, 0), Rx, 1, None, 0)
+                M = cv2.gemm(cv2.gemm(K, R, 1, None, 0), Kinv, 1, None, 0)
+                out[(k, j, i)] = M
+                thx = thx + np.float64(sx)
+            thy = thy + np.float64(sy)
+        thz = thz + np.float64(sz)
+    return out
+
+
+def ulps(a, b):
+    ia = np.asarray(a, np.float32).view(np.int32).astype(np.int64)
+    ib = np.asarray(b, np.float32).view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)
+    ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return np.abs(ia - ib)
+
+
+@pytest.mark.parametrize("config,nW,stepR", [
+    ("C2", (3, 3, 3), (0.02, 0.02, 0.05)),     # ETH_small.yaml:83-88
+    ("C2", (4, 4, 4), (0.02, 0.02, 0.05)),     # the benchmark grid (even counts: start = -trunc((n-1)/2)*step)
+    ("C1", (5, 1, 2), (0.003, 0.01, 0.0011)),
+    ("C3", (4, 4, 1), (0.01, 0.02, 0.05)),
+])
+def test_inverse_homographies_match_opencv_arithmetic(oracle, nmi_lib, config, nW, stepR):
+    from orbslam2_nmi_b200 import search
+
+    sc = synth.make_scene(config, n_points=10)
+    g = Grid.make((1, 1, 1), nW, (0.2, 0.2, 0.5), stepR)
+    cam = search.Camera(W=sc.W, H=sc.H, fx=sc.fx, fy=sc.fy, cx=sc.cx, cy=sc.cy, zn=sc.zn, zf=sc.zf,
+                        point_size=sc.point_size) if hasattr(search, "Camera") else None
+    worst = 0
+    exact = total = 0
+    for (k, j, i), M in image_ctor_matrices(sc, g).items():
+        want = cv2.invert(M)[1].astype(np.float32).reshape(9)   # what warpPerspective's kernel receives
+        got_o = np.asarray(oracle.cell_homography_inv(sc, g, k, j, i), np.float32).reshape(9)
+        d = ulps(got_o, want)
+        # entries that are ~0 relative to the matrix scale carry no information in their last bits
+        big = np.abs(want) > 1e-6 * np.abs(want).max()
+        worst = max(worst, int(d[big].max()))
+        exact += int((d[big] == 0).sum()); total += int(big.sum())
+        assert np.allclose(got_o, want, rtol=3e-7, atol=1e-9 * np.abs(want).max())
+        if cam is not None:
+            got_p = np.asarray(search.cell_homography_inv(cam, g, k, j, i), np.float32).reshape(9)
+            assert np.array_equal(got_p, got_o), "product host code differs from the oracle"
+    assert worst <= 2, f"largest entry-wise distance {worst} ulp"
+    assert exact >= 0.9 * total
