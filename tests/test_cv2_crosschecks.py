@@ -1,8 +1,15 @@
-"""Row a5 against OpenCV's own arithmetic: the warp matrices of Image::Image (image.cpp:76-108)
+"""Rows a5 and a14 against OpenCV's own arithmetic (Python cv2 runs the same cv::gemm / cv::invert the
+reference's cv::Mat expressions call).
+
+a5: the warp matrices of Image::Image (image.cpp:76-108)
 rebuilt with cv2's gemm / invert (the functions `cv::Mat operator*` and `.inv()` call) and inverted
 the way cv::cuda::warpPerspective does before it hands float coefficients to its kernel.  The
 oracle's and the product's inverse homographies have to agree with that to the last float bit or
-the one next to it (OpenCV's gemm and 3x3 inverse may order their double additions differently)."""
+the one next to it (OpenCV's gemm and 3x3 inverse may order their double additions differently).
+
+a14: Tracking::CalculateNMIRelocalization (src/Tracking.cc:2374-2419) -- float rotation matrices from
+`(best - n/2) * step` (integer n/2), R = Rz*Ry*Rx and newLoc = Twc * [R|0] as CV_32F gemms, then the
+translation of the winning synthetic cell added to the last column."""
 import numpy as np
 import pytest
 
@@ -74,3 +81,40 @@ def test_inverse_homographies_match_opencv_arithmetic(oracle, nmi_lib, config, n
             assert np.array_equal(got_p, got_o), "product host code differs from the oracle"
     assert worst <= 2, f"largest entry-wise distance {worst} ulp"
     assert exact >= 0.9 * total
+
+
+def calculate_nmi_relocalization(oracle, Twc, g, s, w):
+    """src/Tracking.cc:2374-2419 on cv2 float matrices (cos / sin of a float are the float overloads)."""
+    rot = [np.float32(np.float32(w[k] - g.nW[k] // 2) * np.float32(g.stepR[k])) for k in range(3)]
+    c = [np.cos(r, dtype=np.float32) for r in rot]
+    sn = [np.sin(r, dtype=np.float32) for r in rot]
+    Rx = np.array([[1, 0, 0], [0, c[0], -sn[0]], [0, sn[0], c[0]]], np.float32)
+    Ry = np.array([[c[1], 0, sn[1]], [0, 1, 0], [-sn[1], 0, c[1]]], np.float32)
+    Rz = np.array([[c[2], -sn[2], 0], [sn[2], c[2], 0], [0, 0, 1]], np.float32)
+    R = cv2.gemm(cv2.gemm(Rz, Ry, 1, None, 0), Rx, 1, None, 0)
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = R
+    new = cv2.gemm(np.asarray(Twc, np.float32).reshape(4, 4), T, 1, None, 0)
+    t = oracle.cell_translation(Twc, g, *s)      # Rendering::calculateTranslationCV (GLM, restated in the oracle)
+    for k in range(3):
+        new[k, 3] += t[k]
+    return new
+
+
+def test_winner_pose_matches_opencv_arithmetic(oracle, nmi_lib):
+    from orbslam2_nmi_b200 import search
+
+    sc = synth.make_scene("tiny", n_points=10)
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        nS = tuple(int(x) for x in rng.integers(1, 6, 3))
+        nW = tuple(int(x) for x in rng.integers(1, 6, 3))
+        g = Grid.make(nS, nW, tuple(float(x) for x in rng.random(3) * 0.5), tuple(float(x) for x in rng.random(3) * 0.05))
+        s = tuple(int(rng.integers(0, n)) for n in nS)
+        w = tuple(int(rng.integers(0, n)) for n in nW)
+        want = calculate_nmi_relocalization(oracle, sc.Twc, g, s, w)
+        got_o = np.asarray(oracle.apply_winner(sc.Twc, g, s, w), np.float32).reshape(4, 4)
+        got_p = np.asarray(search.apply_winner(sc.Twc, g, s, w), np.float32).reshape(4, 4)
+        assert np.array_equal(got_p, got_o), "product host code differs from the oracle"
+        assert ulps(got_o, want).max() <= 1          # cosf implementations may differ in the last place
+    # with this libm they agree exactly
