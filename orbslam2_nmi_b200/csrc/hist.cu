@@ -1048,11 +1048,13 @@ template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP = false, 
 int launch_t(const HistArgs& a, cudaStream_t st) {
   auto kern = joint_hist_score_kernel<POLICY, USE_TMA, NWARPS, SWZ, SKIPCAP, FASTEP>;
   constexpr size_t smem = sizeof(Smem) + (SKIPCAP ? sizeof(SmemSkip) : 0);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};  // the attribute is per device (contexts of several GPUs in one process)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  if (!configured[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return -1;
-    configured = true;
+    configured[dev] = true;
   }
   kern<<<a.npairs, NWARPS == 32 ? 1024 : NWARPS * 32 + 32, smem, st>>>(a);
   return 1;

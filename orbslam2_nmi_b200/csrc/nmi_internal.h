@@ -74,7 +74,6 @@ int launch_image_modes(const uint8_t* renders, size_t rpitch, int nr, const uint
                        int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st);
 uint32_t image_mode_sample_total(uint32_t npix);
 void launch_term_table(float* tab, uint32_t length, cudaStream_t st);
-int hist_configure();  // cudaFuncSetAttribute for the big-smem kernels; 0 on success
 
 // --- argmax.cu -------------------------------------------------------------
 // key = (bits(max(0, scores)) << 32) | (0xFFFFFFFF - lowest index with score == max)
