@@ -381,7 +381,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--variant", type=int, default=0, help="histogram kernel variant (0..9)")
+    ap.add_argument("--variant", type=int, default=0, help="histogram kernel variant (0..10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--frame", default="textured", choices=["textured", "uniform", "constant", "sky", "smooth"])
     ap.add_argument("--extent", type=float, default=None,

@@ -970,6 +970,191 @@ joint_hist_score_persistent_kernel(const HistArgs a) {
   }
 }
 
+// ---- persistent build with the pixel ring staged through TENSOR MEMORY (variant 10) ---------
+// 13 % of the LSU's shared-memory wavefronts in the kernel above only read the staged pixels
+// (LDS.128).  Tensor memory has its own datapath: tcgen05.cp copies shared memory -> TMEM without
+// the LSU and tcgen05.ld brings TMEM -> registers.  Here the TMA ring is unchanged, a second
+// single-thread warp (the "issuer") forwards every landed stage with four tcgen05.cp.128x256b
+// (4 KiB each: two per image) into a ring of 4 x 32 TMEM columns and commits to an mbarrier; the
+// consumers read their 16 + 16 pixels with two tcgen05.ld.32x32b.x4 and never touch the staged
+// bytes with the LSU.  Shared-memory descriptor: no swizzle, LBO 2048 B, SBO 128 B, for which lane t
+// receives bytes [16 t, 16 t + 16) of the 4 KiB block in columns 0-3 and [2048 + 16 t, ...) in columns
+// 4-7 (measured with tools/ubench_tmem.cu); a warp reads the lane quarter (warp % 4) and the column
+// group (warp / 4), so every thread again owns 16 consecutive pixels of the chunk, the same ones
+// in both images.  A stage of shared memory is free again as soon as its copies have committed.
+// RESULT: bit-identical scores at every size, and 4.66 ms instead of 4.53 ms at C2.  The copy
+// engine reads the same bytes out of the same shared-memory array the LDS would have: what bounds
+// the kernel is that array's port, not the LSU in front of it -- LSU wavefronts (1172 M per launch)
+// plus the TMA ring's writes (17 GB / 128 B = 133 M) already equal the SM's active cycles (1283 M).
+// Kept as a tested variant, not the default.
+constexpr int kTmemColsPerStage = 32;  // 16 render + 16 warp columns x 128 lanes x 4 B = 2 x 8192 B
+static_assert(kChunk == 8192, "the TMEM staging is laid out for 8192-pixel chunks");
+struct __align__(16) SmemTm {  // follows Smem
+  unsigned long long tfull[kStages];   // copies of the stage into TMEM have completed (tcgen05.commit)
+  unsigned long long tempty[kStages];  // all 16 consumer warps have read the TMEM stage
+  uint32_t tbase;                      // TMEM base address from tcgen05.alloc
+};
+__device__ __forceinline__ uint64_t tm_desc(uint32_t saddr) {  // no swizzle, LBO 2048 B, SBO 128 B, version 1
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+
+__global__ void __launch_bounds__(16 * 32 + 64, 1)
+joint_hist_score_tmem_kernel(const HistArgs a) {
+  constexpr int NWARPS = 16;
+  constexpr int kConsumers = NWARPS * 32;
+  constexpr int kThreads = kConsumers + 64;
+  constexpr int PIX = 16, NW = 4;
+  constexpr bool SWZ = true;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  SmemTm& tm = *reinterpret_cast<SmemTm*>(smem_raw + sizeof(Smem));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const uint32_t npix = a.npix;
+  const int nchunks = (int)((npix + kChunk - 1) / kChunk);
+  const float L = (float)a.length;
+
+  // ---- once per CTA ----
+  {
+    uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+    for (int i = tid; i < kHistWords / 4; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 256) sm.HB[tid] = 0;
+    if (tid < 8) sm.rowmask[tid] = 0;
+    if (a.term_tab != nullptr)
+      for (int i = tid; i < kTermTab && (uint32_t)i <= a.length; i += kThreads) sm.term_tab[i] = __ldg(a.term_tab + i);
+    else
+      for (int i = tid; i < kTermTab; i += kThreads) sm.term_tab[i] = term((uint32_t)i, L);
+    if (tid == 0) {
+      sm.ev_count = 0;
+      for (int s = 0; s < kStages; s++) {
+        mbar_init(&sm.full[s], 1);
+        mbar_init(&tm.tfull[s], 1);
+        mbar_init(&tm.tempty[s], NWARPS);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == NWARPS + 1) {  // the issuer warp owns the TMEM allocation
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tm.tbase)),
+                   "n"(kTmemColsPerStage * kStages)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = tm.tbase;
+
+  if (warp == NWARPS) {
+    // ===== TMA producer: a shared-memory stage is free once its copies into TMEM have committed =====
+    if (lane == 0) {
+      int kk = 0;
+      for (int pi = blockIdx.x; pi < a.npairs; pi += gridDim.x) {
+        const int2 pr = a.pairs[pi];
+        const uint8_t* rimg = a.renders + (size_t)pr.x * a.render_pitch;
+        const uint8_t* wimg = a.warps + (size_t)pr.y * a.warp_pitch;
+        for (int k = 0; k < nchunks; k++, kk++) {
+          const int st = kk % kStages;
+          if (kk >= kStages) mbar_wait(&tm.tfull[st], ((kk / kStages) - 1) & 1);
+          const uint32_t off = (uint32_t)k * kChunk;
+          uint32_t bytes = npix - off;
+          bytes = bytes > (uint32_t)kChunk ? (uint32_t)kChunk : ((bytes + 15u) & ~15u);
+          mbar_expect_tx(&sm.full[st], 2 * bytes);
+          tma_load_1d(sm.rbuf[st], rimg + off, bytes, &sm.full[st]);
+          tma_load_1d(sm.wbuf[st], wimg + off, bytes, &sm.full[st]);
+        }
+      }
+    }
+    return;
+  }
+  if (warp == NWARPS + 1) {
+    // ===== issuer: shared memory -> TMEM, four 4 KiB copies per stage =====
+    int total = 0;
+    for (int pi = blockIdx.x; pi < a.npairs; pi += gridDim.x) total += nchunks;
+    if (lane == 0) {
+      for (int kk = 0; kk < total; kk++) {
+        const int st = kk % kStages;
+        mbar_wait(&sm.full[st], (kk / kStages) & 1);                                   // the TMA bytes have landed
+        if (kk >= kStages) mbar_wait(&tm.tempty[st], ((kk / kStages) - 1) & 1);        // the TMEM stage has been read
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t col = tbase + (uint32_t)(st * kTmemColsPerStage);
+        const uint32_t rs = smem_u32(sm.rbuf[st]), ws = smem_u32(sm.wbuf[st]);
+        asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(col + 0u), "l"(tm_desc(rs)) : "memory");
+        asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(col + 8u), "l"(tm_desc(rs + 4096u)) : "memory");
+        asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(col + 16u), "l"(tm_desc(ws)) : "memory");
+        asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(col + 24u), "l"(tm_desc(ws + 4096u)) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tm.tfull[st]))
+                     : "memory");
+      }
+    }
+    __syncwarp();
+    asm volatile("bar.sync 2, %0;" ::"n"(kConsumers + 32));  // every consumer has finished its last read
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "n"(kTmemColsPerStage * kStages) : "memory");
+    return;
+  }
+
+  // ===== consumers =====
+  // this thread's 16 pixels of a chunk: TMEM lane 32 (warp % 4) + lane, column group warp / 4
+  const uint32_t tlane = 32u * ((uint32_t)warp & 3u) + (uint32_t)lane, cgrp = (uint32_t)warp >> 2;
+  const uint32_t pix0 = 4096u * (cgrp >> 1) + 2048u * (cgrp & 1u) + 16u * tlane;  // its offset inside the chunk
+  const uint32_t taddr0 = tbase + ((32u * ((uint32_t)warp & 3u)) << 16) + 8u * (cgrp >> 1) + 4u * (cgrp & 1u);
+  int kk = 0;
+  for (int pi = blockIdx.x; pi < a.npairs; pi += gridDim.x) {
+    const bool dump = a.dumpJ != nullptr && pi == 0;
+    for (int k = 0; k < nchunks; k++, kk++) {
+      const int st = kk % kStages;
+      const uint32_t off = (uint32_t)k * kChunk + pix0;
+      uint32_t r[NW], w[NW];
+      mbar_wait(&tm.tfull[st], (kk / kStages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ta = taddr0 + (uint32_t)(st * kTmemColsPerStage);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(ta));
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ta + 16u));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lane == 0) mbar_arrive(&tm.tempty[st]);  // the registers hold the pixels: the TMEM stage may be refilled
+      const int nvalid = off >= npix ? 0 : (int)min((uint32_t)PIX, npix - off);
+      if (nvalid == PIX && a.bg)
+        accum_fast<P_U16G, SWZ, NW>(sm, r, w, 0, warp);
+      else if (nvalid > 0)
+        accum_slow<P_U16G, SWZ, NW>(sm, r, w, nvalid, a.bg, 0, warp);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B1: every increment of this pair has landed
+    if (!dump && a.term_tab != nullptr)
+      rows_epilogue_fast<true>(sm, L, a, warp, lane);
+    else
+      rows_epilogue<P_U16G, SWZ, NWARPS, true>(sm, 0, L, a, dump, warp, lane);
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B2
+    if (warp < 3) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int i = lane + 32 * q;
+        v[q] = warp == 0 ? sm.rowE[i] : term_t(sm.term_tab, a.term_tab, warp == 1 ? sm.HA[i] : sm.HB[i], L);
+      }
+      const float s = tree_lanes<8>(v);
+      if (lane == 0) sm.sums[warp] = s;
+    } else {
+      if (tid == 3 * 32) sm.ev_count = 0;
+      if (tid >= 4 * 32 && tid < 4 * 32 + 8) sm.rowmask[tid - 4 * 32] = 0;
+    }
+    if (dump && tid < 256) {
+      a.dumpHA[tid] = sm.HA[tid];
+      a.dumpHB[tid] = sm.HB[tid];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B3
+    if (tid == 0)
+      a.scores[a.out_index ? a.out_index[pi] : pi] = finish_score(sm.sums[1], sm.sums[2], sm.sums[0], a.mode);
+    if (tid < 256) sm.HB[tid] = 0;
+  }
+  asm volatile("bar.arrive 2, %0;" ::"n"(kConsumers + 32));  // lets the issuer warp free the TMEM columns
+}
+
 // e(c) for every count 0..length (counts cannot exceed the pixel count)
 __global__ void term_table_kernel(float* __restrict__ tab, uint32_t length) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1079,6 +1264,24 @@ int launch_persistent(const HistArgs& a, cudaStream_t st) {
   return 1;
 }
 
+int launch_tmem(const HistArgs& a, cudaStream_t st) {
+  auto kern = joint_hist_score_tmem_kernel;
+  constexpr size_t smem = sizeof(Smem) + sizeof(SmemTm);
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return -1;
+    sms[dev] = n;
+  }
+  const int nsm = sms[dev];
+  kern<<<a.npairs < nsm ? a.npairs : nsm, 16 * 32 + 64, smem, st>>>(a);
+  return 1;
+}
+
 }  // namespace
 
 void launch_term_table(float* tab, uint32_t length, cudaStream_t st) {
@@ -1120,6 +1323,7 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
     case 9:  // one CTA per pair, fast epilogue
       return a.term_tab != nullptr ? launch_t<P_U16G, true, 16, true, false, true>(a, st)
                                    : launch_t<P_U16G, true, 16, true>(a, st);
+    case 10: return launch_tmem(a, st);  // variant 0 with the pixel ring staged through tensor memory
     default:  // variant 0: TMA ring, bank swizzle, persistent CTAs with the fast epilogue
       return launch_persistent<true, false>(a, st);
   }
