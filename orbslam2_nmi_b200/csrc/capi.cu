@@ -19,7 +19,7 @@
 namespace nmi {
 
 // project.cu (not in the header: only capi uses them)
-void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const ViewConst& vc,
+void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const float* aabb, const ViewConst& vc,
                          const float c0[3], const float margin[3], float4* out_pts,
                          uint32_t* out_idx, uint32_t* counter, uint32_t* block_counts,
                          cudaStream_t st);
@@ -116,6 +116,8 @@ struct nmi_ctx {
   DevBuf<uint32_t> tag;   // tie-break word of the z-buffer key: orig, or orig << 8 | value
   bool packed_value = false;  // model has < 2^24 primitives: the key carries the value
   DevBuf<uint8_t> val;    // u8 intensity, indexed by ORIGINAL index
+  DevBuf<float> aabb;     // {lo xyz, hi xyz} of every kCullBlock consecutive (Morton-ordered) points
+  bool use_block_cull = true;  // $NMI_BLOCK_CULL=0: per-point cull only (A/B switch)
   size_t n_pts = 0;
   DevBuf<float4> cpts;    // compacted survivors of the cull
   DevBuf<uint32_t> cidx;  // their original indices
@@ -374,7 +376,8 @@ int cull_model(nmi_ctx* c, const ViewConst& vc, const float Twc[16], const float
     launch_mesh_cull(c->mverts.p, c->mtris.p, (uint32_t)c->n_tris, vc, c0, margin, c->mslots.p,
                      c->counter.p, c->block_counts.p, c->stream);
   } else {
-    launch_cull_compact(c->pts.p, c->tag.p, (uint32_t)c->n_pts, vc, c0, margin, c->cpts.p, c->cidx.p,
+    launch_cull_compact(c->pts.p, c->tag.p, (uint32_t)c->n_pts, c->use_block_cull ? c->aabb.p : nullptr, vc, c0, margin,
+                        c->cpts.p, c->cidx.p,
                         c->counter.p, c->block_counts.p, c->stream);
   }
   c->launches += 3;
@@ -675,6 +678,7 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   CK(cudaMemset(c->zero_pair.p, 0, sizeof(int2)));
   c->timed = true;
   if (const char* e = getenv("NMI_WARP_TEX")) c->use_warp_tex = atoi(e) != 0;
+  if (const char* e = getenv("NMI_BLOCK_CULL")) c->use_block_cull = atoi(e) != 0;
   if (const char* e = getenv("NMI_HIST_SKIP")) {
     const int m = atoi(e);
     if (m >= 0 && m <= 2) c->hist_skip = m;
@@ -687,7 +691,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->pts.release(); c->orig.release(); c->tag.release(); c->val.release(); c->mverts.release(); c->mtris.release();
+  c->pts.release(); c->aabb.release(); c->orig.release(); c->tag.release(); c->val.release(); c->mverts.release(); c->mtris.release();
   c->mtri_orig.release(); c->mslots.release(); c->bin_offsets.release(); c->bin_cursor.release();
   c->bin_total.release(); c->records.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
@@ -805,6 +809,25 @@ int nmi_set_points(nmi_ctx* c, const float* xyzi, size_t n) {
     orig[i] = src;
     memcpy(&sorted[4 * i], &xyzi[4 * (size_t)src], 4 * sizeof(float));
   }
+  // axis-aligned box of every kCullBlock consecutive points (the cull kernels skip whole blocks)
+  const size_t nblk = (n + kCullBlock - 1) / kCullBlock;
+  std::vector<float> boxes(6 * nblk);
+#pragma omp parallel for schedule(static)
+  for (long long b = 0; b < (long long)nblk; b++) {
+    float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const size_t e = std::min(n, (size_t)(b + 1) * kCullBlock);
+    for (size_t i = (size_t)b * kCullBlock; i < e; i++)
+      for (int k = 0; k < 3; k++) {
+        blo[k] = fminf(blo[k], sorted[4 * i + k]);  // fminf / fmaxf ignore NaN
+        bhi[k] = fmaxf(bhi[k], sorted[4 * i + k]);
+      }
+    for (int k = 0; k < 3; k++) {
+      boxes[6 * b + k] = blo[k];
+      boxes[6 * b + 3 + k] = bhi[k];
+    }
+  }
+  CK(c->aabb.reserve(6 * nblk));
+  CK(cudaMemcpyAsync(c->aabb.p, boxes.data(), 6 * nblk * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   CK(c->pts.reserve(n));
   CK(c->orig.reserve(n));
   CK(c->val.reserve(n));

@@ -19,6 +19,7 @@ struct ViewConst {
 };
 
 constexpr int kMaxViewsPerLaunch = 512;
+constexpr int kCullBlock = 1024;  // points per CTA of the cull kernels = points per load-time AABB
 constexpr size_t kImgAlign = 128;  // every render / warp image starts 128 B aligned
 
 inline size_t img_pitch(size_t P) { return (P + kImgAlign - 1) / kImgAlign * kImgAlign; }

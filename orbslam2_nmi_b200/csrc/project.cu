@@ -86,13 +86,57 @@ __device__ __forceinline__ bool cull_keep(const float4& p, const ViewConst& vc, 
 // patch:  count per CTA -> exclusive scan of the CTA counts -> scatter.
 constexpr int kCullThreads = 256;
 constexpr int kCullPer = 4;                              // points per thread
-constexpr int kCullBlock = kCullThreads * kCullPer;      // 1024 points per CTA
+static_assert(kCullThreads * kCullPer == kCullBlock, "one CTA per AABB block");
+
+// Block cull.  The cloud is Morton-ordered, so the kCullBlock consecutive points of a CTA form a
+// compact patch whose axis-aligned box was computed at load time (nmi_set_points).  A box that lies
+// entirely beyond one of the (already conservatively enlarged) planes of the frustum union is
+// skipped without reading a single point: at C2 ~85 % of the cloud.  The test uses the eight
+// corners: every plane function is linear, the slack `sl` is convex, so the extreme over the
+// box is attained at a corner; `eps` covers the fp32 rounding of the two evaluations, and both
+// are far inside the 5 cm + 1 % slack that already separates cull_keep from the exact per-view
+// clip test, so no visible point can be lost.  Boxes holding NaN / inf never reject.
+__device__ __forceinline__ bool block_may_survive(const float* __restrict__ aabb, uint32_t b, const ViewConst& vc,
+                                                  const CullConst& cc) {
+  if (aabb == nullptr || !(vc.kx > 0.0f) || !(vc.ky > 0.0f)) return true;
+  const float lo[3] = {__ldg(aabb + 6 * (size_t)b), __ldg(aabb + 6 * (size_t)b + 1), __ldg(aabb + 6 * (size_t)b + 2)};
+  const float hi[3] = {__ldg(aabb + 6 * (size_t)b + 3), __ldg(aabb + 6 * (size_t)b + 4), __ldg(aabb + 6 * (size_t)b + 5)};
+  float zmin = INFINITY, zmax = -INFINITY, l1 = 0.0f;
+  float fxp = INFINITY, fxn = INFINITY, fyp = INFINITY, fyn = INFINITY;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float dx = ((k & 1) ? hi[0] : lo[0]) - cc.c0[0];
+    const float dy = ((k & 2) ? hi[1] : lo[1]) - cc.c0[1];
+    const float dz = ((k & 4) ? hi[2] : lo[2]) - cc.c0[2];
+    const float X = vc.r0[0] * dx + vc.r0[1] * dy + vc.r0[2] * dz;
+    const float Y = vc.r1[0] * dx + vc.r1[1] * dy + vc.r1[2] * dz;
+    const float Z = vc.r2[0] * dx + vc.r2[1] * dy + vc.r2[2] * dz;
+    zmin = fminf(zmin, Z);
+    zmax = fmaxf(zmax, Z);
+    l1 = fmaxf(l1, fabsf(X) + fabsf(Y) + fabsf(Z));
+    fxp = fminf(fxp, vc.kx * X - Z);
+    fxn = fminf(fxn, -vc.kx * X - Z);
+    fyp = fminf(fyp, vc.ky * Y - Z);
+    fyn = fminf(fyn, -vc.ky * Y - Z);
+  }
+  const float sl = 0.05f + 0.01f * l1;
+  const float eps = 1e-3f * (1.0f + l1);
+  const float bx = vc.kx * (cc.mx + sl) + cc.mz + sl + eps * (1.0f + vc.kx);
+  const float by = vc.ky * (cc.my + sl) + cc.mz + sl + eps * (1.0f + vc.ky);
+  const bool out = (zmax < vc.zn - cc.mz - sl - eps) || (zmin > vc.zf + cc.mz + sl + eps) || (fxp > bx) ||
+                   (fxn > bx) || (fyp > by) || (fyn > by);
+  return !out;  // NaN anywhere: every comparison is false -> kept
+}
 
 __global__ void __launch_bounds__(kCullThreads)
 cull_count_kernel(const float4* __restrict__ pts, uint32_t n, ViewConst vc, CullConst cc,
-                  uint32_t* __restrict__ block_counts) {
+                  const float* __restrict__ aabb, uint32_t* __restrict__ block_counts) {
   __shared__ uint32_t s_cnt[kCullThreads / 32];
   const uint32_t base = blockIdx.x * kCullBlock;
+  if (!block_may_survive(aabb, blockIdx.x, vc, cc)) {  // CTA-uniform
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = 0;
+    return;
+  }
   uint32_t mine = 0;
 #pragma unroll
   for (int k = 0; k < kCullPer; k++) {
@@ -151,10 +195,12 @@ cull_scan_kernel(uint32_t* __restrict__ block_counts, uint32_t nblocks, uint32_t
 
 __global__ void __launch_bounds__(kCullThreads)
 cull_scatter_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ tag, uint32_t n,
-                    ViewConst vc, CullConst cc, const uint32_t* __restrict__ block_offsets,
+                    ViewConst vc, CullConst cc, const float* __restrict__ aabb,
+                    const uint32_t* __restrict__ block_offsets,
                     float4* __restrict__ out_pts, uint32_t* __restrict__ out_idx) {
   __shared__ uint32_t s_warp[kCullPer][kCullThreads / 32];
   const uint32_t base = blockIdx.x * kCullBlock;
+  if (!block_may_survive(aabb, blockIdx.x, vc, cc)) return;  // same decision as the count pass
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 p[kCullPer];
   unsigned m[kCullPer];
@@ -402,15 +448,24 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
   }
 }
 
-template <bool PACKED>
+// A splat covers the S x S pixels whose top-left corner is its ANCHOR (i0, j0), so
+//   zbuf(x, y) = min over anchors in [x-S+1, x] x [y-S+1, y] of  min key of the splats anchored there
+// (min is associative): ONE shared-memory atomic per record and pass into an anchor buffer of
+// (32+S-1)^2 cells, then an S x S min filter over the finished cells -- instead of S*S atomics per
+// record and pass (9 for the reference's glPointSize(3): 18 atomics per record, 3 wavefronts each,
+// was 97 % of the L1 pipe).  Keys are compared as (depth bits, tag), the packed 64-bit order.
+template <bool PACKED, int ST>  // ST = 3: the reference's point size, filter in registers; 0: any S <= 32
 __global__ void __launch_bounds__(kTileThreads)
 tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bin_cap,
                     const uint32_t* __restrict__ offsets, uint32_t* __restrict__ total, int ntx, int nt,
                     int W, int H, int S,
                     const uint8_t* __restrict__ val, uint8_t* __restrict__ images, size_t pitch,
                     uint32_t* __restrict__ winners, size_t P) {
-  __shared__ uint32_t s_depth[kTileCells];
-  __shared__ uint32_t s_tag[kTileCells];
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  if (ST) S = ST;
+  const int E = kTile + S - 1;      // anchors li, lj in [-(S-1), 31] -> u, v in [0, E)
+  uint32_t* s_depth = s_dyn;        // [E * E]
+  uint32_t* s_tag = s_dyn + E * E;  // [E * E]
   const uint32_t bin = blockIdx.x;
   const int v = bin / nt, tile = bin - v * nt;
   const int ty = tile / ntx, tx = tile - ty * ntx;
@@ -428,68 +483,88 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bi
     end = min(bin + 1 < gridDim.x ? offsets[bin + 1] : *total, rec_cap);
   }
   if (tid == 0) atomicMax(total + 2, (uint32_t)(end - start));  // feedback: fullest bin
-  for (int q = tid; q < kTileCells; q += kTileThreads) { s_depth[q] = 0xFFFFFFFFu; s_tag[q] = 0xFFFFFFFFu; }
+  for (int q = tid; q < 2 * E * E; q += kTileThreads) s_dyn[q] = 0xFFFFFFFFu;
   __syncthreads();
-  if (S == 3) {
-    // the reference's glPointSize(3): fully unrolled 3x3, one range test per row / column
-    for (size_t r = start + tid; r < end; r += kTileThreads) {  // pass 1: minimum depth per cell
-      const uint4 e = rec[r];
-      const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
-      const int q = lj * kTile + li;
+  const int ox = x0 - (S - 1) + 32768, oy = y0 - (S - 1) + 32768;
+  // pass 1: minimum depth per anchor cell.  The first kKeep records of a thread stay in registers
+  // for pass 2 (the average bin holds ~4 per thread), the rest are read again (L2).
+  constexpr int kKeep = 4;
+  uint4 keep[kKeep];
+  int ckeep[kKeep];
 #pragma unroll
-      for (int dj = 0; dj < 3; dj++) {
-        if ((unsigned)(lj + dj) >= (unsigned)kTile) continue;
-#pragma unroll
-        for (int di = 0; di < 3; di++)
-          if ((unsigned)(li + di) < (unsigned)kTile) atomicMin(&s_depth[q + dj * kTile + di], e.y);
+  for (int k = 0; k < kKeep; k++) {
+    const size_t r = start + tid + (size_t)k * kTileThreads;
+    ckeep[k] = -1;
+    if (r < end) {
+      keep[k] = rec[r];
+      const int u = (int)(keep[k].x & 0xFFFFu) - ox, w = (int)(keep[k].x >> 16) - oy;
+      if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E) {
+        ckeep[k] = w * E + u;
+        atomicMin(&s_depth[ckeep[k]], keep[k].y);
       }
-    }
-    __syncthreads();
-    for (size_t r = start + tid; r < end; r += kTileThreads) {  // pass 2: min tag at the min depth
-      const uint4 e = rec[r];
-      const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
-      const int q = lj * kTile + li;
-#pragma unroll
-      for (int dj = 0; dj < 3; dj++) {
-        if ((unsigned)(lj + dj) >= (unsigned)kTile) continue;
-#pragma unroll
-        for (int di = 0; di < 3; di++)
-          if ((unsigned)(li + di) < (unsigned)kTile && s_depth[q + dj * kTile + di] == e.y)
-            atomicMin(&s_tag[q + dj * kTile + di], e.z);
-      }
-    }
-  } else {
-    // pass 1: minimum depth per cell
-    for (size_t r = start + tid; r < end; r += kTileThreads) {
-      const uint4 e = rec[r];
-      const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
-      for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
-        for (int i = max(li, 0); i < min(li + S, kTile); i++) atomicMin(&s_depth[j * kTile + i], e.y);
-    }
-    __syncthreads();
-    // pass 2: lowest tie-break word among the fragments at the minimum depth
-    for (size_t r = start + tid; r < end; r += kTileThreads) {
-      const uint4 e = rec[r];
-      const int li = (int)(e.x & 0xFFFFu) - 32768 - x0, lj = (int)(e.x >> 16) - 32768 - y0;
-      for (int j = max(lj, 0); j < min(lj + S, kTile); j++)
-        for (int i = max(li, 0); i < min(li + S, kTile); i++)
-          if (s_depth[j * kTile + i] == e.y) atomicMin(&s_tag[j * kTile + i], e.z);
     }
   }
+  for (size_t r = start + tid + (size_t)kKeep * kTileThreads; r < end; r += kTileThreads) {
+    const uint4 e = rec[r];
+    const int u = (int)(e.x & 0xFFFFu) - ox, w = (int)(e.x >> 16) - oy;
+    if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E) atomicMin(&s_depth[w * E + u], e.y);
+  }
   __syncthreads();
-  // the CTA owns the tile: plain stores of the finished pixels (8 per thread, one row segment)
-  uint8_t* img = images + (size_t)v * pitch;
+  // pass 2: lowest tie-break word among the records at the minimum depth of their cell
+#pragma unroll
+  for (int k = 0; k < kKeep; k++)
+    if (ckeep[k] >= 0 && s_depth[ckeep[k]] == keep[k].y) atomicMin(&s_tag[ckeep[k]], keep[k].z);
+  for (size_t r = start + tid + (size_t)kKeep * kTileThreads; r < end; r += kTileThreads) {
+    const uint4 e = rec[r];
+    const int u = (int)(e.x & 0xFFFFu) - ox, w = (int)(e.x >> 16) - oy;
+    if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E && s_depth[w * E + u] == e.y)
+      atomicMin(&s_tag[w * E + u], e.z);
+  }
+  __syncthreads();
+  // S x S min filter; the CTA owns the tile: plain stores of the finished pixels (8 per thread, one
+  // row segment).  Pixel (i, j) of the tile <- cells u in [i, i+S), v in [j, j+S).
   const int row = tid >> 2, col = (tid & 3) * 8;
+  unsigned long long best[8];
+  auto cell_key = [&](int q) { return ((unsigned long long)s_depth[q] << 32) | s_tag[q]; };
+  if (ST == 3) {
+    unsigned long long vm[10];  // column minima over the three rows
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
+      const int q = row * E + col + c;
+      const unsigned long long k0 = cell_key(q), k1 = cell_key(q + E), k2 = cell_key(q + 2 * E);
+      vm[c] = min(k0, min(k1, k2));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) best[k] = min(vm[k], min(vm[k + 1], vm[k + 2]));
+  } else {
+    // generic point size: horizontal minima of every anchor row into shared memory, then vertical
+    unsigned long long* s_h = reinterpret_cast<unsigned long long*>(s_dyn + 2 * E * E + ((2 * E * E) & 1));  // [E][32]
+    for (int q = tid; q < E * kTile; q += kTileThreads) {
+      const int vv = q >> 5, i = q & 31;
+      unsigned long long m = ~0ull;
+      for (int du = 0; du < S; du++) m = min(m, cell_key(vv * E + i + du));
+      s_h[q] = m;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      unsigned long long m = ~0ull;
+      for (int dv = 0; dv < S; dv++) m = min(m, s_h[(row + dv) * kTile + col + k]);
+      best[k] = m;
+    }
+  }
+  uint8_t* img = images + (size_t)v * pitch;
   const int y = y0 + row;
   if (y < H) {
     unsigned long long packed = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const uint32_t d = s_depth[row * kTile + col + k], tg = s_tag[row * kTile + col + k];
-      const bool empty = d == 0xFFFFFFFFu;
-      const uint32_t pix = empty ? 255u : (PACKED ? (tg & 0xFFu) : (uint32_t)__ldg(val + tg));
-      packed |= (unsigned long long)pix << (8 * k);
+      const uint32_t tg = (uint32_t)best[k];
+      const bool empty = best[k] == ~0ull;
       const int x = x0 + col + k;
+      uint32_t pix = 255u;
+      if (!empty) pix = PACKED ? (tg & 0xFFu) : (x < W ? (uint32_t)__ldg(val + tg) : 0u);
+      packed |= (unsigned long long)pix << (8 * k);
       if (winners && x < W) winners[(size_t)v * P + (size_t)y * W + x] = empty ? NMI_EMPTY : (PACKED ? tg >> 8 : tg);
     }
     const size_t o = (size_t)y * W + x0 + col;
@@ -549,7 +624,7 @@ void launch_intensity_u8(const float4* pts, const uint32_t* orig, uint8_t* val, 
   intensity_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pts, orig, val, tag, packed, n);
 }
 
-void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const ViewConst& vc,
+void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const float* aabb, const ViewConst& vc,
                          const float c0[3], const float margin[3], float4* out_pts,
                          uint32_t* out_idx, uint32_t* counter, uint32_t* block_counts,
                          cudaStream_t st) {
@@ -560,9 +635,9 @@ void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, co
   cc.my = margin[1];
   cc.mz = margin[2];
   const uint32_t nblocks = (n + kCullBlock - 1) / kCullBlock;
-  cull_count_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, n, vc, cc, block_counts);
+  cull_count_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, n, vc, cc, aabb, block_counts);
   cull_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, counter);
-  cull_scatter_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, orig, n, vc, cc, block_counts, out_pts,
+  cull_scatter_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, orig, n, vc, cc, aabb, block_counts, out_pts,
                                                         out_idx);
 }
 
@@ -612,12 +687,20 @@ void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, uint32_t bin_cap, c
   if (nviews == 0) return;
   const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
   const unsigned grid = (unsigned)nviews * ntx * nty;
-  if (packed)
-    tile_resolve_kernel<true><<<grid, kTileThreads, 0, st>>>(rec, rec_cap, bin_cap, offsets, total, ntx, ntx * nty, vc.W, vc.H,
-                                                              vc.s, val, images, pitch, winners, P);
-  else
-    tile_resolve_kernel<false><<<grid, kTileThreads, 0, st>>>(rec, rec_cap, bin_cap, offsets, total, ntx, ntx * nty, vc.W, vc.H,
-                                                               vc.s, val, images, pitch, winners, P);
+  const int E = kTile + vc.s - 1;
+  // anchor cells (depth + tag words); generic point sizes add the [E][32] u64 row minima
+  size_t smem = (size_t)2 * E * E * sizeof(uint32_t);
+  if (vc.s != 3) smem += 8 + (size_t)E * kTile * sizeof(unsigned long long);
+#define NMI_TR(PK, ST3)                                                                                         \
+  tile_resolve_kernel<PK, ST3><<<grid, kTileThreads, smem, st>>>(rec, rec_cap, bin_cap, offsets, total, ntx,     \
+                                                                  ntx * nty, vc.W, vc.H, vc.s, val, images, pitch, \
+                                                                  winners, P)
+  if (vc.s == 3) {
+    if (packed) NMI_TR(true, 3); else NMI_TR(false, 3);
+  } else {
+    if (packed) NMI_TR(true, 0); else NMI_TR(false, 0);
+  }
+#undef NMI_TR
 }
 
 void launch_resolve(unsigned long long* zbuf, const uint8_t* val, int nviews, size_t P,
