@@ -283,6 +283,23 @@ int nmi_get_warp(nmi_ctx *ctx, int w, uint8_t *host);      /* W*H u8         */
 /* integer histograms of pair (s, w): J bins*bins, HA/HB bins (u32)           */
 int nmi_get_hist(nmi_ctx *ctx, int s, int w, const nmi_flags *flags,
                  uint32_t *J, uint32_t *HA, uint32_t *HB, float *score);
+/* The same read-back through a chosen build of the histogram kernel: path 0 = what
+ * nmi_get_hist picks, 1 = the plain batched build a search launches when no hot grey level
+ * was seen (variant 0: persistent CTAs; J is copied out before the epilogue, HA / HB / score
+ * are the fast epilogue's own -- the code the benchmark times), 2 = the build with the
+ * hot-bin side tables.  nmi_last_hist_path: which of 1 / 2 the last batched launch used.     */
+int nmi_get_hist_path(nmi_ctx *ctx, int s, int w, const nmi_flags *flags, int path,
+                      uint32_t *J, uint32_t *HA, uint32_t *HB, float *score);
+int nmi_last_hist_path(nmi_ctx *ctx);
+/* nS*nW x CUDAF::NMIWithCuda_noMask (src/Tracking.cc:1879-1894) over image stacks produced
+ * elsewhere -- e.g. the reference's own GL renders and cv::cuda warps: every (render r,
+ * warp w) pair of n_r renders and n_w warped frames (device memory, W*H u8 each, top-down
+ * rows, `*_stride` bytes apart) is scored by the one batched launch a grid search uses.
+ * scores_host[w * n_r + r] (may be NULL).  Afterwards nmi_get_render / nmi_get_warp /
+ * nmi_get_hist* address these stacks.                                                        */
+int nmi_score_pairs(nmi_ctx *ctx, const void *renders_dev, int n_r, size_t r_stride,
+                    const void *warps_dev, int n_w, size_t w_stride, int W, int H,
+                    const nmi_flags *flags, float *scores_host);
 /* per-stage device times of the last search, ms:
  * [0] params+cull [1] render (bin + tile resolve, all view groups) [2] unused
  * [3] warp [4] hist+score [5] argmax

@@ -168,6 +168,16 @@ def search_mesh(cam, Twc, g, verts, tris, frame, bins=256, bg=True, mode=SUC, ke
     return scores, renders, warps
 
 
+def cell_homography(cam, g, ix, iy, iz):
+    """Forward K R K^-1 (float64 3x3), the matrix image.cpp:104-106 hands to warpPerspective."""
+    m = np.zeros(9, dtype=np.float64)
+    lib = load()
+    lib.orc_cell_homography.argtypes = [C.POINTER(OrcCamera), C.POINTER(OrcGrid), C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p]
+    lib.orc_cell_homography(C.byref(camera(cam)), C.byref(grid(g)), ix, iy, iz, _p(m))
+    return m.reshape(3, 3)
+
+
 def cell_homography_inv(cam, g, ix, iy, iz):
     m = np.zeros(9, dtype=np.float32)
     load().orc_cell_homography_inv(C.byref(camera(cam)), C.byref(grid(g)), ix, iy, iz, _p(m))

@@ -86,6 +86,25 @@ def build_oracle(force: bool = False) -> Path:
     return ORACLE_LIB
 
 
+NPP_LIB = ROOT / "oracle" / "_build" / "libnmi_nppcheck.so"
+
+
+def build_nppcheck(force: bool = False):
+    """NPP's nppiWarpPerspective_8u_C1R behind a C ABI (oracle/npp_check.cu): a checker for the warp
+    stage in the GPU tests, never loaded by the product.  None when libnppig is not installed."""
+    src = ROOT / "oracle" / "npp_check.cu"
+    if not force and NPP_LIB.exists() and NPP_LIB.stat().st_mtime >= src.stat().st_mtime:
+        return NPP_LIB
+    if not Path("/usr/local/cuda/include/nppi_geometry_transforms.h").exists():
+        return NPP_LIB if NPP_LIB.exists() else None
+    res = subprocess.run(["make", "-C", str(ROOT / "oracle"), "npp", f"NVCC={_nvcc()}"] + (["-B"] if force else []),
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("NPP checker build failed")
+    return NPP_LIB
+
+
 REF_LIB = ROOT / "oracle" / "_ref" / "libnmi_ref.so"
 REF_CUF = Path("/root/reference/Thirdparty/CUDA_Functions")
 
@@ -111,3 +130,4 @@ if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose=True))
     print(build_oracle(force="--force" in sys.argv))
     print(build_reference(force="--force" in sys.argv))
+    print(build_nppcheck(force="--force" in sys.argv))

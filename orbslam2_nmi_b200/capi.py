@@ -143,6 +143,10 @@ SYMBOLS = [
     ("nmi_get_winners", C.c_int, [_P, C.c_int, _P]),
     ("nmi_get_warp", C.c_int, [_P, C.c_int, _P]),
     ("nmi_get_hist", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Flags), _P, _P, _P, _P]),
+    ("nmi_get_hist_path", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Flags), C.c_int, _P, _P, _P, _P]),
+    ("nmi_last_hist_path", C.c_int, [_P]),
+    ("nmi_score_pairs", C.c_int, [_P, _P, C.c_int, C.c_size_t, _P, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                  C.POINTER(Flags), _P]),
     ("nmi_get_timings", C.c_int, [_P, _P, C.POINTER(C.c_int)]),
 ]
 

@@ -51,6 +51,23 @@ void launch_mesh_raster(const float4* verts, const uint3* tris, const uint32_t* 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 
+void prefer_max_shared(const void* kernel) {
+  static const bool on = [] {
+    const char* e = getenv("NMI_CARVEOUT");
+    return e && atoi(e) != 0;
+  }();
+  if (!on) return;
+  struct Seen { const void* k; int dev; };
+  static thread_local std::vector<Seen> seen;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  for (const Seen& s : seen)
+    if (s.k == kernel && s.dev == dev) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();
+  seen.push_back({kernel, dev});
+}
+
 }  // namespace nmi
 
 using namespace nmi;
@@ -176,6 +193,7 @@ struct nmi_ctx {
   uint32_t term_tab_len = 0;
   DevBuf<uint32_t> img_mode, hot;
   int hist_skip = 1;  // 0 never, 1 automatic, 2 always ($NMI_HIST_SKIP, nmi_ctx_set_hist_skip)
+  bool last_skipcap = false;  // the last batched launch was the build with the side tables
   cudaEvent_t ev_hot = nullptr;
   bool hot_pending = false;
   uint32_t hot_total = 0;  // pixels sampled per image when h_feedback[5..6] were written
@@ -446,6 +464,85 @@ int render_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int n
   return draw_views(c, vc, d_centres, nviews, images, winners);
 }
 
+// schedule order: tiles of 8 renders x 16 warps, so the ~148 CTAs in flight share
+// ~24 images (48 MB at 1080p) and the histogram inputs are served from L2.
+// hp[k] = (local render, local warp) of evaluation k, hi[k] = its slot in the rating array
+// (warp-major, synthetic view fastest: rating[wz][wy][wx][sz][sy][sx], localization.cpp:185-210).
+void fill_pair_schedule(int2* hp, uint32_t* hi, int nvl, int nwl, int nS_total, int vb, int wb) {
+  const int TS = 8, TW = 16;
+  size_t k = 0;
+  for (int s0 = 0; s0 < nvl; s0 += TS)
+    for (int w0 = 0; w0 < nwl; w0 += TW)
+      for (int w = w0; w < w0 + TW && w < nwl; w++)
+        for (int s = s0; s < s0 + TS && s < nvl; s++) {
+          hp[k] = make_int2(s, w);
+          hi[k] = (uint32_t)((size_t)(w + wb) * nS_total + (s + vb));
+          k++;
+        }
+}
+
+// Histogram + score of every scheduled (render, warp) pair of c->renders x c->warps, then the
+// on-device argmax -- the nS*nW calls of CUDAF::NMIWithCuda_noMask and find_max_elements of one
+// grid search (Tracking.cc:1886-1905).  Records ev[4..6].
+int score_pairs_launch(nmi_ctx* c, const nmi_flags* f, int nvl, int nwl, const int2* d_pairs,
+                       const uint32_t* d_index, size_t npl, size_t nP, unsigned long long* key_dev,
+                       float* scores_dev, bool tiled) {
+  if (c->timed) CK(cudaEventRecord(c->ev[4], c->stream));
+  // hot-bin skipping: sample every image's dominant grey level (decides per pair inside the
+  // kernel); the build with the side tables is launched when the previous search saw levels
+  // that can reach the 1/6 threshold
+  const bool use_skip = c->hist_skip != 0 && f->bins == 256 && f->bg;
+  bool skipcap = c->hist_skip == 2;
+  if (use_skip) {
+    if (c->hist_skip == 1 && c->hot_pending && cudaEventQuery(c->ev_hot) == cudaSuccess)
+      skipcap = ((unsigned long long)c->h_feedback[5] + c->h_feedback[6]) * 6ull >= c->hot_total;
+    CK(c->img_mode.reserve((size_t)(nvl + nwl)));
+    CK(c->hot.reserve(2));
+    c->launches += launch_image_modes(c->renders.p, c->pitch, nvl, c->warps.p, c->pitch, nwl, (uint32_t)c->P,
+                                      c->img_mode.p, c->hot.p, c->stream);
+    CK(cudaMemcpyAsync(c->h_feedback + 5, c->hot.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev_hot, c->stream));
+    c->hot_pending = true;
+    c->hot_total = image_mode_sample_total((uint32_t)c->P);
+  }
+  HistArgs a{};
+  a.renders = c->renders.p;
+  a.warps = c->warps.p;
+  a.render_pitch = a.warp_pitch = c->pitch;
+  a.pairs = d_pairs;
+  a.out_index = d_index;
+  a.npairs = (int)npl;
+  a.npix = (uint32_t)c->P;
+  a.length = (uint32_t)c->P;
+  a.bins = f->bins;
+  a.bg = f->bg;
+  a.mode = f->score_mode;
+  a.variant = f->variant;
+  a.scores = scores_dev ? scores_dev : c->scores.p;
+  if (int rc = ensure_term_table(c, (uint32_t)c->P)) return rc;
+  a.term_tab = c->term_tab.p;
+  if (use_skip) {
+    a.img_mode = c->img_mode.p;
+    a.sample_total = image_mode_sample_total((uint32_t)c->P);
+    a.nrenders = nvl;
+    a.skip_mode = c->hist_skip;
+    a.skipcap = skipcap;
+  }
+  c->last_skipcap = use_skip && skipcap;
+  const int nl = launch_joint_hist_score(a, c->stream);
+  REQUIRE(nl >= 0, NMI_ERR_CUDA, "histogram kernel configuration failed");
+  c->launches += nl;
+  if (c->timed) CK(cudaEventRecord(c->ev[5], c->stream));
+  // an enqueued (multi-GPU) search whose record bins filled up publishes NMI_KEY_RETRY instead
+  // of a winner taken from incomplete renders
+  launch_argmax(a.scores, d_index, (int)npl, (uint32_t)nP, key_dev ? key_dev : c->key.p,
+                key_dev && tiled ? c->bin_total.p + 1 : nullptr, c->stream);
+  c->launches++;
+  if (c->timed) CK(cudaEventRecord(c->ev[6], c->stream));
+  CK(cudaGetLastError());
+  return NMI_OK;
+}
+
 int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_flags* f, int rank,
                 int world, unsigned long long* key_dev, float* scores_dev) {
   REQUIRE(c && Twc, NMI_ERR_INVALID, "null ctx / Twc");
@@ -502,22 +599,8 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
     const int wx = w % g->nW[0], wy = (w / g->nW[0]) % g->nW[1], wz = w / (g->nW[0] * g->nW[1]);
     nmi_cell_homography_inv(&c->cam, g, wx, wy, wz, hm + 9 * (size_t)(w - wb));
   }
-  // schedule order: tiles of 8 renders x 16 warps, so the ~148 CTAs in flight share
-  // ~24 images (48 MB at 1080p) and the histogram inputs are served from L2
-  int2* hp = reinterpret_cast<int2*>(c->h_params + off_p);
-  uint32_t* hi = reinterpret_cast<uint32_t*>(c->h_params + off_i);
-  {
-    const int TS = 8, TW = 16;
-    size_t k = 0;
-    for (int s0 = 0; s0 < nvl; s0 += TS)
-      for (int w0 = 0; w0 < nwl; w0 += TW)
-        for (int w = w0; w < w0 + TW && w < nwl; w++)
-          for (int s = s0; s < s0 + TS && s < nvl; s++) {
-            hp[k] = make_int2(s, w);
-            hi[k] = (uint32_t)((size_t)(w + wb) * nS + (s + vb));
-            k++;
-          }
-  }
+  fill_pair_schedule(reinterpret_cast<int2*>(c->h_params + off_p), reinterpret_cast<uint32_t*>(c->h_params + off_i),
+                     nvl, nwl, nS, vb, wb);
 
   // ---- buffers ----
   CK(c->renders.reserve((size_t)nvl * c->pitch));
@@ -578,58 +661,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
   if (c->timed) CK(cudaEventRecord(c->ev[3], c->stream));
   CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join: the warps are done
-  if (c->timed) CK(cudaEventRecord(c->ev[4], c->stream));
-  // hot-bin skipping: sample every image's dominant grey level (decides per pair inside the
-  // kernel); the build with the side tables is launched when the previous search saw levels
-  // that can reach the 1/6 threshold
-  const bool use_skip = c->hist_skip != 0 && f->bins == 256 && f->bg;
-  bool skipcap = c->hist_skip == 2;
-  if (use_skip) {
-    if (c->hist_skip == 1 && c->hot_pending && cudaEventQuery(c->ev_hot) == cudaSuccess)
-      skipcap = ((unsigned long long)c->h_feedback[5] + c->h_feedback[6]) * 6ull >= c->hot_total;
-    CK(c->img_mode.reserve((size_t)(nvl + nwl)));
-    CK(c->hot.reserve(2));
-    c->launches += launch_image_modes(c->renders.p, c->pitch, nvl, c->warps.p, c->pitch, nwl, (uint32_t)c->P,
-                                      c->img_mode.p, c->hot.p, c->stream);
-    CK(cudaMemcpyAsync(c->h_feedback + 5, c->hot.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaEventRecord(c->ev_hot, c->stream));
-    c->hot_pending = true;
-    c->hot_total = image_mode_sample_total((uint32_t)c->P);
-  }
-  HistArgs a{};
-  a.renders = c->renders.p;
-  a.warps = c->warps.p;
-  a.render_pitch = a.warp_pitch = c->pitch;
-  a.pairs = d_pairs;
-  a.out_index = d_index;
-  a.npairs = (int)npl;
-  a.npix = (uint32_t)c->P;
-  a.length = (uint32_t)c->P;
-  a.bins = f->bins;
-  a.bg = f->bg;
-  a.mode = f->score_mode;
-  a.variant = f->variant;
-  a.scores = scores_dev ? scores_dev : c->scores.p;
-  if (int rc = ensure_term_table(c, (uint32_t)c->P)) return rc;
-  a.term_tab = c->term_tab.p;
-  if (use_skip) {
-    a.img_mode = c->img_mode.p;
-    a.sample_total = image_mode_sample_total((uint32_t)c->P);
-    a.nrenders = nvl;
-    a.skip_mode = c->hist_skip;
-    a.skipcap = skipcap;
-  }
-  const int nl = launch_joint_hist_score(a, c->stream);
-  REQUIRE(nl >= 0, NMI_ERR_CUDA, "histogram kernel configuration failed");
-  c->launches += nl;
-  if (c->timed) CK(cudaEventRecord(c->ev[5], c->stream));
-  // an enqueued (multi-GPU) search whose record bins filled up publishes NMI_KEY_RETRY instead
-  // of a winner taken from incomplete renders
-  launch_argmax(a.scores, d_index, (int)npl, (uint32_t)nP, key_dev ? key_dev : c->key.p,
-                key_dev && tiled ? c->bin_total.p + 1 : nullptr, c->stream);
-  c->launches++;
-  if (c->timed) CK(cudaEventRecord(c->ev[6], c->stream));
-  CK(cudaGetLastError());
+  if (int rc = score_pairs_launch(c, f, nvl, nwl, d_pairs, d_index, npl, nP, key_dev, scores_dev, tiled)) return rc;
 
   c->conservative_once = false;
   c->has_search = true;
@@ -1104,7 +1136,8 @@ int nmi_warp_ptr(nmi_ctx* c, const nmi_grid* g, int wx, int wy, int wz, void** d
 // One evaluation.  J / HA / HB: optional DEVICE destinations of the integer histograms
 // (bins*bins, bins, bins u32); when only some are wanted the rest land in context scratch.
 static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped, uint32_t npix,
-                       const nmi_flags* f, uint32_t* J, uint32_t* HA, uint32_t* HB, float* score_host) {
+                       const nmi_flags* f, uint32_t* J, uint32_t* HA, uint32_t* HB, float* score_host,
+                       int path = 0) {
   HistArgs a{};
   a.renders = render;
   a.warps = warped;
@@ -1128,7 +1161,7 @@ static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped,
     a.dumpHA = HA ? HA : c->dumpH.p;
     a.dumpHB = HB ? HB : c->dumpH.p + 256;
   }
-  if (c->hist_skip != 0 && f->bins == 256 && f->bg && ((uintptr_t)render % 16) == 0 &&
+  if (path != 1 && (c->hist_skip != 0 || path == 2) && f->bins == 256 && f->bg && ((uintptr_t)render % 16) == 0 &&
       ((uintptr_t)warped % 16) == 0) {
     // single evaluation: always the build with the side tables, the kernel decides
     CK(c->img_mode.reserve(2));
@@ -1137,7 +1170,7 @@ static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped,
     a.img_mode = c->img_mode.p;
     a.sample_total = image_mode_sample_total(npix);
     a.nrenders = 1;
-    a.skip_mode = c->hist_skip;
+    a.skip_mode = path == 2 ? 2 : c->hist_skip;
     a.skipcap = true;
   }
   REQUIRE(launch_joint_hist_score(a, c->stream) >= 0, NMI_ERR_CUDA,
@@ -1251,10 +1284,11 @@ int nmi_get_warp(nmi_ctx* c, int w, uint8_t* host) {
   return NMI_OK;
 }
 
-int nmi_get_hist(nmi_ctx* c, int s, int w, const nmi_flags* f, uint32_t* J, uint32_t* HA,
-                 uint32_t* HB, float* score) {
+int nmi_get_hist_path(nmi_ctx* c, int s, int w, const nmi_flags* f, int path, uint32_t* J, uint32_t* HA,
+                      uint32_t* HB, float* score) {
   REQUIRE(c && J && HA && HB, NMI_ERR_INVALID, "null argument");
   REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags");
+  REQUIRE(path >= 0 && path <= 2, NMI_ERR_INVALID, "path must be 0 (automatic), 1 (plain batched build) or 2 (side tables)");
   REQUIRE(c->has_search, NMI_ERR_STATE, "no search has run");
   REQUIRE(s - c->v_begin >= 0 && s - c->v_begin < c->nvl && w - c->w_begin >= 0 &&
               w - c->w_begin < c->nwl,
@@ -1264,12 +1298,69 @@ int nmi_get_hist(nmi_ctx* c, int s, int w, const nmi_flags* f, uint32_t* J, uint
   CK(c->dumpH.reserve(512));
   const int rc = eval_images(c, c->renders.p + (size_t)(s - c->v_begin) * c->pitch,
                              c->warps.p + (size_t)(w - c->w_begin) * c->pitch, (uint32_t)c->P, f,
-                             c->dumpJ.p, c->dumpH.p, c->dumpH.p + 256, score);
+                             c->dumpJ.p, c->dumpH.p, c->dumpH.p + 256, score, path);
   if (rc) return rc;
   const size_t nb = (size_t)f->bins;
   CK(cudaMemcpy(J, c->dumpJ.p, nb * nb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(HA, c->dumpH.p, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(HB, c->dumpH.p + 256, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return NMI_OK;
+}
+
+int nmi_get_hist(nmi_ctx* c, int s, int w, const nmi_flags* f, uint32_t* J, uint32_t* HA,
+                 uint32_t* HB, float* score) {
+  return nmi_get_hist_path(c, s, w, f, 0, J, HA, HB, score);
+}
+
+int nmi_last_hist_path(nmi_ctx* c) { return c && c->has_search ? (c->last_skipcap ? 2 : 1) : 0; }
+
+// Score every pair of two caller-supplied image stacks with the batched launch of a grid search.
+int nmi_score_pairs(nmi_ctx* c, const void* renders_dev, int n_r, size_t r_stride, const void* warps_dev,
+                    int n_w, size_t w_stride, int W, int H, const nmi_flags* f, float* scores_host) {
+  REQUIRE(c && renders_dev && warps_dev, NMI_ERR_INVALID, "null argument");
+  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags");
+  REQUIRE(c->has_cam && W == c->cam.W && H == c->cam.H, NMI_ERR_INVALID, "size != camera size");
+  REQUIRE(n_r >= 1 && n_w >= 1 && (size_t)n_r * n_w <= (1u << 26), NMI_ERR_INVALID, "bad stack sizes");
+  REQUIRE(r_stride >= c->P && w_stride >= c->P, NMI_ERR_INVALID, "stride smaller than an image");
+  REQUIRE(c->P / 4096 + 2 < 2048, NMI_ERR_INVALID, "image too large for the histogram kernel");
+  CK(cudaSetDevice(c->device));
+  const size_t npl = (size_t)n_r * n_w;
+  const size_t off_p = 0;
+  const size_t off_i = align_up(off_p + sizeof(int2) * npl, 256);
+  const size_t bytes = align_up(off_i + sizeof(uint32_t) * npl, 256);
+  if (int rc = params_acquire(c)) return rc;
+  if (int rc = ensure_pinned(&c->h_params, &c->h_params_cap, bytes)) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(c->params.reserve(bytes));
+  CK(c->renders.reserve((size_t)n_r * c->pitch));
+  CK(c->warps.reserve((size_t)n_w * c->pitch));
+  CK(c->scores.reserve(npl));
+  CK(c->key.reserve(1));
+  fill_pair_schedule(reinterpret_cast<int2*>(c->h_params + off_p), reinterpret_cast<uint32_t*>(c->h_params + off_i),
+                     n_r, n_w, n_r, 0, 0);
+  c->launches = 0;
+  if (c->timed) {
+    for (int i = 0; i < 4; i++) CK(cudaEventRecord(c->ev[i], c->stream));
+  }
+  CK(cudaMemcpyAsync(c->params.p, c->h_params, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (int rc = params_uploaded(c)) return rc;
+  // into our padded, 128 B aligned slots (the TMA loads of a last partial chunk stay inside memory we own)
+  CK(cudaMemcpy2DAsync(c->renders.p, c->pitch, renders_dev, r_stride, c->P, (size_t)n_r, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpy2DAsync(c->warps.p, c->pitch, warps_dev, w_stride, c->P, (size_t)n_w, cudaMemcpyDeviceToDevice, c->stream));
+  if (int rc = score_pairs_launch(c, f, n_r, n_w, reinterpret_cast<const int2*>(c->params.p + off_p),
+                                  reinterpret_cast<const uint32_t*>(c->params.p + off_i), npl, npl, nullptr, nullptr,
+                                  false))
+    return rc;
+  if (scores_host)
+    CK(cudaMemcpyAsync(scores_host, c->scores.p, npl * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->has_search = true;  // nmi_get_render / nmi_get_warp / nmi_get_hist* now address these stacks
+  c->grid = nmi_grid{};
+  c->grid.nS[0] = n_r; c->grid.nS[1] = c->grid.nS[2] = 1;
+  c->grid.nW[0] = n_w; c->grid.nW[1] = c->grid.nW[2] = 1;
+  c->nvl = n_r;
+  c->nwl = n_w;
+  c->v_begin = c->w_begin = 0;
   return NMI_OK;
 }
 

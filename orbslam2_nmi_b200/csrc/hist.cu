@@ -544,6 +544,24 @@ __device__ __forceinline__ void rows_epilogue_fast(Smem& sm, float L, const Hist
   }
 }
 
+// Parity dump for the builds that run the fast epilogue: the 65 536 counters are copied out of the
+// swizzled packed-u16 words BEFORE the epilogue reads (and, in the persistent kernel, clears) them,
+// repaid crossings added (+4096 each).  The epilogue then runs exactly as in a timed launch, so the
+// marginals and the score that are read back are the fast path's own.  All 512 consumers call it.
+__device__ __forceinline__ void dump_joint_swizzled(const Smem& sm, uint32_t* __restrict__ J, int tid) {
+  constexpr int kConsumers = 16 * 32;
+  for (uint32_t i = tid; i < (uint32_t)kHistWords; i += kConsumers) {
+    const uint32_t r = i >> 7, m = i & 127u;
+    const uint32_t wv = sm.hist[((r << 7) ^ r) ^ m];  // u16g_word<true>((r << 8) | 2m)
+    J[r * 256u + 2u * m] = wv & 0xFFFFu;
+    J[r * 256u + 2u * m + 1u] = wv >> 16;
+  }
+  __threadfence_block();
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+  const uint32_t nev = min(sm.ev_count, (uint32_t)kEvCap);
+  for (uint32_t e = tid; e < nev; e += kConsumers) atomicAdd(J + sm.ev_list[e], 4096u);
+}
+
 template <int NW>
 __device__ __forceinline__ void load_words(uint32_t (&dst)[NW], const uint8_t* p) {
   if (NW % 4 == 0) {
@@ -599,7 +617,7 @@ joint_hist_score_kernel(const HistArgs a) {
   const int nchunks = (int)((npix + kChunk - 1) / kChunk);
   const int total = nchunks * NPASS;
   const float L = (float)a.length;
-  const bool dump = a.dumpJ != nullptr && blockIdx.x == 0;
+  const bool dump = a.dumpJ != nullptr && (int)blockIdx.x == a.dump_pair;
 
   // ---- init ----
   {
@@ -757,9 +775,10 @@ joint_hist_score_kernel(const HistArgs a) {
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
-      if (FASTEP && !dump && a.term_tab != nullptr)
+      if (FASTEP && a.term_tab != nullptr) {
+        if (dump) dump_joint_swizzled(sm, a.dumpJ, tid);  // CTA-uniform
         rows_epilogue_fast<false>(sm, L, a, warp, lane);
-      else
+      } else
         rows_epilogue<POLICY, SWZ, NWARPS>(sm, 0, L, a, dump, warp, lane, SKIPCAP ? &sk : nullptr, skipT);
     }
   }
@@ -802,8 +821,22 @@ joint_hist_score_kernel(const HistArgs a) {
 // mbarriers need no re-initialisation between pairs.  The schedule is static (pair i on CTA
 // i mod gridDim.x): the builds with the side tables, whose pairs differ a lot in cost, stay on
 // one CTA per pair and the hardware's dynamic block scheduler.
-template <bool SWZ, bool SKIPCAP>
-__global__ void __launch_bounds__(16 * 32 + 32, 1)
+// Launched with 544 threads.  -DNMI_HIST_REGCAP_THREADS=1024 caps the kernel at 64 registers (ptxas:
+// no spills) so that other kernels' CTAs fit next to this one on an SM.  Measured (round 2, two
+// contexts alternating searches on one GPU, with and without a common L1/shared carve-out on all
+// kernels): the kernel itself gets 2 % slower (4.55 -> 4.64 ms) and the overlap buys nothing,
+// because this kernel already keeps 74 % of the issue slots and 91 % of the shared-memory pipe busy
+// (profiles/r01_hist_ncu_summary.txt) -- the render-stage kernels are issue-bound too.  Default: 95
+// registers.
+#ifndef NMI_HIST_REGCAP_THREADS
+#define NMI_HIST_REGCAP_THREADS (16 * 32 + 32)
+#endif
+// DUMP: the parity build (nmi_get_hist_path): the same source, plus the copy-out of the joint
+// histogram in front of the epilogue.  A separate instantiation, because this kernel's speed moves
+// by several per cent with its register allocation (the mere presence of the never-taken dump branch
+// cost 4.55 -> 4.72 ms at C2): the timed build contains no parity code at all.
+template <bool SWZ, bool SKIPCAP, bool DUMP = false>
+__global__ void __launch_bounds__(NMI_HIST_REGCAP_THREADS, 1)
 joint_hist_score_persistent_kernel(const HistArgs a) {
   constexpr int NWARPS = 16;
   constexpr int kConsumers = NWARPS * 32;
@@ -873,7 +906,7 @@ joint_hist_score_persistent_kernel(const HistArgs a) {
   int kk = 0;
   for (int pi = blockIdx.x; pi < a.npairs; pi += gridDim.x) {
     const int2 pr = a.pairs[pi];
-    const bool dump = a.dumpJ != nullptr && pi == 0;
+    const bool dump = DUMP && a.dumpJ != nullptr && pi == a.dump_pair;
     // hot-bin skipping: the sampled modes of this pair's two images decide (CTA-uniform)
     uint32_t skipT = 0xFFFFFFFFu;
     if (SKIPCAP && a.img_mode != nullptr && a.bg && a.skip_mode != 0) {
@@ -936,10 +969,12 @@ joint_hist_score_persistent_kernel(const HistArgs a) {
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B1: every increment of this pair has landed
-    if (SWZ && !SKIPCAP && !dump && a.term_tab != nullptr)
+    if (SWZ && !SKIPCAP && a.term_tab != nullptr) {
+      if (dump) dump_joint_swizzled(sm, a.dumpJ, tid);  // CTA-uniform; the epilogue below is the timed one
       rows_epilogue_fast<true>(sm, L, a, warp, lane);
-    else
+    } else {
       rows_epilogue<P_U16G, SWZ, NWARPS, true>(sm, 0, L, a, dump, warp, lane, SKIPCAP ? &sk : nullptr, skipT);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B2: rows read and cleared, marginals complete
     if (warp < 3) {
       float v[8];
@@ -1103,7 +1138,7 @@ joint_hist_score_tmem_kernel(const HistArgs a) {
   const uint32_t taddr0 = tbase + ((32u * ((uint32_t)warp & 3u)) << 16) + 8u * (cgrp >> 1) + 4u * (cgrp & 1u);
   int kk = 0;
   for (int pi = blockIdx.x; pi < a.npairs; pi += gridDim.x) {
-    const bool dump = a.dumpJ != nullptr && pi == 0;
+    const bool dump = a.dumpJ != nullptr && pi == a.dump_pair;
     for (int k = 0; k < nchunks; k++, kk++) {
       const int st = kk % kStages;
       const uint32_t off = (uint32_t)k * kChunk + pix0;
@@ -1125,10 +1160,12 @@ joint_hist_score_tmem_kernel(const HistArgs a) {
         accum_slow<P_U16G, SWZ, NW>(sm, r, w, nvalid, a.bg, 0, warp);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B1: every increment of this pair has landed
-    if (!dump && a.term_tab != nullptr)
+    if (a.term_tab != nullptr) {
+      if (dump) dump_joint_swizzled(sm, a.dumpJ, tid);
       rows_epilogue_fast<true>(sm, L, a, warp, lane);
-    else
+    } else {
       rows_epilogue<P_U16G, SWZ, NWARPS, true>(sm, 0, L, a, dump, warp, lane);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B2
     if (warp < 3) {
       float v[8];
@@ -1245,9 +1282,9 @@ int launch_t(const HistArgs& a, cudaStream_t st) {
   return 1;
 }
 
-template <bool SWZ, bool SKIPCAP>
+template <bool SWZ, bool SKIPCAP, bool DUMP = false>
 int launch_persistent(const HistArgs& a, cudaStream_t st) {
-  auto kern = joint_hist_score_persistent_kernel<SWZ, SKIPCAP>;
+  auto kern = joint_hist_score_persistent_kernel<SWZ, SKIPCAP, DUMP>;
   constexpr size_t smem = sizeof(Smem) + (SKIPCAP ? sizeof(SmemSkip) : 0);
   static int sms[64] = {0};  // per device: one CTA per SM (the histogram takes most of an SM's shared memory)
   int dev = 0;
@@ -1294,6 +1331,7 @@ int launch_image_modes(const uint8_t* renders, size_t rpitch, int nr, const uint
                        int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st) {
   if (nr + nw == 0) return 0;
   cudaMemsetAsync(hot, 0, 2 * sizeof(uint32_t), st);
+  prefer_max_shared((const void*)image_mode_kernel);
   image_mode_kernel<<<nr + nw, kImThreads, 0, st>>>(renders, rpitch, nr, warps, wpitch, npix, img_mode, hot);
   return 1;
 }
@@ -1325,7 +1363,7 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
                                    : launch_t<P_U16G, true, 16, true>(a, st);
     case 10: return launch_tmem(a, st);  // variant 0 with the pixel ring staged through tensor memory
     default:  // variant 0: TMA ring, bank swizzle, persistent CTAs with the fast epilogue
-      return launch_persistent<true, false>(a, st);
+      return a.dumpJ != nullptr ? launch_persistent<true, false, true>(a, st) : launch_persistent<true, false>(a, st);
   }
 }
 

@@ -63,7 +63,8 @@ struct HistArgs {
   int nrenders;
   int skip_mode;
   bool skipcap;
-  // optional dumps (parity): when non-null, pair 0 of the launch writes them
+  // optional dumps (parity): when non-null, pair `dump_pair` of the launch writes them
+  int dump_pair;
   uint32_t* dumpJ;
   uint32_t* dumpHA;
   uint32_t* dumpHB;
@@ -86,5 +87,13 @@ void make_view_const(const nmi_camera& cam, const float Twc[16], ViewConst* vc);
 uint64_t pack_key(float max_score, int64_t index);
 
 void set_error(const std::string& msg);
+
+// An SM's L1 / shared-memory split is a per-SM state: CTAs of two kernels that ask for different
+// carve-outs cannot be resident on one SM together.  With $NMI_CARVEOUT=1 the render-stage and warp
+// kernels prefer the maximum shared-memory split the histogram kernel needs, so that their CTAs can
+// run next to a histogram CTA when two searches are in flight on one GPU (tools/exp_pipeline.py).
+// Measured in round 2: no gain (6.17 vs 6.06 ms per search at depth 2, every kernel a little slower
+// with the small L1) -- off by default, kept as a switch.
+void prefer_max_shared(const void* kernel);
 
 }  // namespace nmi

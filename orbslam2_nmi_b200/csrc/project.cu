@@ -635,6 +635,9 @@ void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, co
   cc.my = margin[1];
   cc.mz = margin[2];
   const uint32_t nblocks = (n + kCullBlock - 1) / kCullBlock;
+  prefer_max_shared((const void*)cull_count_kernel);
+  prefer_max_shared((const void*)cull_scan_kernel);
+  prefer_max_shared((const void*)cull_scatter_kernel);
   cull_count_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, n, vc, cc, aabb, block_counts);
   cull_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, counter);
   cull_scatter_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, orig, n, vc, cc, aabb, block_counts, out_pts,
@@ -663,6 +666,9 @@ void launch_bin_points(int mode, const float4* cpts, const uint32_t* ctag, const
   const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
   const dim3 grid(148 * 16), block(256);
   const size_t smem = sizeof(float4) * nviews;
+  prefer_max_shared((const void*)bin_kernel<0>);
+  prefer_max_shared((const void*)bin_kernel<1>);
+  prefer_max_shared((const void*)bin_kernel<2>);
   if (mode == 0)
     bin_kernel<0><<<grid, block, smem, st>>>(cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts,
                                              offsets, rec, rec_cap, bin_cap, overflow);
@@ -692,13 +698,14 @@ void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, uint32_t bin_cap, c
   size_t smem = (size_t)2 * E * E * sizeof(uint32_t);
   if (vc.s != 3) smem += 8 + (size_t)E * kTile * sizeof(unsigned long long);
 #define NMI_TR(PK, ST3)                                                                                         \
+  prefer_max_shared((const void*)tile_resolve_kernel<PK, ST3>);                                                   \
   tile_resolve_kernel<PK, ST3><<<grid, kTileThreads, smem, st>>>(rec, rec_cap, bin_cap, offsets, total, ntx,     \
                                                                   ntx * nty, vc.W, vc.H, vc.s, val, images, pitch, \
                                                                   winners, P)
   if (vc.s == 3) {
-    if (packed) NMI_TR(true, 3); else NMI_TR(false, 3);
+    if (packed) { NMI_TR(true, 3); } else { NMI_TR(false, 3); }
   } else {
-    if (packed) NMI_TR(true, 0); else NMI_TR(false, 0);
+    if (packed) { NMI_TR(true, 0); } else { NMI_TR(false, 0); }
   }
 #undef NMI_TR
 }

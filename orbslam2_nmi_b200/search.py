@@ -212,15 +212,31 @@ class NmiSearcher:
         check(self.lib.nmi_get_warp(self.h, w, ptr(out)))
         return out
 
-    def get_hist(self, s: int, w: int, flags: Flags | None = None):
+    def get_hist(self, s: int, w: int, flags: Flags | None = None, path: int = 0):
+        """Integer histograms + score of pair (s, w).  path 0: automatic; 1: the plain batched build
+        (variant 0 = the persistent kernel with the fast epilogue, the code a benchmark step times);
+        2: the build with the hot-bin side tables."""
         flags = flags or self.flags()
         b = flags.bins
         J = np.zeros((b, b), dtype=np.uint32)
         HA = np.zeros(b, dtype=np.uint32)
         HB = np.zeros(b, dtype=np.uint32)
         sc = np.zeros(1, dtype=np.float32)
-        check(self.lib.nmi_get_hist(self.h, s, w, C.byref(flags), ptr(J), ptr(HA), ptr(HB), ptr(sc)))
+        check(self.lib.nmi_get_hist_path(self.h, s, w, C.byref(flags), path, ptr(J), ptr(HA), ptr(HB), ptr(sc)))
         return J, HA, HB, float(sc[0])
+
+    def last_hist_path(self) -> int:
+        return int(self.lib.nmi_last_hist_path(self.h))
+
+    def score_pairs(self, renders_dev: int, n_r: int, r_stride: int, warps_dev: int, n_w: int, w_stride: int,
+                    flags: Flags | None = None) -> np.ndarray:
+        """nmi_score_pairs: every (render, warp) pair of two device image stacks through the batched
+        launch of a grid search; scores[w, r]."""
+        flags = flags or self.flags()
+        out = np.zeros(n_r * n_w, dtype=np.float32)
+        check(self.lib.nmi_score_pairs(self.h, renders_dev, n_r, r_stride, warps_dev, n_w, w_stride,
+                                       self.cam.W, self.cam.H, C.byref(flags), ptr(out)))
+        return out.reshape(n_w, n_r)
 
     def timings(self):
         ms = np.zeros(8, dtype=np.float32)

@@ -1,72 +1,114 @@
-// ubench_atoms.cu -- shared-memory atomic throughput on B200 (design input for hist.cu).
+// ubench_atoms.cu -- shared-memory atomic throughput on B200 (design input for csrc/hist.cu and the
+// denominator of bench.py's "smem_atomic" roofline).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench_atoms tools/ubench_atoms.cu
-// Prints atomics/s (whole chip) and lanes/clk/SM at the SM clock it measures itself.
+// Prints atomics/s (whole chip) and lanes/clk/SM at the SM clock the kernel measures itself.
+//
+// Round-2 rewrite: round 1 seeded an LCG with threadIdx.x * constant, so the 32 lanes of a warp
+// walked an arithmetic progression -- its "random" case was close to conflict-free (12.3 lanes/clk
+// vs 12.8 for distinct banks).  Here every index is an independent hash of (thread, iteration)
+// (lowbias32), the hash cost alone is measured as a control, and the cases that matter for the
+// histogram kernel are separate: conflict-free, uniformly random words, the kernel's own
+// packed-u16 + swizzle + return-value pattern, and that pattern with the LDS.128 staging reads.
 #include <cuda_runtime.h>
-#include <cstdio>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
-constexpr int kThreads = 512;
-constexpr int kWords = 32768;  // 128 KiB
+constexpr int kWords = 32768;  // 128 KiB, the joint histogram of hist.cu
 constexpr int kIters = 4096;
 
-enum Mode { RANDOM = 0, DISTINCT_BANKS, SAME_ADDR, RANDOM_RET, U16_RET, MATCH_RANDOM, MATCH_16VALS,
-            SMOOTH, RANDOM_1K, SAME_BANK_DIFF_ADDR, RANDOM_256T, RANDOM_1024T, LOWENT16, NMODES };
-const char* kNames[] = {"random idx (32K words), no return", "distinct banks, random rows", "same address (all lanes)",
-                        "random idx, return value used", "u16-packed + return + wrap check (hist.cu P_U16G)",
-                        "match_any + leader add, random idx", "match_any + leader add, 16 distinct values",
-                        "smooth image-like idx (neighbouring lanes +-2)", "random idx in 1K words",
-                        "same bank, different addresses", "random idx, 256 thr/CTA x2 CTAs/SM?", "random idx 1024 thr",
-                        "plain atomics, 16 distinct values/warp"};
+enum Mode { HASH_ONLY = 0, DISTINCT_BANKS, RANDOM, RANDOM_RET, SAME_ADDR, SAME_BANK_DIFF_ADDR, TWO_WAY, HALF_WARP_RANDOM,
+            HIST_PATTERN, HIST_PATTERN_LDS, RANDOM_RED, NMODES };
+const char* kNames[] = {"control: hash only, no atomics",
+                        "distinct banks (lane = bank), random rows",
+                        "uniformly random words (independent per lane)",
+                        "uniformly random words, return value used",
+                        "same address in all 32 lanes",
+                        "same bank, 32 different addresses",
+                        "2-way: lanes l and l+16 same bank, different rows",
+                        "16 active lanes, random words",
+                        "hist.cu pattern: packed u16 + XOR swizzle + return + OR-check",
+                        "hist.cu pattern + 2 LDS.128 of staged pixels per 16 atomics",
+                        "uniformly random words, red.shared (no return)"};
 
-__device__ __forceinline__ uint32_t lcg(uint32_t& x) { x = x * 1664525u + 1013904223u; return x; }
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {  // lowbias32
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k_atoms(uint32_t* out, long long* cycles) {
-  extern __shared__ uint32_t h[];
+  extern __shared__ __align__(16) uint32_t h[];  // kWords of histogram + 16 KiB of "staged pixels"
+  uint32_t* stage = h + kWords;
+  for (int i = threadIdx.x; i < kWords + 4096; i += blockDim.x) h[i] = i * 2654435761u;
   for (int i = threadIdx.x; i < kWords; i += blockDim.x) h[i] = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  uint32_t x = threadIdx.x * 2654435761u + blockIdx.x * 40503u + 12345u;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(h);
   uint32_t acc = 0;
-  long long t0 = clock64();
+  const long long t0 = clock64();
+  if (MODE == HIST_PATTERN || MODE == HIST_PATTERN_LDS) {
+    // 16 pixels per thread and step, as accum_fast<P_U16G, SWZ>: t = a << 8 | b
+    for (int it = 0; it < kIters / 16; it++) {
+      uint32_t r[4], w[4];
+      if (MODE == HIST_PATTERN_LDS) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(stage + ((threadIdx.x * 4 + it * 64) & 2047));
+        const uint4 wv = *reinterpret_cast<const uint4*>(stage + 2048 + ((threadIdx.x * 4 + it * 64) & 2047));
+        r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
+        w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {  // the staged words are constants: mix so that the pixels stay random
+          r[j] ^= hash32(gtid * 64u + it * 8u + j);
+          w[j] ^= hash32(gtid * 64u + it * 8u + 4u + j);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          r[j] = hash32(gtid * 64u + it * 8u + j);
+          w[j] = hash32(gtid * 64u + it * 8u + 4u + j);
+        }
+      }
+      uint32_t orv = 0;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const uint32_t t = __byte_perm(w[i >> 2], r[i >> 2], 0x4440 + (i & 3) * 0x11);
+        uint32_t addr = (t * 2u) & 0x1FFFCu;
+        addr ^= __byte_perm(r[i >> 2], 0u, 0x4440 + (i & 3)) * 4u;
+        uint32_t inc;
+        asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc) : "r"(t & 1u));
+        uint32_t old;
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(base + addr), "r"(inc) : "memory");
+        orv |= old + inc;
+      }
+      if (orv & 0xF000F000u) acc++;
+    }
+  } else {
 #pragma unroll 8
-  for (int it = 0; it < kIters; it++) {
-    uint32_t r = lcg(x);
-    if (MODE == RANDOM) {
-      atomicAdd(&h[r >> 17], 1u);
-    } else if (MODE == DISTINCT_BANKS) {
-      uint32_t rr = __shfl_sync(0xffffffffu, r, 0);  // same row for the warp
-      atomicAdd(&h[((rr >> 22) << 5) + lane], 1u);
-    } else if (MODE == SAME_ADDR) {
-      uint32_t rr = __shfl_sync(0xffffffffu, r, 0);
-      atomicAdd(&h[rr >> 17], 1u);
-    } else if (MODE == RANDOM_RET) {
-      acc ^= atomicAdd(&h[r >> 17], 1u);
-    } else if (MODE == U16_RET) {
-      uint32_t t = r >> 16;
-      uint32_t sh = (t & 1u) << 4;
-      uint32_t old = atomicAdd(&h[t >> 1], 1u << sh);
-      if (((old >> sh) & 0x3FFFu) == 0x3FFFu) { atomicSub(&h[t >> 1], 0x4000u << sh); acc++; }
-    } else if (MODE == MATCH_RANDOM || MODE == MATCH_16VALS) {
-      uint32_t idx = MODE == MATCH_RANDOM ? (r >> 17) : ((r >> 28) * 37u);
-      unsigned m = __match_any_sync(0xffffffffu, idx);
-      if (lane == (__ffs(m) - 1)) atomicAdd(&h[idx], (uint32_t)__popc(m));
-    } else if (MODE == SMOOTH) {
-      uint32_t rr = __shfl_sync(0xffffffffu, r, 0);
-      uint32_t a = ((rr >> 24) + ((r >> 5) & 3u)) & 255u, b = ((rr >> 16) + ((r >> 9) & 3u)) & 255u;
-      atomicAdd(&h[((a << 8) | b) >> 1], 1u);
-    } else if (MODE == RANDOM_1K) {
-      atomicAdd(&h[r >> 22], 1u);
-    } else if (MODE == SAME_BANK_DIFF_ADDR) {
-      atomicAdd(&h[(r >> 22) << 5], 1u);
-    } else if (MODE == LOWENT16) {
-      atomicAdd(&h[(r >> 28) * 37u], 1u);
-    } else {
-      atomicAdd(&h[r >> 17], 1u);
+    for (int it = 0; it < kIters; it++) {
+      const uint32_t r = hash32(gtid * 4099u + (uint32_t)it * 0x9E3779B9u);
+      if (MODE == HASH_ONLY) {
+        acc ^= r;
+      } else if (MODE == DISTINCT_BANKS) {
+        atomicAdd(&h[((r >> 22) << 5) + lane], 1u);
+      } else if (MODE == RANDOM) {
+        atomicAdd(&h[r >> 17], 1u);
+      } else if (MODE == RANDOM_RED) {
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + ((r >> 17) << 2)) : "memory");
+      } else if (MODE == RANDOM_RET) {
+        acc |= atomicAdd(&h[r >> 17], 1u);
+      } else if (MODE == SAME_ADDR) {
+        atomicAdd(&h[__shfl_sync(0xffffffffu, r, 0) >> 17], 1u);
+      } else if (MODE == SAME_BANK_DIFF_ADDR) {
+        atomicAdd(&h[(r >> 22) << 5], 1u);
+      } else if (MODE == TWO_WAY) {
+        atomicAdd(&h[((r >> 22) << 5) + (lane & 15u)], 1u);
+      } else if (MODE == HALF_WARP_RANDOM) {
+        if (lane < 16) atomicAdd(&h[r >> 17], 1u);
+      }
     }
   }
-  long long t1 = clock64();
+  const long long t1 = clock64();
   __syncthreads();
   uint32_t s = acc;
   for (int i = threadIdx.x; i < kWords; i += blockDim.x) s += h[i];
@@ -74,28 +116,31 @@ __global__ void __launch_bounds__(1024, 1) k_atoms(uint32_t* out, long long* cyc
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+static double g_lanes[NMODES];
+
 template <int MODE>
-void run(int threads, int ctas_per_sm, int sms, uint32_t* d_out, long long* d_cyc) {
+void run(int threads, int sms, uint32_t* d_out, long long* d_cyc) {
   auto k = k_atoms<MODE>;
-  size_t smem = kWords * 4 / ctas_per_sm;  // split the 128 KiB when two CTAs share an SM
-  if (ctas_per_sm == 1) smem = kWords * 4;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWords * 4));
-  int grid = sms * ctas_per_sm;
+  const size_t smem = (size_t)(kWords + 4096) * 4;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  k<<<grid, threads, kWords * 4 / (ctas_per_sm > 1 ? 1 : 1), 0>>>(d_out, d_cyc);  // warm
+  k<<<sms, threads, smem>>>(d_out, d_cyc);  // warm
   cudaEventRecord(e0);
-  k<<<grid, threads, kWords * 4, 0>>>(d_out, d_cyc);
+  k<<<sms, threads, smem>>>(d_out, d_cyc);
   cudaEventRecord(e1);
   cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
-  long long* h = (long long*)malloc(sizeof(long long) * grid);
-  cudaMemcpy(h, d_cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
-  double cyc = 0; for (int i = 0; i < grid; i++) cyc += (double)h[i]; cyc /= grid;
-  free(h);
-  double total = (double)grid * threads * kIters;
-  printf("%-58s thr=%4d  %8.1f Gatom/s  %6.2f lanes/clk/SM (in-kernel)  %7.3f ms  err=%s\n", kNames[MODE], threads,
-         total / ms / 1e6, (double)threads * kIters / cyc, ms, cudaGetErrorString(cudaGetLastError()));
+  long long* hc = (long long*)malloc(sizeof(long long) * sms);
+  cudaMemcpy(hc, d_cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+  double cyc = 0; for (int i = 0; i < sms; i++) cyc += (double)hc[i]; cyc /= sms;
+  free(hc);
+  const double active = MODE == HALF_WARP_RANDOM ? 0.5 : 1.0;
+  const double total = (double)sms * threads * kIters * active;
+  const double lanes = (double)threads * kIters * active / cyc;
+  g_lanes[MODE] = lanes;
+  printf("%-66s thr=%4d %8.1f Gop/s %6.2f lanes/clk/SM %6.2f clk per 32-lane instr  %7.3f ms  %s\n", kNames[MODE], threads,
+         total / ms / 1e6, lanes, 32.0 * active / lanes, ms, cudaGetErrorString(cudaGetLastError()));
 }
 
 int main() {
@@ -103,20 +148,24 @@ int main() {
   printf("%s  SMs=%d  smem/SM=%zu\n", p.name, p.multiProcessorCount, p.sharedMemPerMultiprocessor);
   uint32_t* d_out; long long* d_cyc;
   cudaMalloc(&d_out, 4); cudaMalloc(&d_cyc, 8 * 4096);
-  int sms = p.multiProcessorCount;
-  run<RANDOM>(512, 1, sms, d_out, d_cyc);
-  run<RANDOM>(256, 1, sms, d_out, d_cyc);
-  run<RANDOM>(1024, 1, sms, d_out, d_cyc);
-  run<DISTINCT_BANKS>(512, 1, sms, d_out, d_cyc);
-  run<SAME_ADDR>(512, 1, sms, d_out, d_cyc);
-  run<SAME_BANK_DIFF_ADDR>(512, 1, sms, d_out, d_cyc);
-  run<RANDOM_RET>(512, 1, sms, d_out, d_cyc);
-  run<U16_RET>(512, 1, sms, d_out, d_cyc);
-  run<U16_RET>(1024, 1, sms, d_out, d_cyc);
-  run<MATCH_RANDOM>(512, 1, sms, d_out, d_cyc);
-  run<MATCH_16VALS>(512, 1, sms, d_out, d_cyc);
-  run<LOWENT16>(512, 1, sms, d_out, d_cyc);
-  run<SMOOTH>(512, 1, sms, d_out, d_cyc);
-  run<RANDOM_1K>(512, 1, sms, d_out, d_cyc);
+  const int sms = p.multiProcessorCount;
+  run<HASH_ONLY>(512, sms, d_out, d_cyc);
+  run<DISTINCT_BANKS>(512, sms, d_out, d_cyc);
+  run<DISTINCT_BANKS>(1024, sms, d_out, d_cyc);
+  run<RANDOM>(512, sms, d_out, d_cyc);
+  run<RANDOM>(1024, sms, d_out, d_cyc);
+  run<RANDOM_RED>(512, sms, d_out, d_cyc);
+  run<RANDOM_RET>(512, sms, d_out, d_cyc);
+  run<SAME_ADDR>(512, sms, d_out, d_cyc);
+  run<SAME_BANK_DIFF_ADDR>(512, sms, d_out, d_cyc);
+  run<TWO_WAY>(512, sms, d_out, d_cyc);
+  run<HALF_WARP_RANDOM>(512, sms, d_out, d_cyc);
+  run<HIST_PATTERN>(512, sms, d_out, d_cyc);
+  run<HIST_PATTERN>(1024, sms, d_out, d_cyc);
+  run<HIST_PATTERN_LDS>(512, sms, d_out, d_cyc);
+  // one machine-readable line for bench.py / profiles
+  printf("JSON {\"sms\": %d, \"conflict_free_lanes_per_clk_sm\": %.3f, \"random_lanes_per_clk_sm\": %.3f, "
+         "\"hist_pattern_lanes_per_clk_sm\": %.3f, \"hist_pattern_lds_lanes_per_clk_sm\": %.3f}\n",
+         sms, g_lanes[DISTINCT_BANKS], g_lanes[RANDOM], g_lanes[HIST_PATTERN], g_lanes[HIST_PATTERN_LDS]);
   return 0;
 }
