@@ -86,6 +86,24 @@ def build_oracle(force: bool = False) -> Path:
     return ORACLE_LIB
 
 
+UBENCH = LIBDIR / "ubench_atoms"
+
+
+def build_ubench(force: bool = False) -> Path:
+    """tools/ubench_atoms.cu -> _lib/ubench_atoms: the shared-memory atomic microbenchmark bench.py runs
+    for the peak of its smem_atomic roofline (a measurement tool, not part of the search path)."""
+    src = ROOT / "tools" / "ubench_atoms.cu"
+    if not force and UBENCH.exists() and UBENCH.stat().st_mtime >= src.stat().st_mtime:
+        return UBENCH
+    LIBDIR.mkdir(parents=True, exist_ok=True)
+    res = subprocess.run([_nvcc(), "-ccbin", _host_cxx(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3",
+                          "-lineinfo", "-o", str(UBENCH), str(src)], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("ubench_atoms build failed")
+    return UBENCH
+
+
 NPP_LIB = ROOT / "oracle" / "_build" / "libnmi_nppcheck.so"
 
 
@@ -131,3 +149,4 @@ if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     print(build_reference(force="--force" in sys.argv))
     print(build_nppcheck(force="--force" in sys.argv))
+    print(build_ubench(force="--force" in sys.argv))

@@ -232,11 +232,46 @@ __device__ __forceinline__ void accum_slow(Smem& sm, const uint32_t (&rw)[NW], c
 }
 
 // fast path: full chunk, every pixel counted (nmi_prop_BG == true, the reference default)
-template <int POLICY, bool SWZ, int NW>
+// SCHED (packed-u16 only; experiment knob of the persistent build, variants 11-13): how the address
+// arithmetic and the ATOMS of a thread's 16 pixels are grouped in the SOURCE -- 0: pixel by pixel
+// (ptxas interleaves as it likes), 1: all 16 addresses first, then 16 ATOMS back to back,
+// 2: two halves of 8, 3: four quarters of 4.
+template <int POLICY, bool SWZ, int NW, int SCHED = 0>
 __device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], const uint32_t (&ww)[NW],
                                            int pass, int warp) {
   constexpr int N = NW * 4;
-  if (POLICY == P_U16G) {
+  if (POLICY == P_U16G && SCHED != 0) {
+    constexpr int G = SCHED == 1 ? N : (SCHED == 2 ? N / 2 : N / 4);  // pixels per group
+    uint32_t tt[N], nw[N];
+    const uint32_t base = smem_u32(sm.hist);
+#pragma unroll
+    for (int g0 = 0; g0 < N; g0 += G) {
+      uint32_t ad[G], inc[G];
+#pragma unroll
+      for (int j = 0; j < G; j++) {
+        const int i = g0 + j;
+        const uint32_t t = __byte_perm(ww[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);
+        uint32_t addr = (t * 2u) & 0x1FFFCu;
+        if (SWZ) addr ^= __byte_perm(rw[i >> 2], 0u, 0x4440 + (i & 3)) * 4u;
+        asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc[j]) : "r"(t & 1u));
+        ad[j] = base + addr;
+        tt[i] = t;
+      }
+#pragma unroll
+      for (int j = 0; j < G; j++) {
+        uint32_t old;
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(ad[j]), "r"(inc[j]) : "memory");
+        nw[g0 + j] = old + inc[j];
+      }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) acc |= nw[i];
+    if (acc & kFlagMask) {
+#pragma unroll
+      for (int i = 0; i < N; i++) u16g_repay_if_crossed<SWZ>(sm, tt[i] & 0xFFFFu, nw[i]);
+    }
+  } else if (POLICY == P_U16G) {
     // 16 (or 8) independent ATOMS in flight; the returned words are only ORed together.
     // Integer work is split between the ALU pipe (PRMT, LOP3) and the FMA pipe (IMAD).
     uint32_t tt[N], nw[N];
@@ -835,7 +870,7 @@ joint_hist_score_kernel(const HistArgs a) {
 // histogram in front of the epilogue.  A separate instantiation, because this kernel's speed moves
 // by several per cent with its register allocation (the mere presence of the never-taken dump branch
 // cost 4.55 -> 4.72 ms at C2): the timed build contains no parity code at all.
-template <bool SWZ, bool SKIPCAP, bool DUMP = false>
+template <bool SWZ, bool SKIPCAP, bool DUMP = false, int SCHED = 0>
 __global__ void __launch_bounds__(NMI_HIST_REGCAP_THREADS, 1)
 joint_hist_score_persistent_kernel(const HistArgs a) {
   constexpr int NWARPS = 16;
@@ -906,7 +941,7 @@ joint_hist_score_persistent_kernel(const HistArgs a) {
   int kk = 0;
   for (int pi = blockIdx.x; pi < a.npairs; pi += gridDim.x) {
     const int2 pr = a.pairs[pi];
-    const bool dump = DUMP && a.dumpJ != nullptr && pi == a.dump_pair;
+    const bool dump = a.dumpJ != nullptr && pi == (DUMP ? a.dump_pair : 0);
     // hot-bin skipping: the sampled modes of this pair's two images decide (CTA-uniform)
     uint32_t skipT = 0xFFFFFFFFu;
     if (SKIPCAP && a.img_mode != nullptr && a.bg && a.skip_mode != 0) {
@@ -928,7 +963,7 @@ joint_hist_score_persistent_kernel(const HistArgs a) {
       const int nvalid = off >= npix ? 0 : (int)min((uint32_t)PIX, npix - off);
       if (nvalid == PIX && a.bg) {
         if (!skip) {
-          accum_fast<P_U16G, SWZ, NW>(sm, r, w, 0, warp);
+          accum_fast<P_U16G, SWZ, NW, SCHED>(sm, r, w, 0, warp);
         } else {
           uint32_t dr = 0, dw = 0;
 #pragma unroll
@@ -969,11 +1004,18 @@ joint_hist_score_persistent_kernel(const HistArgs a) {
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B1: every increment of this pair has landed
-    if (SWZ && !SKIPCAP && a.term_tab != nullptr) {
-      if (dump) dump_joint_swizzled(sm, a.dumpJ, tid);  // CTA-uniform; the epilogue below is the timed one
-      rows_epilogue_fast<true>(sm, L, a, warp, lane);
-    } else {
-      rows_epilogue<P_U16G, SWZ, NWARPS, true>(sm, 0, L, a, dump, warp, lane, SKIPCAP ? &sk : nullptr, skipT);
+    if constexpr (DUMP) {
+      if (SWZ && !SKIPCAP && a.term_tab != nullptr) {
+        if (dump) dump_joint_swizzled(sm, a.dumpJ, tid);  // CTA-uniform; the epilogue below is the timed one
+        rows_epilogue_fast<true>(sm, L, a, warp, lane);
+      } else {
+        rows_epilogue<P_U16G, SWZ, NWARPS, true>(sm, 0, L, a, dump, warp, lane, SKIPCAP ? &sk : nullptr, skipT);
+      }
+    } else {  // the timed build: kept statement for statement as measured in round 1 (see DUMP above)
+      if (SWZ && !SKIPCAP && !dump && a.term_tab != nullptr)
+        rows_epilogue_fast<true>(sm, L, a, warp, lane);
+      else
+        rows_epilogue<P_U16G, SWZ, NWARPS, true>(sm, 0, L, a, dump, warp, lane, SKIPCAP ? &sk : nullptr, skipT);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // B2: rows read and cleared, marginals complete
     if (warp < 3) {
@@ -1282,9 +1324,9 @@ int launch_t(const HistArgs& a, cudaStream_t st) {
   return 1;
 }
 
-template <bool SWZ, bool SKIPCAP, bool DUMP = false>
+template <bool SWZ, bool SKIPCAP, bool DUMP = false, int SCHED = 0>
 int launch_persistent(const HistArgs& a, cudaStream_t st) {
-  auto kern = joint_hist_score_persistent_kernel<SWZ, SKIPCAP, DUMP>;
+  auto kern = joint_hist_score_persistent_kernel<SWZ, SKIPCAP, DUMP, SCHED>;
   constexpr size_t smem = sizeof(Smem) + (SKIPCAP ? sizeof(SmemSkip) : 0);
   static int sms[64] = {0};  // per device: one CTA per SM (the histogram takes most of an SM's shared memory)
   int dev = 0;
@@ -1362,6 +1404,9 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
       return a.term_tab != nullptr ? launch_t<P_U16G, true, 16, true, false, true>(a, st)
                                    : launch_t<P_U16G, true, 16, true>(a, st);
     case 10: return launch_tmem(a, st);  // variant 0 with the pixel ring staged through tensor memory
+    case 11: return launch_persistent<true, false, false, 1>(a, st);  // variant 0, source-level ATOMS grouping 16
+    case 12: return launch_persistent<true, false, false, 2>(a, st);  // ... 2 x 8
+    case 13: return launch_persistent<true, false, false, 3>(a, st);  // ... 4 x 4
     default:  // variant 0: TMA ring, bank swizzle, persistent CTAs with the fast epilogue
       return a.dumpJ != nullptr ? launch_persistent<true, false, true>(a, st) : launch_persistent<true, false>(a, st);
   }

@@ -63,11 +63,12 @@ struct HistArgs {
   int nrenders;
   int skip_mode;
   bool skipcap;
-  // optional dumps (parity): when non-null, pair `dump_pair` of the launch writes them
-  int dump_pair;
+  // optional dumps (parity): when non-null, pair 0 of the launch writes them (the DUMP build of the
+  // persistent kernel: pair `dump_pair`)
   uint32_t* dumpJ;
   uint32_t* dumpHA;
   uint32_t* dumpHB;
+  int dump_pair;
 };
 int launch_joint_hist_score(const HistArgs& a, cudaStream_t st);  // returns launches, <0 on error
 // sampled per-image modes for HistArgs::img_mode; hot[0] / hot[1] = largest sampled count over

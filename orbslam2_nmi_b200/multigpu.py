@@ -61,12 +61,21 @@ def sharded_search(searcher, Twc, grid: Grid, flags: Flags, key_tensor, rank: in
     same stream (no host sync in between). Returns the decoded global winner."""
     import torch
 
-    ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
-    with ctx:
-        searcher.search_enqueue(Twc, grid, flags, rank, world, key_tensor.data_ptr())
-        allreduce_key(key_tensor)
-    (stream or torch.cuda.current_stream()).synchronize()
-    return searcher.decode(grid, int(key_tensor.item()))
+    from . import capi
+
+    for attempt in range(2):
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+        with ctx:
+            searcher.search_enqueue(Twc, grid, flags, rank, world, key_tensor.data_ptr())
+            allreduce_key(key_tensor)
+        (stream or torch.cuda.current_stream()).synchronize()
+        # nmi_read_key also notices a LOCAL bin overflow and arms the exact sizing for the retry
+        key = searcher.read_key(key_tensor.data_ptr())
+        if key != capi.NMI_KEY_RETRY:
+            return searcher.decode(grid, key)
+        # some rank's fixed-capacity splat bins filled up: every rank sees the same RETRY key and
+        # redoes the level once, like csrc/driver.cpp sharded_level
+    raise capi.NmiError(capi.NMI_ERR_RETRY, "splat record bins overflowed twice")
 
 
 def relocalize_sharded(searcher, Twc, grid: Grid, flags: Flags | None, key_tensor, rank: int, world: int,

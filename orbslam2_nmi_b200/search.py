@@ -115,10 +115,21 @@ class NmiSearcher:
         """Hot-bin skipping of the histogram kernel: 0 never, 1 automatic, 2 always."""
         check(self.lib.nmi_ctx_set_hist_skip(self.h, int(mode)))
 
-    def decode(self, grid: Grid, key: int) -> SearchResult:
+    def decode(self, grid: Grid, key: int, strict: bool = True) -> SearchResult:
+        """nmi_decode_key.  strict: NMI_ERR_RETRY (a rank's splat bins overflowed: the key carries no
+        winner, the level must be redone) raises NmiError instead of returning best_index -1."""
         r = Result()
-        self.lib.nmi_decode_key(C.byref(grid), C.c_uint64(key), C.byref(r))
+        code = self.lib.nmi_decode_key(C.byref(grid), C.c_uint64(key), C.byref(r))
+        if strict and code == capi.NMI_ERR_RETRY:
+            raise capi.NmiError(code, "reduced key is NMI_KEY_RETRY: a rank's record bins overflowed, redo the search")
         return _result(r)
+
+    def read_key(self, key_dev: int) -> int:
+        """nmi_read_key: stream-synchronise and fetch the (reduced) key; a local bin overflow arms the
+        exact two-pass sizing for this context's next search."""
+        k = C.c_uint64(0)
+        check(self.lib.nmi_read_key(self.h, key_dev, C.byref(k)))
+        return int(k.value)
 
     def relocalize(self, Twc, grid: Grid, flags: Flags | None = None, threshold=0.1, max_iterations=4,
                    dist=(0.0, 0.0, 0.0), rot=(0.0, 0.0, 0.0)):
