@@ -356,12 +356,14 @@ def config_c3(local):
 
     c = synth.CONFIGS["C3"]
     verts, tris = synth.make_mesh(1000, 1000)
+    uv = synth.make_mesh_uv(verts, tris, repeats=6.0)
+    tex = synth.make_texture(1024, 1024)
     frame = synth.frame_textured(c["W"], c["H"])
     Twc = synth.prior_pose()
     s = NmiSearcher(local)
     try:
         s.set_camera(c["W"], c["H"], c["fx"], c["fy"], c["cx"], c["cy"], synth.ZN, synth.ZF, 3.0)
-        s.set_mesh(verts, tris)
+        s.set_mesh_textured(verts, tris, uv, tex)  # Rendering<1>: per-fragment texture shading
         s.set_frame(frame)
         g = Grid.make((4, 4, 4), (4, 4, 1), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
         fl = s.flags(bins=64)
@@ -373,10 +375,10 @@ def config_c3(local):
         gs = Grid.make((2, 1, 1), (2, 2, 1), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
         got = s.search(Twc, gs, fl, want_scores=True)
         sc = synth.Scene(c["W"], c["H"], c["fx"], c["fy"], c["cx"], c["cy"], synth.ZN, synth.ZF, 3.0, None, Twc)
-        want, renders, _ = oracle.search_mesh(sc, Twc, gs, verts, tris, frame, bins=64, keep_images=True)
+        want, renders, _ = oracle.search_mesh_tex(sc, Twc, gs, verts, tris, uv, tex, frame, bins=64, keep_images=True)
         same_render = bool(np.array_equal(s.get_render(0), renders[0]))
         med = float(np.median(ms))
-        return {"workload": "C3 Newer-College-shaped: 848x480 frame vs 2M-triangle mesh, 4^3 x (4x4x1) = 1024 poses, 64 bins",
+        return {"workload": "C3 Newer-College-shaped: 848x480 frame vs 2M-triangle mesh with a 1024^2 texture shaded per fragment, 4^3 x (4x4x1) = 1024 poses, 64 bins",
                 "search_ms": med, "evals_per_s": g.n_pose / med * 1e3, "stage_ms": st,
                 "parity": {"checker": "oracle on a 8-pose sub-grid at full size", "renders_bit_exact": same_render,
                            "scores_bit_identical": bool(np.array_equal(got.scores.view(np.uint32), want.view(np.uint32))),

@@ -23,7 +23,11 @@ class NmiObjects {
   NmiSearchKernel* LastNmiKernel;
   NmiSearchKernel* InitialNmiKernel;
 
-  explicit NmiObjects(const std::string& strSettingsFile);
+  // localization.cpp:82.  The renderer's mode is the compile-time nmi_prop_RENDER of the code that
+  // includes this header (allProperties.hpp:42: 1 = textured OBJ mesh, 4 = .xyz cloud); the library
+  // carries both renderers and builds the one named here.
+  explicit NmiObjects(const std::string& strSettingsFile) : NmiObjects(strSettingsFile, nmi_prop_RENDER) {}
+  NmiObjects(const std::string& strSettingsFile, int render_mode);
   ~NmiObjects();
 
   void setNmiObjectsKernel(int numsynthx, int numsynthy, int numsynthz, int numwarpx, int numwarpy,

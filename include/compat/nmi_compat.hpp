@@ -71,5 +71,10 @@ bool loadBMP24(const char* path, int& width, int& height, std::vector<unsigned c
 // flat per-triangle shading from the first vertex is this build's documented deviation.
 bool meshFromObjBmp(const char* obj_path, const char* bmp_path, std::vector<float>& verts_xyzg,
                     std::vector<uint32_t>& tris);
+// The same plus what per-fragment shading needs (nmi_set_mesh_textured): the UV of every face corner
+// (un-indexed, objloader.cpp:206-220) and the BMP payload exactly as loadBMP_custom uploads it.
+bool meshFromObjBmp(const char* obj_path, const char* bmp_path, std::vector<float>& verts_xyzg,
+                    std::vector<uint32_t>& tris, std::vector<float>* corner_uv, std::vector<unsigned char>* texture,
+                    int* tex_w, int* tex_h);
 
 }  // namespace nmi_compat

@@ -69,13 +69,18 @@ class Rendering {
       }
     } else if (!object_path.empty()) {
       // RENDER_TEXTURE (rendering.hpp:172-178, 219-229): OBJ + 24-bpp BMP
-      std::vector<float> verts;
+      // per-fragment texture shading like ShadingWithTexture.fragmentshader (nmi_set_mesh_textured)
+      std::vector<float> verts, uv;
       std::vector<uint32_t> tris;
-      if (!nmi_compat::meshFromObjBmp(object_path.c_str(), texture_path.c_str(), verts, tris)) {
+      std::vector<unsigned char> tex;
+      int tw = 0, th = 0;
+      if (!nmi_compat::meshFromObjBmp(object_path.c_str(), texture_path.c_str(), verts, tris, &uv, &tex, &tw, &th)) {
         std::fprintf(stderr, "Rendering: cannot load %s / %s\n", object_path.c_str(), texture_path.c_str());
         std::exit(EXIT_FAILURE);
       }
-      setMesh(verts.data(), verts.size() / 4, tris.data(), tris.size() / 3);
+      nmi_compat::check(nmi_set_mesh_textured(nmi_compat::context(), verts.data(), verts.size() / 4, tris.data(),
+                                              tris.size() / 3, uv.data(), tex.data(), tw, th),
+                        "Rendering: textured mesh");
     }
   }
 

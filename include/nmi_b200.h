@@ -118,6 +118,18 @@ int nmi_set_points_device(nmi_ctx *ctx, const void *xyzi_dev, size_t n);
  * Setting a mesh replaces a point cloud and vice versa.                        */
 int nmi_set_mesh(nmi_ctx *ctx, const float *verts_host, size_t nv,
                  const uint32_t *tris_host, size_t nt);
+/* Rendering<1> as the reference runs it (rendering.hpp:176-189: loadOBJ + loadBMP_custom, draw at
+ * :588-620): the mesh with per-fragment texture shading.  corner_uv: 6 floats per triangle, (u, v)
+ * of its corners 0, 1, 2 -- un-indexed, the layout loadOBJ's out_uvs has (objloader.cpp:206-220).
+ * texture: tex_h rows of tex_w texels, 3 bytes each, in the FILE's byte order and row order
+ * (loadBMP_custom hands the BMP payload to glTexImage2D(GL_RGB) untouched, texture.cpp:90: the
+ * file's B,G,R land in the shader's r,g,b; row 0 = v 0).  Per fragment: perspective-correct UV,
+ * GL_REPEAT, level-0 bilinear fetch of 0.299 r + 0.587 g + 0.114 b
+ * (ShadingWithTexture.fragmentshader:16).  The reference's minification filter is trilinear over a
+ * driver-built mip chain -- not reproducible, level 0 is used at every scale.    */
+int nmi_set_mesh_textured(nmi_ctx *ctx, const float *verts, size_t nv, const uint32_t *tris,
+                          size_t nt, const float *corner_uv, const uint8_t *texture, int tex_w,
+                          int tex_h);
 /* Image::loadOriginal (image.cpp:130-135): H2D upload of the grey frame.     */
 int nmi_set_frame(nmi_ctx *ctx, const uint8_t *gray_host, int W, int H);
 int nmi_set_frame_device(nmi_ctx *ctx, const void *gray_dev, int W, int H);

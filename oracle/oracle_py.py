@@ -151,6 +151,50 @@ def render_mesh(cam, Twc, t, verts, tris):
     return win, img
 
 
+def render_mesh_tex(cam, Twc, t, verts, tris, corner_uv, tex):
+    """Rendering<1> with the texture: corner_uv (nt, 3, 2) float32, tex (th, tw, 3) u8 in file byte order."""
+    W, H = cam.W, cam.H
+    win = np.empty((H, W), dtype=np.uint32)
+    img = np.empty((H, W), dtype=np.uint8)
+    T = _twc(Twc)
+    t = np.ascontiguousarray(t, dtype=np.float32)
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    tris = np.ascontiguousarray(tris, dtype=np.uint32)
+    uv = np.ascontiguousarray(corner_uv, dtype=np.float32)
+    tex = np.ascontiguousarray(tex, dtype=np.uint8)
+    lib = load()
+    lib.orc_render_mesh_tex.argtypes = [C.POINTER(OrcCamera), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]
+    lib.orc_render_mesh_tex(C.byref(camera(cam)), _p(T), _p(t), _p(verts), verts.shape[0], _p(tris), tris.shape[0],
+                            _p(uv), _p(tex), tex.shape[1], tex.shape[0], _p(win), _p(img))
+    return win, img
+
+
+def search_mesh_tex(cam, Twc, g, verts, tris, corner_uv, tex, frame, bins=256, bg=True, mode=SUC,
+                    keep_images=False, threads=0):
+    og = grid(g)
+    nS = g.nS[0] * g.nS[1] * g.nS[2]
+    nW = g.nW[0] * g.nW[1] * g.nW[2]
+    scores = np.zeros(nS * nW, dtype=np.float32)
+    renders = np.empty((nS, cam.H, cam.W), dtype=np.uint8) if keep_images else None
+    warps = np.empty((nW, cam.H, cam.W), dtype=np.uint8) if keep_images else None
+    T = _twc(Twc)
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    tris = np.ascontiguousarray(tris, dtype=np.uint32)
+    uv = np.ascontiguousarray(corner_uv, dtype=np.float32)
+    tex = np.ascontiguousarray(tex, dtype=np.uint8)
+    frame = np.ascontiguousarray(frame, dtype=np.uint8)
+    lib = load()
+    lib.orc_search_mesh_tex.argtypes = [C.POINTER(OrcCamera), C.c_void_p, C.POINTER(OrcGrid), C.c_void_p, C.c_size_t,
+                                        C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.orc_search_mesh_tex(C.byref(camera(cam)), _p(T), C.byref(og), _p(verts), verts.shape[0], _p(tris),
+                            tris.shape[0], _p(uv), _p(tex), tex.shape[1], tex.shape[0], _p(frame), bins, int(bg), mode,
+                            _p(scores), _p(renders), _p(warps), threads)
+    return scores, renders, warps
+
+
 def search_mesh(cam, Twc, g, verts, tris, frame, bins=256, bg=True, mode=SUC, keep_images=False, threads=0):
     og = grid(g)
     nS = g.nS[0] * g.nS[1] * g.nS[2]

@@ -110,6 +110,7 @@ SYMBOLS = [
     ("nmi_set_points", C.c_int, [_P, _P, C.c_size_t]),
     ("nmi_set_points_device", C.c_int, [_P, _P, C.c_size_t]),
     ("nmi_set_mesh", C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t]),
+    ("nmi_set_mesh_textured", C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, _P, _P, C.c_int, C.c_int]),
     ("nmi_set_frame", C.c_int, [_P, _P, C.c_int, C.c_int]),
     ("nmi_set_frame_device", C.c_int, [_P, _P, C.c_int, C.c_int]),
     ("nmi_search", C.c_int, [_P, _P, C.POINTER(Grid), C.POINTER(Flags), C.POINTER(Result), _P]),

@@ -47,6 +47,10 @@ void launch_mesh_cull(const float4* verts, const uint3* tris, uint32_t nt, const
 void launch_mesh_raster(const float4* verts, const uint3* tris, const uint32_t* tri_orig,
                         const uint32_t* slots, const uint32_t* counter, const float4* centres, int nviews,
                         const ViewConst& vc, unsigned long long* zbuf, size_t P, cudaStream_t st);
+void launch_mesh_luma(const uint8_t* tex, float* luma, size_t n, cudaStream_t st);
+void launch_mesh_shade(unsigned long long* zbuf, const float4* verts, const uint3* tris_orig, const float* corner_uv,
+                       const float* luma, int tw, int th, const float4* centres, int nviews, const ViewConst& vc,
+                       size_t P, uint8_t* images, size_t pitch, uint32_t* winners, cudaStream_t st);
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -146,6 +150,11 @@ struct nmi_ctx {
   DevBuf<uint3> mtris;
   DevBuf<uint32_t> mtri_orig, mslots;
   size_t n_tris = 0;  // > 0: the model is a mesh, else a point cloud
+  // textured mesh (Rendering<1> as the reference runs it): triangles in ORIGINAL order (what the
+  // z-buffer key names), un-indexed corner UVs, the texture's luma in 0..255 units
+  DevBuf<uint3> mtris_o;
+  DevBuf<float> muv, mluma;
+  int tex_w = 0, tex_h = 0;  // > 0: per-fragment texture shading
 
   // feedback from the previous search, copied to pinned host memory asynchronously:
   // [0] survivors, [1] records of the last view group, [2] overflow flag, [3] fullest bin,
@@ -449,8 +458,12 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
     launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->zbuf.p, c->P,
                          (uint32_t)c->n_pts, c->stream);
   }
-  launch_resolve(c->zbuf.p, c->val.p, nviews, c->P, images, c->pitch, winners, c->packed_value,
-                 c->stream);
+  if (c->n_tris && c->tex_w > 0)
+    launch_mesh_shade(c->zbuf.p, c->mverts.p, c->mtris_o.p, c->muv.p, c->mluma.p, c->tex_w, c->tex_h, d_centres, nviews, vc,
+                      c->P, images, c->pitch, winners, c->stream);
+  else
+    launch_resolve(c->zbuf.p, c->val.p, nviews, c->P, images, c->pitch, winners, c->packed_value,
+                   c->stream);
   c->launches += 2;
   CK(cudaGetLastError());
   return NMI_OK;
@@ -724,7 +737,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->pts.release(); c->aabb.release(); c->orig.release(); c->tag.release(); c->val.release(); c->mverts.release(); c->mtris.release();
-  c->mtri_orig.release(); c->mslots.release(); c->bin_offsets.release(); c->bin_cursor.release();
+  c->mtri_orig.release(); c->mslots.release(); c->mtris_o.release(); c->muv.release(); c->mluma.release(); c->bin_offsets.release(); c->bin_cursor.release();
   c->bin_total.release(); c->records.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
@@ -934,7 +947,31 @@ int nmi_set_mesh(nmi_ctx* c, const float* verts, size_t nv, const uint32_t* tris
   c->n_tris = nt;
   c->packed_value = false;  // mesh keys carry the plain triangle index
   c->n_pts = 0;
+  c->tex_w = c->tex_h = 0;  // flat grey of the first vertex until nmi_set_mesh_textured says otherwise
   c->has_search = false;
+  return NMI_OK;
+}
+
+int nmi_set_mesh_textured(nmi_ctx* c, const float* verts, size_t nv, const uint32_t* tris, size_t nt,
+                          const float* corner_uv, const uint8_t* texture, int tex_w, int tex_h) {
+  REQUIRE(c && corner_uv && texture && tex_w > 0 && tex_h > 0 && (size_t)tex_w * tex_h < (1ull << 31), NMI_ERR_INVALID,
+          "bad texture / UVs");
+  if (int rc = nmi_set_mesh(c, verts, nv, tris, nt)) return rc;
+  const size_t ntex = (size_t)tex_w * tex_h;
+  CK(c->mtris_o.reserve(nt));
+  CK(c->muv.reserve(6 * nt));
+  CK(c->mluma.reserve(ntex));
+  DevBuf<uint8_t> raw;
+  CK(raw.reserve(3 * ntex));
+  CK(cudaMemcpyAsync(c->mtris_o.p, tris, nt * sizeof(uint3), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->muv.p, corner_uv, 6 * nt * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(raw.p, texture, 3 * ntex, cudaMemcpyHostToDevice, c->stream));
+  launch_mesh_luma(raw.p, c->mluma.p, ntex, c->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  raw.release();
+  c->tex_w = tex_w;
+  c->tex_h = tex_h;
   return NMI_OK;
 }
 

@@ -228,8 +228,14 @@ bool loadBMP24(const char* path, int& width, int& height, std::vector<unsigned c
   return (size_t)f.gcount() >= (size_t)width * height * 3;
 }
 
+// OBJ + BMP -> the arguments of nmi_set_mesh_textured: un-indexed corners like the reference's VBOs
+// (objloader.cpp:206-220: one position and one UV per face corner), the BMP payload untouched
+// (texture.cpp:90 hands it to glTexImage2D(GL_RGB) as it lies in the file: B,G,R, bottom row first;
+// tightly packed rows, GL_UNPACK_ALIGNMENT 1, rendering.hpp:313).  verts[4i+3] additionally carries
+// the luma of the corner's nearest texel -- only used by the flat-shaded fallback nmi_set_mesh.
 bool meshFromObjBmp(const char* obj_path, const char* bmp_path, std::vector<float>& verts,
-                    std::vector<uint32_t>& tris) {
+                    std::vector<uint32_t>& tris, std::vector<float>* corner_uv, std::vector<unsigned char>* texture,
+                    int* tex_w, int* tex_h) {
   std::vector<float> xyz, uv;
   std::vector<unsigned char> tex;
   int tw = 0, th = 0;
@@ -238,8 +244,6 @@ bool meshFromObjBmp(const char* obj_path, const char* bmp_path, std::vector<floa
   verts.resize(4 * nv);
   tris.resize(nv);
   for (size_t i = 0; i < nv; i++) {
-    // GL_REPEAT + nearest texel of level 0; the reference uploads tightly packed rows
-    // (GL_UNPACK_ALIGNMENT 1, rendering.hpp:313), i.e. stride = 3 * width
     const float u = uv[2 * i] - std::floor(uv[2 * i]), v = uv[2 * i + 1] - std::floor(uv[2 * i + 1]);
     int tx = (int)std::floor(u * tw), ty = (int)std::floor(v * th);
     tx = tx < 0 ? 0 : (tx >= tw ? tw - 1 : tx);
@@ -252,7 +256,19 @@ bool meshFromObjBmp(const char* obj_path, const char* bmp_path, std::vector<floa
     verts[4 * i + 3] = 0.299f * r + 0.587f * g + 0.114f * b;
     tris[i] = (uint32_t)i;
   }
+  if (corner_uv) *corner_uv = uv;  // 2 floats per corner, 3 corners per triangle, in face order
+  if (texture) {
+    tex.resize((size_t)tw * th * 3);
+    *texture = tex;
+  }
+  if (tex_w) *tex_w = tw;
+  if (tex_h) *tex_h = th;
   return nv >= 3 && nv % 3 == 0;
+}
+
+bool meshFromObjBmp(const char* obj_path, const char* bmp_path, std::vector<float>& verts,
+                    std::vector<uint32_t>& tris) {
+  return meshFromObjBmp(obj_path, bmp_path, verts, tris, nullptr, nullptr, nullptr, nullptr);
 }
 
 }  // namespace nmi_compat
@@ -294,7 +310,7 @@ static std::string make_results_dir(std::string* log_path) {
   return dir.string();
 }
 
-NmiObjects::NmiObjects(const std::string& strSettingsFile) : rating(nullptr), N(0) {
+NmiObjects::NmiObjects(const std::string& strSettingsFile, int render_mode) : rating(nullptr), N(0) {
   std::stringstream ss_log;
   resultsPath = make_results_dir(&logPath);
   ss_log << resultsPath << std::endl << "logPath: " << logPath << std::endl;
@@ -320,11 +336,17 @@ NmiObjects::NmiObjects(const std::string& strSettingsFile) : rating(nullptr), N(
   threshold_ = (float)y.num("NMI.Treshold");
 
   // localization.cpp:133-158 (1280x720 is the hidden GL window of the reference)
-  myRenderer = new Rendering<nmi_prop_RENDER>(
-      (float)y.num("NMI.Render.PointSize", 3.0), 1280, 720, W, H, nsx, nsy, nsz, sx, sy, sz, zero, zero, zero,
-      y.num("NMI.Render.NearPlane", 5.0), y.num("NMI.Render.FarPlane", 30.0), fx, fy, cx, cy,
-      y.str("NMI.Render.Object"), y.str("NMI.Render.Texture"), y.str("NMI.Render.Cloud"),
-      y.str("NMI.Render.Offset"), logPath);
+  // nmi_prop_RENDER is the CALLER's compile-time choice (allProperties.hpp:42, handed over by the inline
+  // constructor in localization.hpp); Rendering<1> and Rendering<4> differ only in which loader their
+  // constructor runs (rendering.hpp:172-189), their layout is the same
+#define NMI_NEW_RENDERER(MODE)                                                                                    \
+  reinterpret_cast<Rendering<nmi_prop_RENDER>*>(new Rendering<MODE>(                                              \
+      (float)y.num("NMI.Render.PointSize", 3.0), 1280, 720, W, H, nsx, nsy, nsz, sx, sy, sz, zero, zero, zero,     \
+      y.num("NMI.Render.NearPlane", 5.0), y.num("NMI.Render.FarPlane", 30.0), fx, fy, cx, cy,                      \
+      y.str("NMI.Render.Object"), y.str("NMI.Render.Texture"), y.str("NMI.Render.Cloud"),                          \
+      y.str("NMI.Render.Offset"), logPath))
+  myRenderer = render_mode == RENDER_TEXTURE ? NMI_NEW_RENDERER(RENDER_TEXTURE) : NMI_NEW_RENDERER(RENDER_POINT_CLOUD);
+#undef NMI_NEW_RENDERER
 
   cv::Mat K = cv::Mat::eye(3, 3, CV_64F);  // localization.cpp:165-169
   K.at<double>(0, 0) = fx;

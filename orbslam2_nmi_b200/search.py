@@ -76,6 +76,16 @@ class NmiSearcher:
         assert verts.ndim == 2 and verts.shape[1] == 4 and tris.ndim == 2 and tris.shape[1] == 3
         check(self.lib.nmi_set_mesh(self.h, ptr(verts), verts.shape[0], ptr(tris), tris.shape[0]))
 
+    def set_mesh_textured(self, verts: np.ndarray, tris: np.ndarray, corner_uv: np.ndarray, texture: np.ndarray):
+        """Rendering<1> with its texture: corner_uv (nt, 3, 2) float32, texture (th, tw, 3) u8 in file byte order."""
+        verts = np.ascontiguousarray(verts, dtype=np.float32)
+        tris = np.ascontiguousarray(tris, dtype=np.uint32)
+        uv = np.ascontiguousarray(corner_uv, dtype=np.float32)
+        tex = np.ascontiguousarray(texture, dtype=np.uint8)
+        assert uv.size == 6 * tris.shape[0] and tex.ndim == 3 and tex.shape[2] == 3
+        check(self.lib.nmi_set_mesh_textured(self.h, ptr(verts), verts.shape[0], ptr(tris), tris.shape[0], ptr(uv),
+                                             ptr(tex), tex.shape[1], tex.shape[0]))
+
     def set_frame(self, gray: np.ndarray):
         gray = np.ascontiguousarray(gray, dtype=np.uint8)
         check(self.lib.nmi_set_frame(self.h, ptr(gray), gray.shape[1], gray.shape[0]))

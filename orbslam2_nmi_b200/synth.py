@@ -83,6 +83,28 @@ def make_mesh(nx: int = 1000, ny: int = 1000, seed: int = 1234, extent: float = 
     return verts, tris
 
 
+def make_mesh_uv(verts: np.ndarray, tris: np.ndarray, extent: float = 40.0, repeats: float = 3.0) -> np.ndarray:
+    """Corner UVs (nt, 3, 2) for make_mesh's terrain, un-indexed like loadOBJ's out_uvs
+    (objloader.cpp:206-220): the texture is laid over the terrain `repeats` times per axis, so the
+    UVs leave [0, 1] and GL_REPEAT (texture.cpp:100-101) is exercised."""
+    xy = verts[:, :2].astype(np.float64)
+    uv = (xy + extent) / (2.0 * extent) * repeats - 0.25
+    return uv[tris.astype(np.int64)].astype(np.float32)
+
+
+def make_texture(tw: int = 512, th: int = 512, seed: int = 77) -> np.ndarray:
+    """(th, tw, 3) u8 texture in BMP payload order (row 0 = bottom row, bytes B, G, R): smooth colour
+    fields + texel noise, the three channels different so that the channel swap of
+    loadBMP_custom (texture.cpp:90) matters."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:th, 0:tw].astype(np.float64)
+    c0 = 128 + 90 * np.sin(xx / 23.0) * np.cos(yy / 31.0)
+    c1 = 128 + 80 * np.cos((xx + 2 * yy) / 47.0)
+    c2 = 128 + 100 * np.sin((xx - yy) / 19.0)
+    t = np.stack([c0, c1, c2], axis=-1) + 10.0 * rng.standard_normal((th, tw, 3))
+    return np.clip(np.rint(t), 0, 255).astype(np.uint8)
+
+
 def prior_pose(height_above: float = 15.0, tilt_deg: float = 10.0) -> np.ndarray:
     """Camera `height_above` m over the terrain (world z up), looking down, tilted about x."""
     # CV camera: x right, y down, z forward.  Looking straight down: z_cam = -z_world.

@@ -220,3 +220,89 @@ def test_nmi_cuh_secondary_exports(tmp_path, oracle):
     got = [float(v) for v in res.stdout.split("SCORE")[1].split()[:2]]
     assert got[0] == got[1]
     assert abs(got[0] - want) <= 1e-5 * abs(want)
+
+
+# ---- Rendering<1>: the reference's default render mode (allProperties.hpp:42), OBJ + BMP -> GPU ----
+@pytest.fixture(scope="module")
+def exe_mesh(tmp_path_factory):
+    """The same drop-in program compiled the way a RENDER_TEXTURE build of the reference compiles it:
+    -Dnmi_prop_RENDER=1 -> NmiObjects::myRenderer is a Rendering<1> (loadOBJ + loadBMP_custom)."""
+    lib = build.build_cuda()
+    out = tmp_path_factory.mktemp("bin") / "test_compat_mesh"
+    cmd = ["/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++", "-std=c++17", "-O1", "-Dnmi_prop_RENDER=1",
+           "-ffp-contract=off", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cpp" / "test_compat.cpp"),
+           "-L", str(lib.parent), "-lnmi_b200", f"-Wl,-rpath,{lib.parent}", "-o", str(out)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return out
+
+
+def _write_obj_bmp(d, verts, tris, uv, tex):
+    """OBJ in the one dialect loadOBJ reads (v / vt / f a/b c/d e/f, 1-based, objloader.cpp:167-196) and
+    a 24-bit BMP whose payload is `tex` as it lies (rows bottom-up, B,G,R)."""
+    import struct
+
+    lines = ["# synthetic terrain"]
+    lines += ["v %.9g %.9g %.9g" % tuple(v[:3]) for v in verts]
+    flat_uv = uv.reshape(-1, 2)
+    lines += ["vt %.9g %.9g" % tuple(t) for t in flat_uv]
+    for i, t in enumerate(tris):
+        lines.append("f %d/%d %d/%d %d/%d" % (t[0] + 1, 3 * i + 1, t[1] + 1, 3 * i + 2, t[2] + 1, 3 * i + 3))
+    (d / "mesh.obj").write_text("\n".join(lines) + "\n")
+    th, tw, _ = tex.shape
+    payload = tex.tobytes()  # width * 3 is a multiple of 4 here: no row padding
+    assert (tw * 3) % 4 == 0
+    hdr = b"BM" + struct.pack("<IHHI", 54 + len(payload), 0, 0, 54) + struct.pack(
+        "<IiiHHIIiiII", 40, tw, th, 1, 24, 0, len(payload), 2835, 2835, 0, 0)
+    (d / "tex.bmp").write_bytes(hdr + payload)
+
+
+@pytest.fixture(scope="module")
+def workdir_mesh(tmp_path_factory):
+    d = tmp_path_factory.mktemp("compat_mesh")
+    sc = synth.make_scene("tiny", n_points=10)
+    verts, tris = synth.make_mesh(40, 40, extent=24.0)
+    uv = synth.make_mesh_uv(verts, tris, extent=24.0, repeats=2.0)
+    tex = synth.make_texture(64, 48)
+    _write_obj_bmp(d, verts, tris, uv, tex)
+    (d / "settings.yaml").write_text(YAML.format(fx=sc.fx, fy=sc.fy, cx=sc.cx, cy=sc.cy, W=sc.W, H=sc.H,
+                                                 cloud="unused.xyz", offset="unused.xyz")
+                                     .replace('"unused.obj"', '"%s"' % (d / "mesh.obj"))
+                                     .replace('"unused.bmp"', '"%s"' % (d / "tex.bmp")))
+    frame = synth.frame_textured(sc.W, sc.H, seed=21)
+    frame.tofile(d / "frame.raw")
+    np.savetxt(d / "twc.txt", sc.Twc.reshape(1, 16), fmt="%.9g")
+    return d, sc, frame, verts, tris, uv, tex
+
+
+def test_compat_mesh_build_compiles(exe_mesh):
+    assert exe_mesh.exists()
+
+
+@pytest.mark.gpu
+def test_compat_textured_mesh_on_gpu(exe_mesh, workdir_mesh, oracle):
+    """OBJ + BMP files -> Rendering<1> -> nmi_set_mesh_textured -> the reference's loop and the batched
+    search, against the oracle's textured renderer fed with what the loaders produce."""
+    import os
+
+    d, sc, frame, verts, tris, uv, tex = workdir_mesh
+    res = subprocess.run([str(exe_mesh), "gpu", str(d / "settings.yaml"), str(d / "frame.raw"), str(d / "twc.txt")],
+                         capture_output=True, text=True, cwd=d, timeout=600,
+                         env=dict(os.environ, NMI_OUTPUT_LOC=str(d / "results")))
+    assert res.returncode == 0 and "GPU OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+    out = {l.split(" ", 1)[0]: l.split()[1:] for l in res.stdout.splitlines() if l and l.split()[0].isupper()}
+    g = Grid.make((2, 1, 2), (1, 2, 1), (0.2, 0.2, 0.5), (0.02, 0.03, 0.05))
+    # what loadOBJ builds: one vertex per face corner (objloader.cpp:206-220), parsed from "%.9g" text
+    corners = np.array([[float("%.9g" % c) for c in verts[k, :3]] for k in tris.reshape(-1)], np.float32)
+    v4 = np.concatenate([corners, np.zeros((corners.shape[0], 1), np.float32)], axis=1)
+    t3 = np.arange(corners.shape[0], dtype=np.uint32).reshape(-1, 3)
+    uvp = np.array([[float("%.9g" % c) for c in t] for t in uv.reshape(-1, 2)], np.float32).reshape(-1, 3, 2)
+    scores, renders, _ = oracle.search_mesh_tex(sc, sc.Twc, g, v4, t3, uvp, tex, frame, keep_images=True)
+    assert (renders[0] != 255).mean() > 0.9
+    batch = np.array(out["BATCH"], dtype=np.float64)
+    loop = np.array(out["LOOP"], dtype=np.float64)
+    assert np.allclose(batch, scores, rtol=1e-5, atol=0)
+    assert np.allclose(loop, scores, rtol=5e-3, atol=0)  # per-call path: Twc rebuilt from (pos, dir, up)
+    want, _ = oracle.argmax(scores)
+    s, w = oracle.unravel(g, want)
+    assert [int(v) for v in out["BATCHBEST"][:6]] == list(s) + list(w)

@@ -524,6 +524,53 @@ def test_mesh_search_matches_oracle(searcher, oracle, bins):
     assert_scores_close(r2.scores, s2)
 
 
+@pytest.mark.parametrize("bins,height", [(256, 15.0), (64, 15.0), (256, 5.6)])
+def test_textured_mesh_search_matches_oracle(searcher, oracle, bins, height):
+    """Rendering<1> as the reference runs it (nmi_set_mesh_textured): per-fragment perspective-correct
+    UV, GL_REPEAT, level-0 bilinear luma of a B,G,R texture (ShadingWithTexture.fragmentshader:16,
+    texture.cpp:90-104) -- z-buffer winners and renders bit-exact, scores within 1e-5, same winner.
+    height 5.6 m puts part of the terrain before the near plane (zn = 5 m): triangles are clipped per
+    fragment like GL clips them, instead of dropped whole."""
+    sc = synth.make_scene("small", n_points=10)
+    verts, tris = synth.make_mesh(170, 170, extent=24.0)
+    uv = synth.make_mesh_uv(verts, tris, extent=24.0, repeats=3.0)
+    tex = synth.make_texture(160, 96)
+    Twc = synth.prior_pose(height_above=height, tilt_deg=10.0 if height > 10 else 35.0)
+    g = Grid.make((2, 2, 1), (2, 1, 2), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    frame = synth.frame_textured(sc.W, sc.H, seed=31)
+    searcher.set_camera(sc.W, sc.H, sc.fx, sc.fy, sc.cx, sc.cy, sc.zn, sc.zf, sc.point_size)
+    searcher.set_mesh_textured(verts, tris, uv, tex)
+    searcher.set_frame(frame)
+    fl = searcher.flags(bins=bins)
+    res = searcher.search(Twc, g, fl, want_scores=True)
+    scores, renders, warps = oracle.search_mesh_tex(sc, Twc, g, verts, tris, uv, tex, frame, bins=bins, keep_images=True)
+    covered = 0.0
+    for s in range(g.n_synth):
+        t = oracle.cell_translation(Twc, g, s % 2, (s // 2) % 2, 0)
+        win, img = oracle.render_mesh_tex(sc, Twc, t, verts, tris, uv, tex)
+        assert np.array_equal(img, renders[s])
+        assert np.array_equal(searcher.get_winners(s), win), f"mesh z-buffer winners differ, view {s}"
+        got = searcher.get_render(s)
+        assert np.array_equal(got, img), f"view {s}: {(got != img).sum()} of {img.size} shaded pixels differ"
+        covered = (win != oracle.EMPTY).mean()
+        flat = oracle.render_mesh(sc, Twc, t, verts, tris)[1]
+        assert (flat != img).mean() > 0.5     # the texture really shades the fragments
+    assert covered > (0.9 if height > 10 else 0.3)
+    if height < 10:  # the near plane really cuts the terrain: some triangles have vertices on both sides
+        Rt = Twc[:3, :3].T
+        zc = (verts[:, :3] - Twc[:3, 3]) @ Rt.T[:, 2]
+        tz = zc[tris.astype(np.int64)]
+        assert ((tz.min(1) < sc.zn) & (tz.max(1) > sc.zn)).sum() > 50
+    assert_scores_close(res.scores, scores)
+    assert np.array_equal(res.scores.view(np.uint32), scores.view(np.uint32))
+    assert res.best_index == oracle.argmax(scores)[0]
+    # back to the flat-shaded entry point: the texture is dropped
+    searcher.set_mesh(verts, tris)
+    r2 = searcher.search(Twc, g, fl, want_scores=True)
+    s2, _, _ = oracle.search_mesh(sc, Twc, g, verts, tris, frame, bins=bins)
+    assert_scores_close(r2.scores, s2)
+
+
 def test_large_cloud_uses_gather_path(searcher, oracle):
     """>= 2^24 points: the key cannot carry the value, resolve gathers it (both paths exact)."""
     sc = synth.make_scene("tiny", n_points=(1 << 24) + 1000)

@@ -457,11 +457,19 @@ def test_mesh_depth_ties_and_clip(oracle):
     # nearer wins; equal depth -> lower triangle index; outside [zn, zf] dropped
     assert set(np.unique(win)) == {1, oracle.EMPTY}
     assert img[15, 15] == int(np.floor(255 * np.float32(0.2) + 0.5))
-    # a triangle with ONE vertex beyond the far plane is dropped entirely (our definition)
+    # a triangle with ONE vertex beyond the far plane is CLIPPED like GL clips it (per fragment on the
+    # interpolated depth): the part inside [zn, zf] is drawn, the rest is not
+    full, _ = oracle.render_mesh(cam, T, t0, np.array(tri(12.0, 0.1), np.float32), tris[:1])
     verts2 = np.array(tri(12.0, 0.1), np.float32)
-    verts2[2, :3] = _px_to_xyz(cam, 40, 10, 31.0)
+    verts2[2, :3] = _px_to_xyz(cam, 40, 10, 60.0)
     w2, _ = oracle.render_mesh(cam, T, t0, verts2, tris[:1])
-    assert not (w2 != oracle.EMPTY).any()
+    n_full, n_clip = int((full != oracle.EMPTY).sum()), int((w2 != oracle.EMPTY).sum())
+    assert 0 < n_clip < n_full
+    assert w2[35, 11] != oracle.EMPTY or w2[11, 11] != oracle.EMPTY   # near the two vertices at 12 m: kept
+    assert w2[11, 38] == oracle.EMPTY                                  # next to the vertex at 60 m: beyond zf = 30 m
+    # a triangle entirely beyond the far plane, or with a vertex that cannot be projected, draws nothing
+    far = np.array(tri(31.0, 0.5), np.float32)
+    assert not (oracle.render_mesh(cam, T, t0, far, tris[:1])[0] != oracle.EMPTY).any()
 
 
 def test_mesh_synthetic_terrain_renders(oracle):
@@ -471,3 +479,65 @@ def test_mesh_synthetic_terrain_renders(oracle):
     covered = (win != oracle.EMPTY).mean()
     assert covered > 0.95  # the terrain fills the view from 15 m up
     assert 20 < img[win != oracle.EMPTY].mean() < 235
+
+
+# ------------------------------------------------------- textured mesh (A.4, shading) -----
+def test_mesh_texture_shading_hand_values(oracle):
+    """Per-fragment shading of Rendering<1> (ShadingWithTexture.fragmentshader:16 over a texture that
+    loadBMP_custom uploads with its B,G,R bytes as r,g,b, texture.cpp:90)."""
+    cam, T, t0 = _mesh_cam()
+    quad = [_px_to_xyz(cam, 8, 4, 10.0) + [0.0], _px_to_xyz(cam, 8, 44, 10.0) + [0.0],
+            _px_to_xyz(cam, 56, 4, 10.0) + [0.0], _px_to_xyz(cam, 56, 44, 10.0) + [0.0]]
+    verts = np.array(quad, np.float32)
+    tris = np.array([[0, 1, 2], [2, 1, 3]], np.uint32)
+    win, _ = oracle.render_mesh(cam, T, t0, verts, tris)
+    if not (win != oracle.EMPTY).any():
+        tris = tris[:, [0, 2, 1]].copy()
+    uv_of = {0: (0.0, 0.0), 1: (0.0, 1.0), 2: (1.0, 0.0), 3: (1.0, 1.0)}
+    uv = np.array([[uv_of[int(k)] for k in t] for t in tris], np.float32)
+    # (i) a constant texture: every covered pixel = floor(0.299 c0 + 0.587 c1 + 0.114 c2 + 0.5) on the FILE order
+    tex = np.zeros((4, 4, 3), np.uint8)
+    tex[...] = (255, 0, 0)
+    win, img = oracle.render_mesh_tex(cam, T, t0, verts, tris, uv, tex)
+    cov = win != oracle.EMPTY
+    assert cov.sum() > 1800 and set(np.unique(img[cov])) == {76} and set(np.unique(img[~cov])) == {255}
+    tex[...] = (0, 0, 255)
+    assert set(np.unique(oracle.render_mesh_tex(cam, T, t0, verts, tris, uv, tex)[1][cov])) == {29}
+    # (ii) a two-texel texture along u: black | white, bilinear + GL_REPEAT: the middle of the quad is
+    # the texel border (grey ~128), a quarter in is a texel centre (pure), the quad's edges wrap to ~128
+    tex2 = np.zeros((1, 2, 3), np.uint8)
+    tex2[0, 1] = 255
+    _, img2 = oracle.render_mesh_tex(cam, T, t0, verts, tris, uv, tex2)
+    row = img2[24].astype(int)
+    assert abs(row[32] - 128) <= 6 and row[20] <= 8 and row[44] >= 247   # pixel 20 / 44: u = 0.26 / 0.76
+    # pixel 9: u = 1.5/48 -> x = -0.4375: texel -1 wraps to the white one, weight 0.4375 -> 111.6;
+    # pixel 55: u = 47.5/48 -> x = 1.479: white texel blending into the wrapped black one -> 132.8
+    assert abs(row[9] - 112) <= 1 and abs(row[55] - 133) <= 1
+    # (iii) the flat-shaded entry point is untouched by the texture machinery
+    w3, i3 = oracle.render_mesh(cam, T, t0, verts, tris)
+    assert np.array_equal(w3, win) and set(np.unique(i3[cov])) == {0}
+
+
+def test_mesh_texture_perspective_correct(oracle):
+    """A quad tilted in depth: UV is interpolated perspective-correctly (1/Zc weights), so the texel
+    boundary of a two-texel texture does NOT fall on the quad's screen-space midpoint."""
+    cam, T, t0 = _mesh_cam()
+    near, far = 6.0, 24.0
+    quad = [_px_to_xyz(cam, 8, 4, near) + [0.0], _px_to_xyz(cam, 8, 44, near) + [0.0],
+            _px_to_xyz(cam, 56, 4, far) + [0.0], _px_to_xyz(cam, 56, 44, far) + [0.0]]
+    verts = np.array(quad, np.float32)
+    tris = np.array([[0, 1, 2], [2, 1, 3]], np.uint32)
+    uv_of = {0: (0.0, 0.0), 1: (0.0, 1.0), 2: (1.0, 0.0), 3: (1.0, 1.0)}
+    for flip in (False, True):
+        tt = tris[:, [0, 2, 1]].copy() if flip else tris
+        uv = np.array([[uv_of[int(k)] for k in t] for t in tt], np.float32)
+        tex2 = np.zeros((1, 2, 3), np.uint8)
+        tex2[0, 1] = 255
+        win, img = oracle.render_mesh_tex(cam, T, t0, verts, tt, uv, tex2)
+        if (win != oracle.EMPTY).any():
+            break
+    row = img[24].astype(int)
+    cross = int(np.argmax(row[10:54] >= 128)) + 10      # first pixel past the u = 0.5 boundary
+    # u(s) = (s / far) / ((1 - s) / near + s / far) at screen fraction s -> u = 0.5 at s = far / (near + far)
+    want = 8 + (56 - 8) * (far / (near + far))
+    assert abs(cross - want) <= 2 and abs(cross - 32) >= 8
