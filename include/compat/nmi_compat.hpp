@@ -56,6 +56,15 @@ class Yaml {
 // Like the reference's `while(!in.eof())` loop, a trailing newline duplicates the last point.
 bool loadXYZ(const char* path, const char* offset_path, std::vector<float>& xyzi);
 
+// setupCam (ioData.cpp:177-197) reduces the pose to (pos, dir = pos + z, up) and the GL renderer rebuilds
+// its view from those three vectors (rendering.hpp:547-553) -- `dir - pos` is then z only up to the
+// rounding of a sum at the magnitude of the camera position.  The drop-in keeps the reference's
+// signatures, but has no reason to lose those bits: setupCam remembers the Twc it was given and
+// Rendering::setCamera, handed the very triple setupCam produced, gets the exact matrix back, so the
+// zero-change call sequence (Tracking.cc:1873-1894) scores bit for bit what the batched search scores.
+void remember_setup_cam(const float pos[3], const float dir[3], const float up[3], const float Twc[16]);
+bool recall_setup_cam(const float pos[3], const float dir[3], const float up[3], float Twc[16]);
+
 // loadOBJ (objloader.cpp:140-223): "v x y z", "vt u v", "f a/b c/d e/f" (1-based); any other
 // face syntax is rejected like the reference ("File can't be read by this simple parser").
 // Output is un-indexed like the reference's VBOs: 3 positions + 3 uvs per triangle.

@@ -32,6 +32,9 @@ class Rendering {
   // setupCam convention (ioData.cpp:177-197) back to a camera->world matrix:
   // z_cam = dir - pos, y_cam = up, x_cam = y_cam x z_cam.
   void twc(float T[16]) const {
+    const float p[3] = {Camera_pos.x, Camera_pos.y, Camera_pos.z}, d[3] = {Camera_direction.x, Camera_direction.y, Camera_direction.z},
+                u[3] = {Camera_up.x, Camera_up.y, Camera_up.z};
+    if (nmi_compat::recall_setup_cam(p, d, u, T)) return;  // the triple came from setupCam: the exact pose
     const glm::vec3 z = Camera_direction - Camera_pos, y = Camera_up;
     const glm::vec3 x(y.y * z.z - y.z * z.y, y.z * z.x - y.x * z.z, y.x * z.y - y.y * z.x);
     const float m[16] = {x.x, y.x, z.x, Camera_pos.x, x.y, y.y, z.y, Camera_pos.y,

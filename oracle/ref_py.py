@@ -163,3 +163,69 @@ def format_kernel(nS, nW, stepT, stepR, best_s, best_w, nmi) -> str:
     buf = C.create_string_buffer(1024)
     load_host().nmirefh_format(_p(s), _p(w), _p(t), _p(r), _p(bs), _p(bw), C.c_float(nmi), buf, 1024)
     return buf.value.decode()
+
+
+# ---- host-side geometry of the reference (oracle/_ref/libnmi_ref_geom.so; CPU only) ----------------
+GEOM_LIB_PATH = HERE / "_ref" / "libnmi_ref_geom.so"
+_geom = None
+
+
+def geom_available() -> bool:
+    return GEOM_LIB_PATH.exists()
+
+
+def _geom_lib():
+    global _geom
+    if _geom is None:
+        if not GEOM_LIB_PATH.exists():
+            raise RuntimeError(f"{GEOM_LIB_PATH} not built (make -C oracle -f Makefile.ref, needs /root/reference)")
+        _geom = C.CDLL(str(GEOM_LIB_PATH))
+        P = C.c_void_p
+        _geom.nmirefg_warp_matrices.argtypes = [P, P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                P, P, P]
+        _geom.nmirefg_setup_cam.argtypes = [P, P, P, P]
+        _geom.nmirefg_cell_translation.argtypes = [P, P, P, C.c_int, C.c_int, C.c_int, P]
+        _geom.nmirefg_apply_winner.argtypes = [P] * 8
+    return _geom
+
+
+def geom_warp_matrices(nW, stepR, W, H, fx, fy, cx, cy, resize=None):
+    """Image::Image (image.cpp:33-111) [+ Image::resizeKernel(nW', stepR')]: forward K R K^-1, float64,
+    shape (nWz, nWy, nWx, 3, 3)."""
+    nW = np.asarray(nW, np.int32)
+    stepR = np.asarray(stepR, np.float32)
+    n = np.asarray(resize[0], np.int32) if resize else nW
+    out = np.zeros((int(n[2]), int(n[1]), int(n[0]), 3, 3), np.float64)
+    rn = np.asarray(resize[0], np.int32) if resize else None
+    rs = np.asarray(resize[1], np.float32) if resize else None
+    got = _geom_lib().nmirefg_warp_matrices(_p(nW), _p(stepR), W, H, fx, fy, cx, cy, _p(rn) if resize else None,
+                                            _p(rs) if resize else None, _p(out))
+    assert got == out.size // 9
+    return out
+
+
+def geom_setup_cam(Twc):
+    T = np.ascontiguousarray(Twc, np.float32).reshape(16)
+    pos, d, up = (np.zeros(3, np.float32) for _ in range(3))
+    _geom_lib().nmirefg_setup_cam(_p(T), _p(pos), _p(d), _p(up))
+    return pos, d, up
+
+
+def geom_cell_translation(Twc, nS, stepT, sx, sy, sz):
+    """setupCam -> Rendering::setCamera -> calculateTranslation(sx, sy, sz) (Tracking.cc:1873-1882)."""
+    T = np.ascontiguousarray(Twc, np.float32).reshape(16)
+    nS = np.asarray(nS, np.int32)
+    st = np.asarray(stepT, np.float32)
+    t = np.zeros(3, np.float32)
+    _geom_lib().nmirefg_cell_translation(_p(T), _p(nS), _p(st), sx, sy, sz, _p(t))
+    return t
+
+
+def geom_apply_winner(Twc, nS, nW, stepT, stepR, s, w):
+    """Tracking::CalculateNMIRelocalization (Tracking.cc:2374-2419)."""
+    T = np.ascontiguousarray(Twc, np.float32).reshape(16)
+    a = [np.asarray(nS, np.int32), np.asarray(nW, np.int32), np.asarray(stepT, np.float32), np.asarray(stepR, np.float32),
+         np.asarray(s, np.int32), np.asarray(w, np.int32)]
+    out = np.zeros(16, np.float32)
+    _geom_lib().nmirefg_apply_winner(_p(T), *[_p(x) for x in a], _p(out))
+    return out.reshape(4, 4)

@@ -4,6 +4,7 @@
 #include <cerrno>
 #include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <ctime>
 #include <filesystem>
@@ -226,6 +227,30 @@ bool loadBMP24(const char* path, int& width, int& height, std::vector<unsigned c
   f.seekg(dataPos);
   f.read(reinterpret_cast<char*>(rgb.data()), imageSize);
   return (size_t)f.gcount() >= (size_t)width * height * 3;
+}
+
+namespace {
+struct SetupCamMemo {
+  float pos[3], dir[3], up[3], Twc[16];
+  bool valid = false;
+};
+thread_local SetupCamMemo g_memo;
+}  // namespace
+
+void remember_setup_cam(const float pos[3], const float dir[3], const float up[3], const float Twc[16]) {
+  std::memcpy(g_memo.pos, pos, sizeof g_memo.pos);
+  std::memcpy(g_memo.dir, dir, sizeof g_memo.dir);
+  std::memcpy(g_memo.up, up, sizeof g_memo.up);
+  std::memcpy(g_memo.Twc, Twc, sizeof g_memo.Twc);
+  g_memo.valid = true;
+}
+
+bool recall_setup_cam(const float pos[3], const float dir[3], const float up[3], float Twc[16]) {
+  if (!g_memo.valid || std::memcmp(g_memo.pos, pos, sizeof g_memo.pos) || std::memcmp(g_memo.dir, dir, sizeof g_memo.dir) ||
+      std::memcmp(g_memo.up, up, sizeof g_memo.up))
+    return false;
+  std::memcpy(Twc, g_memo.Twc, sizeof g_memo.Twc);
+  return true;
 }
 
 // OBJ + BMP -> the arguments of nmi_set_mesh_textured: un-indexed corners like the reference's VBOs

@@ -23,12 +23,6 @@ struct V3 {
 
 inline V3 column(const float* T, int c) { return V3{T[c], T[4 + c], T[8 + c]}; }
 
-// unit vector along +-column c of Twc
-inline V3 axis(const float* T, int c, float sign) {
-  const V3 v = column(T, c);
-  const float len = std::sqrt((v.x * v.x + v.y * v.y) + v.z * v.z);
-  return V3{sign * (v.x / len), sign * (v.y / len), sign * (v.z / len)};
-}
 
 struct M3 {
   double m[9];
@@ -104,20 +98,54 @@ uint64_t pack_key(float max_score, int64_t index) {
 
 extern "C" {
 
+// Statement for statement what the reference computes between the prior pose and the translation of a
+// grid cell -- setupCam (ioData.cpp:177-197), Rendering::setCamera, calculateTranslation
+// (rendering.hpp:644-665) with glm::rotate of GLM 0.9.7.1 (gtx/rotate_vector over
+// gtc/matrix_transform's axis-angle matrix) -- in the float / double mix a C++11 compiler gives that
+// source (pow(float, int) is a double).  Bit-identical to the reference's own lines compiled here
+// (the geometry target of oracle/Makefile.ref; tests/test_reference_geometry.py).  Note what the reference does:
+// `dir` is stored as pos + z and subtracted again, so its camera axes carry the rounding of a sum at the
+// magnitude of the camera POSITION; the third axis comes from a -90 degree rotation whose cosine is
+// cosf(-pi/2) = -4.4e-8, not 0.
 void nmi_cell_translation(const float Twc[16], const nmi_grid* g, int sx, int sy, int sz,
                           float t[3]) {
-  const V3 ax = axis(Twc, 0, -1.0f);  // camera-left  (= glm::rotate(dir_y,-90,dir_z))
-  const V3 ay = axis(Twc, 1, 1.0f);   // camera-down  (Camera_up of setupCam)
-  const V3 az = axis(Twc, 2, -1.0f);  // camera-back  (-(dir - pos))
-  const float ox = (static_cast<float>(g->nS[0]) - 1.0f) / 2.0f;
-  const float oy = (static_cast<float>(g->nS[1]) - 1.0f) / 2.0f;
-  const float oz = (static_cast<float>(g->nS[2]) - 1.0f) / 2.0f;
-  const float cx = (static_cast<float>(sx) - ox) * g->stepT[0];
-  const float cy = (static_cast<float>(sy) - oy) * g->stepT[1];
-  const float cz = (static_cast<float>(sz) - oz) * g->stepT[2];
-  t[0] = (cx * ax.x + cy * ay.x) + cz * az.x;
-  t[1] = (cx * ax.y + cy * ay.y) + cz * az.y;
-  t[2] = (cx * ax.z + cy * ay.z) + cz * az.z;
+  // setupCam
+  const float pos[3] = {Twc[3], Twc[7], Twc[11]};
+  const float dir[3] = {Twc[2] + pos[0], Twc[6] + pos[1], Twc[10] + pos[2]};
+  const float up[3] = {Twc[1], Twc[5], Twc[9]};
+  // calculateTranslation
+  const float x_offset = (static_cast<float>(g->nS[0]) - 1.0f) / 2.0f;
+  const float y_offset = (static_cast<float>(g->nS[1]) - 1.0f) / 2.0f;
+  const float z_offset = (static_cast<float>(g->nS[2]) - 1.0f) / 2.0f;
+  float length = static_cast<float>(std::sqrt(static_cast<double>(up[0]) * up[0] + static_cast<double>(up[1]) * up[1] +
+                                              static_cast<double>(up[2]) * up[2]));
+  const float dy[3] = {up[0] / length, up[1] / length, up[2] / length};
+  const float d0 = dir[0] - pos[0], d1 = dir[1] - pos[1], d2 = dir[2] - pos[2];
+  length = static_cast<float>(std::sqrt(static_cast<double>(d0) * d0 + static_cast<double>(d1) * d1 +
+                                        static_cast<double>(d2) * d2));
+  const float dz[3] = {-(d0 / length), -(d1 / length), -(d2 / length)};  // -1.0 * (float)(..): exact negation
+  // dir_x = glm::rotate(dir_y, glm::radians(-90.0f), dir_z)
+  const float angle = -90.0f * 0.01745329251994329576923690768489f;
+  const float c = std::cos(angle), sn = std::sin(angle);  // float overloads: cosf / sinf
+  const float inv = 1.0f / std::sqrt((dz[0] * dz[0] + dz[1] * dz[1]) + dz[2] * dz[2]);  // normalize = v * inversesqrt(dot)
+  const float ax[3] = {dz[0] * inv, dz[1] * inv, dz[2] * inv};
+  const float tmp[3] = {(1.0f - c) * ax[0], (1.0f - c) * ax[1], (1.0f - c) * ax[2]};
+  float R[3][3];  // R[column][row]
+  R[0][0] = c + tmp[0] * ax[0];
+  R[0][1] = 0 + tmp[0] * ax[1] + sn * ax[2];
+  R[0][2] = 0 + tmp[0] * ax[2] - sn * ax[1];
+  R[1][0] = 0 + tmp[1] * ax[0] - sn * ax[2];
+  R[1][1] = c + tmp[1] * ax[1];
+  R[1][2] = 0 + tmp[1] * ax[2] + sn * ax[0];
+  R[2][0] = 0 + tmp[2] * ax[0] + sn * ax[1];
+  R[2][1] = 0 + tmp[2] * ax[1] - sn * ax[0];
+  R[2][2] = c + tmp[2] * ax[2];
+  const float dx[3] = {R[0][0] * dy[0] + R[1][0] * dy[1] + R[2][0] * dy[2], R[0][1] * dy[0] + R[1][1] * dy[1] + R[2][1] * dy[2],
+                       R[0][2] * dy[0] + R[1][2] * dy[1] + R[2][2] * dy[2]};
+  const float cx = (static_cast<float>(sx) - x_offset) * g->stepT[0];
+  const float cy = (static_cast<float>(sy) - y_offset) * g->stepT[1];
+  const float cz = (static_cast<float>(sz) - z_offset) * g->stepT[2];
+  for (int k = 0; k < 3; ++k) t[k] = (cx * dx[k] + cy * dy[k]) + cz * dz[k];
 }
 
 void nmi_cell_homography_inv(const nmi_camera* cam, const nmi_grid* g, int wx, int wy, int wz,
