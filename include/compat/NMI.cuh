@@ -56,7 +56,6 @@ __device__ __forceinline__ float tree256(const float* in, float* scratch) {
   }
   return scratch[0];
 }
-__device__ unsigned int g_pairwise_done = 0;
 }  // namespace nmi_compat_detail
 
 // <<<258, 256>>>: block 0 -> histogram 1, block 1 -> histogram 2, blocks 2.. -> joint rows
@@ -88,22 +87,21 @@ static __global__ void AddvectorParwiseMidKernel(float* d_Array, float* d_out) {
 #define NMI_COMPAT_SCORE SUC
 #endif
 static __global__ void AddVectorPairwiseKernel(float* d_Array1, float* d_Array2, float* d_Array3) {
+  // The reference's three blocks each reduce one array and block 1 then reads the other two blocks'
+  // results without any grid-wide synchronisation (NMI.cu:340-342: a race that does fire on B200).
+  // Here block 0 walks the three trees one after the other -- same order of additions inside each tree,
+  // no inter-block communication, no global state (two launches on different streams cannot disturb
+  // each other); blocks 1 and 2 of the reference's <<<3, 128>>> launch shape simply return.
   __shared__ float s[128];
-  __shared__ bool last;
-  float* arr = blockIdx.x == 0 ? d_Array1 : blockIdx.x == 1 ? d_Array2 : d_Array3;
-  const float v = nmi_compat_detail::tree256(arr, s);
-  if (threadIdx.x == 0) {
-    arr[0] = v;
-    __threadfence();
-    last = atomicAdd(&nmi_compat_detail::g_pairwise_done, 1u) == gridDim.x - 1;
-  }
+  if (blockIdx.x != 0) return;
+  const float sa = nmi_compat_detail::tree256(d_Array1, s);
   __syncthreads();
-  if (last && threadIdx.x == 0) {  // the block that finishes last sees all three sums
-    __threadfence();
-    const volatile float* a1 = d_Array1;
-    const volatile float* a2 = d_Array2;
-    const volatile float* a3 = d_Array3;
-    const float sa = a1[0], sb = a2[0], sab = a3[0];
+  const float sb = nmi_compat_detail::tree256(d_Array2, s);
+  __syncthreads();
+  const float sab = nmi_compat_detail::tree256(d_Array3, s);
+  if (threadIdx.x == 0) {
+    d_Array2[0] = sb;   // the reference leaves each array's total in its element 0
+    d_Array3[0] = sab;
     float score;
     if (sa == 0.0f && sb == 0.0f && sab == 0.0f)
       score = 0.0f;  // NMI.cu:344,353
@@ -112,7 +110,6 @@ static __global__ void AddVectorPairwiseKernel(float* d_Array1, float* d_Array2,
     else
       score = __fmul_rn(2.0f, __fsub_rn(1.0f, __fdiv_rn(-sab, __fadd_rn(-sa, -sb))));  // NMI.cu:357
     d_Array1[0] = score;
-    nmi_compat_detail::g_pairwise_done = 0;
   }
 }
 #endif  // __CUDACC__

@@ -55,6 +55,18 @@ void launch_mesh_shade(unsigned long long* zbuf, const float4* verts, const uint
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 
+int sm_count() {
+  static thread_local int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 void prefer_max_shared(const void* kernel) {
   static const bool on = [] {
     const char* e = getenv("NMI_CARVEOUT");
@@ -310,7 +322,10 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   // (b) two-pass counting sort; record buffer sized for any pose (1.5 records per point and
   // view) or, in steady state, from what the previous search really produced (x1.5)
   const size_t cap_records = (2ull << 30) / sizeof(uint4);
-  size_t per_view = (size_t)((double)c->n_pts * 1.5) + 65536;
+  // records per (point, view): a splat of s px touches (1 + (s-1)/32)^2 tiles on average, 4 at most
+  const double sps = (double)(vc_point_size(c->cam) - 1) / 32.0;
+  const double tiles_per_splat = std::min(4.0, (1.0 + sps) * (1.0 + sps)) * 1.35 + 0.15;  // 1.5 for s = 3
+  size_t per_view = (size_t)((double)c->n_pts * tiles_per_splat) + 65536;
   if (fb && c->h_feedback[1] > 0) {  // ([1] is only filled by a two-pass search)
     const size_t seen = (size_t)c->h_feedback[1] / c->h_feedback[4];
     const size_t guess = seen + seen / 2 + 65536;
@@ -391,7 +406,7 @@ bool valid_grid(const nmi_grid* g) {
 bool valid_flags(const nmi_flags* f) {
   return f && (f->bins == 256 || f->bins == 64) &&
          (f->score_mode == NMI_SCORE_SUC || f->score_mode == NMI_SCORE_ENMI) && f->variant >= 0 &&
-         f->variant <= 13;
+         f->variant <= 10;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -560,7 +575,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
                 int world, unsigned long long* key_dev, float* scores_dev) {
   REQUIRE(c && Twc, NMI_ERR_INVALID, "null ctx / Twc");
   REQUIRE(valid_grid(g), NMI_ERR_INVALID, "invalid grid (counts must be 1..4096, nP <= 2^26)");
-  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags (bins 256|64, score 0|1, variant 0..13)");
+  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags (bins 256|64, score 0|1, variant 0..10)");
   REQUIRE(c->has_cam && (c->n_pts > 0 || c->n_tris > 0) && c->has_frame, NMI_ERR_STATE,
           "camera, model and frame must be set before a search");
   CK(cudaSetDevice(c->device));

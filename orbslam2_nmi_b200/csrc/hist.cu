@@ -182,14 +182,15 @@ __device__ __forceinline__ float finish_score(float sa, float sb, float sab, int
 }
 
 // ---- bin addressing ----------------------------------------------------------
-// t = (a << 8) | b (upper bits of t may hold garbage).  U16G: word w = t >> 1 (15 bits),
-// field t & 1.  With SWZ the low 8 bits of w are XORed with a: the bank then depends on
-// both images, so a flat region in one of them no longer piles a warp onto one bank.
-// The map stays a bijection (a's upper 7 bits sit untouched in w's upper bits).
+// t = (a << 8) | b (upper bits of t may hold garbage).  U16G: word w = t >> 1 (15 bits: a in the upper
+// 8, m = b >> 1 in the lower 7), field t & 1.  With SWZ m is XORed with the low 7 bits of a: the bank
+// then depends on both images, so a flat region in one of them no longer piles a warp onto one bank.
+// The map stays a bijection (a itself sits untouched in w's upper bits).  Written on the pixel BYTES
+// the swizzle is b' = b ^ ((a & 0x7F) << 1) -- one LOP3 on a word of four pixels (accum_fast).
 template <bool SWZ>
 __device__ __forceinline__ uint32_t u16g_word(uint32_t t) {
   const uint32_t w = (t >> 1) & 0x7FFFu;
-  return SWZ ? (w ^ ((t >> 8) & 0xFFu)) : w;
+  return SWZ ? (w ^ ((t >> 8) & 0x7Fu)) : w;
 }
 // The thread whose increment made field (t & 1) of word w cross a multiple of 4096 repays
 // it.  `nw` is the word right after that increment.
@@ -232,59 +233,34 @@ __device__ __forceinline__ void accum_slow(Smem& sm, const uint32_t (&rw)[NW], c
 }
 
 // fast path: full chunk, every pixel counted (nmi_prop_BG == true, the reference default)
-// SCHED (packed-u16 only; experiment knob of the persistent build, variants 11-13): how the address
-// arithmetic and the ATOMS of a thread's 16 pixels are grouped in the SOURCE -- 0: pixel by pixel
-// (ptxas interleaves as it likes), 1: all 16 addresses first, then 16 ATOMS back to back,
-// 2: two halves of 8, 3: four quarters of 4.
+// Per pixel the hot loop costs 8 issue slots (was 10.5): the swizzle is applied to four pixels at once on
+// the warp-image word (b' = b ^ ((a & 0x7F) << 1): one shift + one LOP3 per word), PRMT then delivers
+// t' = a << 8 | b' directly, and the byte address is ONE IMAD, (t' & 0xFFFE) * 2 + base, instead of
+// shift / extract / shift / xor / add.  The kernel keeps the issue slots as busy as the ATOMS pipe
+// (14.25 instructions per 32-lane atomic = 3.6 clk of issue against 3.5 clk of ATOMS, ncu round 1), so
+// instructions are time here.  SCHED: round-2 experiment (source-level grouping of the ATOMS, variants
+// 11-13) measured no difference (4.543 vs 4.547 ms) and is gone; the parameter is kept so that the
+// kernel templates' signatures do not change.
 template <int POLICY, bool SWZ, int NW, int SCHED = 0>
 __device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], const uint32_t (&ww)[NW],
                                            int pass, int warp) {
   constexpr int N = NW * 4;
-  if (POLICY == P_U16G && SCHED != 0) {
-    constexpr int G = SCHED == 1 ? N : (SCHED == 2 ? N / 2 : N / 4);  // pixels per group
-    uint32_t tt[N], nw[N];
-    const uint32_t base = smem_u32(sm.hist);
-#pragma unroll
-    for (int g0 = 0; g0 < N; g0 += G) {
-      uint32_t ad[G], inc[G];
-#pragma unroll
-      for (int j = 0; j < G; j++) {
-        const int i = g0 + j;
-        const uint32_t t = __byte_perm(ww[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);
-        uint32_t addr = (t * 2u) & 0x1FFFCu;
-        if (SWZ) addr ^= __byte_perm(rw[i >> 2], 0u, 0x4440 + (i & 3)) * 4u;
-        asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc[j]) : "r"(t & 1u));
-        ad[j] = base + addr;
-        tt[i] = t;
-      }
-#pragma unroll
-      for (int j = 0; j < G; j++) {
-        uint32_t old;
-        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(ad[j]), "r"(inc[j]) : "memory");
-        nw[g0 + j] = old + inc[j];
-      }
-    }
-    uint32_t acc = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) acc |= nw[i];
-    if (acc & kFlagMask) {
-#pragma unroll
-      for (int i = 0; i < N; i++) u16g_repay_if_crossed<SWZ>(sm, tt[i] & 0xFFFFu, nw[i]);
-    }
-  } else if (POLICY == P_U16G) {
+  if (POLICY == P_U16G) {
     // 16 (or 8) independent ATOMS in flight; the returned words are only ORed together.
     // Integer work is split between the ALU pipe (PRMT, LOP3) and the FMA pipe (IMAD).
-    uint32_t tt[N], nw[N];
+    uint32_t tt[N], nw[N], ws[NW];
     const uint32_t base = smem_u32(sm.hist);
 #pragma unroll
+    for (int j = 0; j < NW; j++) ws[j] = SWZ ? (ww[j] ^ ((rw[j] << 1) & 0xFEFEFEFEu)) : ww[j];
+#pragma unroll
     for (int i = 0; i < N; i++) {
-      const uint32_t t = __byte_perm(ww[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);
-      uint32_t addr = (t * 2u) & 0x1FFFCu;  // byte offset of word t >> 1
-      if (SWZ) addr ^= __byte_perm(rw[i >> 2], 0u, 0x4440 + (i & 3)) * 4u;  // ^ (a << 2)
-      uint32_t inc;  // 1 or 0x10000; a real IMAD (FMA pipe), not the ISETP+SEL the compiler prefers
-      asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc) : "r"(t & 1u));
+      const uint32_t t = __byte_perm(ws[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);  // a << 8 | b' (+ garbage above)
+      uint32_t addr, inc;
+      asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(t & 0xFFFEu), "r"(base));  // byte address of word t' >> 1
+      asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc) : "r"(t & 1u));  // 1 or 0x10000; a real IMAD (FMA pipe)
       uint32_t old;
-      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(base + addr), "r"(inc) : "memory");
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(inc) : "memory");
+      // the bin's un-swizzled name, for the rare repay path: b = b' ^ ((a & 0x7F) << 1)
       tt[i] = t;
       nw[i] = old + inc;  // the word right after this thread's increment
     }
@@ -293,7 +269,10 @@ __device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], c
     for (int i = 0; i < N; i++) acc |= nw[i];
     if (acc & kFlagMask) {  // rare: some field of a touched word is >= 4096
 #pragma unroll
-      for (int i = 0; i < N; i++) u16g_repay_if_crossed<SWZ>(sm, tt[i] & 0xFFFFu, nw[i]);
+      for (int i = 0; i < N; i++) {
+        const uint32_t ts = tt[i] & 0xFFFFu;
+        u16g_repay_if_crossed<SWZ>(sm, SWZ ? (ts ^ ((ts >> 7) & 0xFEu)) : ts, nw[i]);
+      }
     }
   } else if (POLICY == P_U32X2) {
     const uint32_t base = smem_u32(sm.hist);
@@ -532,7 +511,7 @@ __device__ __forceinline__ void rows_epilogue_fast(Smem& sm, float L, const Hist
   {
     const uint32_t row = (uint32_t)warp * 16u + ((uint32_t)lane & 15u);
     const uint32_t pb = (uint32_t)lane >> 4;
-    const uint32_t rowx = ((row << 7) ^ row) ^ (pb ? 17u : 0u);  // u16g_word<true>(row << 8); B: odd words, bit 4 swapped
+    const uint32_t rowx = ((row << 7) ^ (row & 0x7Fu)) ^ (pb ? 17u : 0u);  // u16g_word<true>(row << 8); B: odd words, bit 4 swapped
     uint32_t rs = 0;
     // bits 1..3 of m: eight subtrees visited depth-first (bit 1 is the split nearest the root, so
     // the visiting order counts q = bits 3..1 bit-reversed) and folded like a binary counter --
@@ -568,7 +547,7 @@ __device__ __forceinline__ void rows_epilogue_fast(Smem& sm, float L, const Hist
     uint32_t slo = 0, shi = 0;
 #pragma unroll 16
     for (uint32_t r = r0; r < r0 + 64u; r++) {
-      const uint32_t idx = ((r << 7) ^ r) ^ cw;
+      const uint32_t idx = ((r << 7) ^ (r & 0x7Fu)) ^ cw;
       const uint32_t wv = sm.hist[idx];
       if (ZERO) sm.hist[idx] = 0u;
       slo += wv & 0xFFFFu;
@@ -587,7 +566,7 @@ __device__ __forceinline__ void dump_joint_swizzled(const Smem& sm, uint32_t* __
   constexpr int kConsumers = 16 * 32;
   for (uint32_t i = tid; i < (uint32_t)kHistWords; i += kConsumers) {
     const uint32_t r = i >> 7, m = i & 127u;
-    const uint32_t wv = sm.hist[((r << 7) ^ r) ^ m];  // u16g_word<true>((r << 8) | 2m)
+    const uint32_t wv = sm.hist[((r << 7) ^ (r & 0x7Fu)) ^ m];  // u16g_word<true>((r << 8) | 2m)
     J[r * 256u + 2u * m] = wv & 0xFFFFu;
     J[r * 256u + 2u * m + 1u] = wv >> 16;
   }
@@ -1404,9 +1383,6 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
       return a.term_tab != nullptr ? launch_t<P_U16G, true, 16, true, false, true>(a, st)
                                    : launch_t<P_U16G, true, 16, true>(a, st);
     case 10: return launch_tmem(a, st);  // variant 0 with the pixel ring staged through tensor memory
-    case 11: return launch_persistent<true, false, false, 1>(a, st);  // variant 0, source-level ATOMS grouping 16
-    case 12: return launch_persistent<true, false, false, 2>(a, st);  // ... 2 x 8
-    case 13: return launch_persistent<true, false, false, 3>(a, st);  // ... 4 x 4
     default:  // variant 0: TMA ring, bank swizzle, persistent CTAs with the fast epilogue
       return a.dumpJ != nullptr ? launch_persistent<true, false, true>(a, st) : launch_persistent<true, false>(a, st);
   }

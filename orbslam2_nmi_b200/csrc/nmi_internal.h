@@ -96,5 +96,8 @@ void set_error(const std::string& msg);
 // Measured in round 2: no gain (6.17 vs 6.06 ms per search at depth 2, every kernel a little slower
 // with the small L1) -- off by default, kept as a switch.
 void prefer_max_shared(const void* kernel);
+// SM count of the current device (cached per device; 148 on B200): grid-stride kernels size their grids
+// as a multiple of it.
+int sm_count();
 
 }  // namespace nmi

@@ -483,7 +483,10 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bi
     end = min(bin + 1 < gridDim.x ? offsets[bin + 1] : *total, rec_cap);
   }
   if (tid == 0) atomicMax(total + 2, (uint32_t)(end - start));  // feedback: fullest bin
-  for (int q = tid; q < 2 * E * E; q += kTileThreads) s_dyn[q] = 0xFFFFFFFFu;
+  {
+    uint4* s4 = reinterpret_cast<uint4*>(s_dyn);  // 2 * E * E words, rounded up to whole uint4s (the buffer is padded)
+    for (int q = tid; q < (2 * E * E + 3) / 4; q += kTileThreads) s4[q] = make_uint4(~0u, ~0u, ~0u, ~0u);
+  }
   __syncthreads();
   const int ox = x0 - (S - 1) + 32768, oy = y0 - (S - 1) + 32768;
   // pass 1: minimum depth per anchor cell.  The first kKeep records of a thread stay in registers
@@ -524,21 +527,33 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bi
   // S x S min filter; the CTA owns the tile: plain stores of the finished pixels (8 per thread, one
   // row segment).  Pixel (i, j) of the tile <- cells u in [i, i+S), v in [j, j+S).
   const int row = tid >> 2, col = (tid & 3) * 8;
-  unsigned long long best[8];
-  auto cell_key = [&](int q) { return ((unsigned long long)s_depth[q] << 32) | s_tag[q]; };
+  // The minimum of the packed (depth, tag) keys = the minimum depth, then the minimum tag among the cells
+  // that hold it: two 32-bit stages (one VIMNMX3 per three values) instead of 64-bit compares.
+  uint32_t bd[8], bt[8];
   if (ST == 3) {
-    unsigned long long vm[10];  // column minima over the three rows
+    uint32_t vd[10], vt[10];  // per column: min over the three anchor rows
 #pragma unroll
     for (int c = 0; c < 10; c++) {
       const int q = row * E + col + c;
-      const unsigned long long k0 = cell_key(q), k1 = cell_key(q + E), k2 = cell_key(q + 2 * E);
-      vm[c] = min(k0, min(k1, k2));
+      const uint32_t d0 = s_depth[q], d1 = s_depth[q + E], d2 = s_depth[q + 2 * E];
+      const uint32_t m = min(d0, min(d1, d2));
+      const uint32_t t0 = d0 == m ? s_tag[q] : 0xFFFFFFFFu, t1 = d1 == m ? s_tag[q + E] : 0xFFFFFFFFu,
+                     t2 = d2 == m ? s_tag[q + 2 * E] : 0xFFFFFFFFu;
+      vd[c] = m;
+      vt[c] = min(t0, min(t1, t2));
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++) best[k] = min(vm[k], min(vm[k + 1], vm[k + 2]));
+    for (int k = 0; k < 8; k++) {
+      const uint32_t m = min(vd[k], min(vd[k + 1], vd[k + 2]));
+      const uint32_t t0 = vd[k] == m ? vt[k] : 0xFFFFFFFFu, t1 = vd[k + 1] == m ? vt[k + 1] : 0xFFFFFFFFu,
+                     t2 = vd[k + 2] == m ? vt[k + 2] : 0xFFFFFFFFu;
+      bd[k] = m;
+      bt[k] = min(t0, min(t1, t2));
+    }
   } else {
     // generic point size: horizontal minima of every anchor row into shared memory, then vertical
-    unsigned long long* s_h = reinterpret_cast<unsigned long long*>(s_dyn + 2 * E * E + ((2 * E * E) & 1));  // [E][32]
+    auto cell_key = [&](int q) { return ((unsigned long long)s_depth[q] << 32) | s_tag[q]; };
+    unsigned long long* s_h = reinterpret_cast<unsigned long long*>(s_dyn + ((2 * E * E + 3) & ~3));  // [E][32]
     for (int q = tid; q < E * kTile; q += kTileThreads) {
       const int vv = q >> 5, i = q & 31;
       unsigned long long m = ~0ull;
@@ -550,7 +565,8 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bi
     for (int k = 0; k < 8; k++) {
       unsigned long long m = ~0ull;
       for (int dv = 0; dv < S; dv++) m = min(m, s_h[(row + dv) * kTile + col + k]);
-      best[k] = m;
+      bd[k] = (uint32_t)(m >> 32);
+      bt[k] = (uint32_t)m;
     }
   }
   uint8_t* img = images + (size_t)v * pitch;
@@ -559,8 +575,8 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bi
     unsigned long long packed = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const uint32_t tg = (uint32_t)best[k];
-      const bool empty = best[k] == ~0ull;
+      const uint32_t tg = bt[k];
+      const bool empty = bd[k] == 0xFFFFFFFFu;  // depth bits of a real splat are < 0x7F800000
       const int x = x0 + col + k;
       uint32_t pix = 255u;
       if (!empty) pix = PACKED ? (tg & 0xFFu) : (x < W ? (uint32_t)__ldg(val + tg) : 0u);
@@ -615,7 +631,7 @@ resolve_kernel(unsigned long long* __restrict__ zbuf, const uint8_t* __restrict_
 
 void launch_fill_u64(unsigned long long* p, size_t n, unsigned long long v, cudaStream_t st) {
   if (n == 0) return;
-  fill_u64_kernel<<<148 * 8, 256, 0, st>>>(p, n, v);
+  fill_u64_kernel<<<sm_count() * 8, 256, 0, st>>>(p, n, v);
 }
 
 void launch_intensity_u8(const float4* pts, const uint32_t* orig, uint8_t* val, uint32_t* tag,
@@ -652,7 +668,7 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
                           const float4* centres, int nviews, const ViewConst& vc,
                           unsigned long long* zbuf, size_t P, uint32_t max_points, cudaStream_t st) {
   if (nviews == 0 || max_points == 0) return;
-  project_splat_kernel<<<148 * 16, 256, sizeof(float4) * nviews, st>>>(cpts, cidx, counter,
+  project_splat_kernel<<<sm_count() * 16, 256, sizeof(float4) * nviews, st>>>(cpts, cidx, counter,
                                                                       centres, nviews, vc, zbuf, P);
 }
 
@@ -664,7 +680,7 @@ void launch_bin_points(int mode, const float4* cpts, const uint32_t* ctag, const
                        uint32_t* overflow, cudaStream_t st) {
   if (nviews == 0) return;
   const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
-  const dim3 grid(148 * 16), block(256);
+  const dim3 grid(sm_count() * 16), block(256);
   const size_t smem = sizeof(float4) * nviews;
   prefer_max_shared((const void*)bin_kernel<0>);
   prefer_max_shared((const void*)bin_kernel<1>);
@@ -695,8 +711,8 @@ void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, uint32_t bin_cap, c
   const unsigned grid = (unsigned)nviews * ntx * nty;
   const int E = kTile + vc.s - 1;
   // anchor cells (depth + tag words); generic point sizes add the [E][32] u64 row minima
-  size_t smem = (size_t)2 * E * E * sizeof(uint32_t);
-  if (vc.s != 3) smem += 8 + (size_t)E * kTile * sizeof(unsigned long long);
+  size_t smem = (size_t)((2 * E * E + 3) & ~3) * sizeof(uint32_t);  // whole uint4s (the init stores 16 bytes at a time)
+  if (vc.s != 3) smem += (size_t)E * kTile * sizeof(unsigned long long);
 #define NMI_TR(PK, ST3)                                                                                         \
   prefer_max_shared((const void*)tile_resolve_kernel<PK, ST3>);                                                   \
   tile_resolve_kernel<PK, ST3><<<grid, kTileThreads, smem, st>>>(rec, rec_cap, bin_cap, offsets, total, ntx,     \

@@ -30,7 +30,7 @@ if quick:
 s.set_scene(sc)
 s.set_frame(synth.frame_textured(sc.W, sc.H, seed=3))
 g = synth.default_grid((2, 1, 1), (2, 1, 1)) if quick else synth.default_grid((3, 2, 2), (2, 3, 1))
-variants = (0, 0, 9, 10) if quick else (0, 0, 9, 10, 1, 2, 5, 8, 11)
+variants = (0, 0, 9, 10) if quick else (0, 0, 9, 10, 1, 2, 5, 8)
 for v in variants:
     r = s.search(sc.Twc, g, s.flags(variant=v))
 for flags in (s.flags(bg=0), s.flags(bins=64)):

@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(1024, 1) k_atoms(uint32_t* out, long long* cyc
   const long long t0 = clock64();
   if (MODE == HIST_PATTERN || MODE == HIST_PATTERN_LDS) {
     // 16 pixels per thread and step, as accum_fast<P_U16G, SWZ>: t = a << 8 | b
+    // pixels from a per-thread multiplicative-congruential stream (independently hashed seeds, one IMAD
+    // per word of four pixels) so that generating them costs 0.5 issue slots per pixel, not 4.5
+    uint32_t x = hash32(gtid) | 1u;
     for (int it = 0; it < kIters / 16; it++) {
       uint32_t r[4], w[4];
       if (MODE == HIST_PATTERN_LDS) {
@@ -57,28 +60,28 @@ __global__ void __launch_bounds__(1024, 1) k_atoms(uint32_t* out, long long* cyc
         const uint4 wv = *reinterpret_cast<const uint4*>(stage + 2048 + ((threadIdx.x * 4 + it * 64) & 2047));
         r[0] = rv.x; r[1] = rv.y; r[2] = rv.z; r[3] = rv.w;
         w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {  // the staged words are constants: mix so that the pixels stay random
-          r[j] ^= hash32(gtid * 64u + it * 8u + j);
-          w[j] ^= hash32(gtid * 64u + it * 8u + 4u + j);
-        }
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          r[j] = hash32(gtid * 64u + it * 8u + j);
-          w[j] = hash32(gtid * 64u + it * 8u + 4u + j);
-        }
+        for (int j = 0; j < 4; j++) r[j] = w[j] = 0;
       }
-      uint32_t orv = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        x = x * 0x9E3779B1u + 0x7F4A7C15u;
+        r[j] ^= x;
+        x = x * 0x9E3779B1u + 0x7F4A7C15u;
+        w[j] ^= __byte_perm(x, 0u, 0x0123);  // the well-mixed high bytes into every byte position
+      }
+      uint32_t orv = 0, ws[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) ws[j] = w[j] ^ ((r[j] << 1) & 0xFEFEFEFEu);  // swizzle on four pixels at once
 #pragma unroll
       for (int i = 0; i < 16; i++) {
-        const uint32_t t = __byte_perm(w[i >> 2], r[i >> 2], 0x4440 + (i & 3) * 0x11);
-        uint32_t addr = (t * 2u) & 0x1FFFCu;
-        addr ^= __byte_perm(r[i >> 2], 0u, 0x4440 + (i & 3)) * 4u;
-        uint32_t inc;
+        const uint32_t t = __byte_perm(ws[i >> 2], r[i >> 2], 0x4440 + (i & 3) * 0x11);
+        uint32_t addr, inc;
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(t & 0xFFFEu), "r"(base));
         asm("mad.lo.u32 %0, %1, 0xFFFF, 1;" : "=r"(inc) : "r"(t & 1u));
         uint32_t old;
-        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(base + addr), "r"(inc) : "memory");
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(inc) : "memory");
         orv |= old + inc;
       }
       if (orv & 0xF000F000u) acc++;
