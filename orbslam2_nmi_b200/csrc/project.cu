@@ -296,6 +296,16 @@ project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict
 //                  fragments at the minimum depth (== the packed 64-bit key minimum) -- and
 //                  the CTA, sole owner of the tile, stores the finished u8 pixels directly.
 // No global z-buffer, no global atomics on pixels, no separate resolve pass.
+// bin_kernel waits on the L2 round trip of its slot atomics (ncu: 42 % of the stall cycles).  Measured at
+// C2 (round 2, bin + tile_resolve ms): 8 views in flight per thread / 3 CTAs per SM 1.24, 6 / 4 1.14,
+// 4 / 5 (round 1, 48 registers with spills) 1.04, 2 / 6 1.01, 1 / 8 and 2 / 8 0.98 -- full occupancy
+// (32 registers, 64 warps per SM, no spills) hides the latency better than unrolling does.
+#ifndef NMI_BIN_U
+#define NMI_BIN_U 1      // views projected together per thread (independent slot atomics in flight)
+#endif
+#ifndef NMI_BIN_CTAS
+#define NMI_BIN_CTAS 8   // resident CTAs per SM the register budget is cut for
+#endif
 constexpr int kTile = 32;  // (bin_kernel shifts by 5)
 constexpr int kTileCells = kTile * kTile;
 constexpr int kTileThreads = 128;
@@ -334,7 +344,7 @@ __device__ __forceinline__ Splat project_splat_point(const float4& p, const floa
 // pass of the counting sort).  MODE 2: single pass into fixed-capacity bins (capacity known
 // from the previous search; a bin that fills up raises the overflow flag).
 template <int MODE>
-__global__ void __launch_bounds__(256, 5)  // <= 51 registers: five CTAs per SM hide the slot-atomic latency (measured)
+__global__ void __launch_bounds__(256, NMI_BIN_CTAS)
 bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
            const uint32_t* __restrict__ counter, const float4* __restrict__ centres, int nviews,
            ViewConst vc, int ntx, int nt, uint32_t* __restrict__ counts,
@@ -379,9 +389,9 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
   // Slot allocation.  The cloud is Morton-ordered, so neighbouring lanes usually fall into the
   // same (view, tile) bin: each run of consecutive lanes with the same bin takes its slots with
   // ONE atomic (issued by the run's first lane, which adds the run length), an order of
-  // magnitude fewer L2 atomics than one per record.  Four views are projected together and
-  // their atomics issued back to back, so four round trips (~700 cycles each) are in flight.
-  constexpr int U = 4;
+  // magnitude fewer L2 atomics than one per record.  U views are projected together and their
+  // atomics issued back to back (U round trips of ~700 cycles in flight per thread; see NMI_BIN_U).
+  constexpr int U = NMI_BIN_U;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); t0 < count; t0 += stride) {
