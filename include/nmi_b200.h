@@ -73,7 +73,7 @@ typedef struct {
   int bins;       /* 256 (NMI.cuh:39) or 64                                   */
   int score_mode; /* NMI_SCORE_SUC / NMI_SCORE_ENMI (kernel.cuh:22-23)        */
   int bg;         /* nmi_prop_BG (allProperties.hpp:39); 0 skips value-0 px   */
-  int variant;    /* histogram kernel variant 0..10, 0 = default */
+  int variant;    /* histogram kernel variant 0..11, 0 = default */
 } nmi_flags;
 
 typedef struct {

@@ -406,7 +406,7 @@ bool valid_grid(const nmi_grid* g) {
 bool valid_flags(const nmi_flags* f) {
   return f && (f->bins == 256 || f->bins == 64) &&
          (f->score_mode == NMI_SCORE_SUC || f->score_mode == NMI_SCORE_ENMI) && f->variant >= 0 &&
-         f->variant <= 10;
+         f->variant <= 11;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -575,7 +575,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
                 int world, unsigned long long* key_dev, float* scores_dev) {
   REQUIRE(c && Twc, NMI_ERR_INVALID, "null ctx / Twc");
   REQUIRE(valid_grid(g), NMI_ERR_INVALID, "invalid grid (counts must be 1..4096, nP <= 2^26)");
-  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags (bins 256|64, score 0|1, variant 0..10)");
+  REQUIRE(valid_flags(f), NMI_ERR_INVALID, "invalid flags (bins 256|64, score 0|1, variant 0..11)");
   REQUIRE(c->has_cam && (c->n_pts > 0 || c->n_tris > 0) && c->has_frame, NMI_ERR_STATE,
           "camera, model and frame must be set before a search");
   CK(cudaSetDevice(c->device));

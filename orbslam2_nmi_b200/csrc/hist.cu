@@ -606,7 +606,10 @@ __device__ __forceinline__ void ldg_words(uint32_t (&dst)[NW], const uint8_t* p)
 // NWARPS consumer warps.  With 16 of them a 17th warp is the dedicated TMA producer; with 32
 // (the 1024-thread CTA limit) thread 0 doubles as producer: after releasing chunk k it waits
 // until every warp has released it and refills that stage with chunk k + kStages.
-template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP, bool FASTEP = false>
+// LDGD (USE_TMA == false only): chunks a thread keeps in flight in registers (ld.global.nc straight from
+// L2, no shared-memory staging at all: the pixels then cross the shared-memory array zero times instead
+// of twice -- round-2 experiment, variants 11-13).
+template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP, bool FASTEP = false, int LDGD = 1>
 __global__ void __launch_bounds__(NWARPS == 32 ? 1024 : NWARPS * 32 + 32, 1)
 joint_hist_score_kernel(const HistArgs a) {
   static_assert(!SKIPCAP || POLICY == P_U16G, "hot-bin skipping is built for the packed-u16 policy");
@@ -693,17 +696,26 @@ joint_hist_score_kernel(const HistArgs a) {
     if (INLINE_PRODUCER && USE_TMA && tid == 0)
       for (int k = 0; k < kStages && k < total; k++) issue_chunk(k);
     // ===== consumers =====
-    uint32_t nr[NW], nw[NW];
+    uint32_t qr[LDGD][NW], qw[LDGD][NW];  // LDG build: the next LDGD chunks of this thread, in registers
 #pragma unroll
-    for (int j = 0; j < NW; j++) nr[j] = nw[j] = 0;
+    for (int d = 0; d < LDGD; d++)
+#pragma unroll
+      for (int j = 0; j < NW; j++) qr[d][j] = qw[d][j] = 0;
     if (!USE_TMA) {
-      const uint32_t off = (uint32_t)tid * PIX;
-      if (off < npix) {
-        ldg_words<NW>(nr, rimg + off);
-        ldg_words<NW>(nw, wimg + off);
+#pragma unroll
+      for (int d = 0; d < LDGD; d++) {
+        const uint32_t off = (uint32_t)(d % nchunks) * kChunk + (uint32_t)tid * PIX;
+        if (d < total && off < npix) {
+          ldg_words<NW>(qr[d], rimg + off);
+          ldg_words<NW>(qw[d], wimg + off);
+        }
       }
     }
-    for (int k = 0; k < total; k++) {
+    for (int k0 = 0; k0 < total; k0 += (USE_TMA ? 1 : LDGD))
+#pragma unroll
+    for (int dd = 0; dd < (USE_TMA ? 1 : LDGD); dd++) {
+      const int k = k0 + dd;
+      if (k >= total) break;
       const int pass = k / nchunks;
       const int ck = k - pass * nchunks;
       const uint32_t off = (uint32_t)ck * kChunk + (uint32_t)tid * PIX;
@@ -715,13 +727,13 @@ joint_hist_score_kernel(const HistArgs a) {
         load_words<NW>(w, sm.wbuf[st] + tid * PIX);
       } else {
 #pragma unroll
-        for (int j = 0; j < NW; j++) { r[j] = nr[j]; w[j] = nw[j]; }
-        if (k + 1 < total) {  // register prefetch of the next chunk
-          const int ck2 = (k + 1) % nchunks;
+        for (int j = 0; j < NW; j++) { r[j] = qr[dd][j]; w[j] = qw[dd][j]; }
+        if (k + LDGD < total) {  // refill this register slot with the chunk LDGD ahead
+          const int ck2 = (k + LDGD) % nchunks;
           const uint32_t off2 = (uint32_t)ck2 * kChunk + (uint32_t)tid * PIX;
           if (off2 < npix) {
-            ldg_words<NW>(nr, rimg + off2);
-            ldg_words<NW>(nw, wimg + off2);
+            ldg_words<NW>(qr[dd], rimg + off2);
+            ldg_words<NW>(qw[dd], wimg + off2);
           }
         }
       }
@@ -761,8 +773,10 @@ joint_hist_score_kernel(const HistArgs a) {
           mbar_wait(&sm.empty[k % kStages], (k / kStages) & 1);
           issue_chunk(k + kStages);
         }
-      } else if (POLICY == P_U16G && (k & 1)) {
-        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // bound the in-flight pixels
+      } else if (POLICY == P_U16G && (k & 3) == 3) {
+        // bound the in-flight pixels: between two barriers the fastest warp gets at most 4 chunks
+        // = 32 768 pixels ahead of a thread that still has a crossing to repay (< 15 * 4096)
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
       }
       if (NPASS == 2 && ck == nchunks - 1) {
         // end of a pass: rows of this half are final
@@ -1287,9 +1301,9 @@ image_mode_kernel(const uint8_t* __restrict__ renders, size_t rpitch, int nr,
   }
 }
 
-template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP = false, bool FASTEP = false>
+template <int POLICY, bool USE_TMA, int NWARPS, bool SWZ, bool SKIPCAP = false, bool FASTEP = false, int LDGD = 1>
 int launch_t(const HistArgs& a, cudaStream_t st) {
-  auto kern = joint_hist_score_kernel<POLICY, USE_TMA, NWARPS, SWZ, SKIPCAP, FASTEP>;
+  auto kern = joint_hist_score_kernel<POLICY, USE_TMA, NWARPS, SWZ, SKIPCAP, FASTEP, LDGD>;
   constexpr size_t smem = sizeof(Smem) + (SKIPCAP ? sizeof(SmemSkip) : 0);
   static bool configured[64] = {false};  // the attribute is per device (contexts of several GPUs in one process)
   int dev = 0;
@@ -1383,6 +1397,11 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
       return a.term_tab != nullptr ? launch_t<P_U16G, true, 16, true, false, true>(a, st)
                                    : launch_t<P_U16G, true, 16, true>(a, st);
     case 10: return launch_tmem(a, st);  // variant 0 with the pixel ring staged through tensor memory
+    // variant 9 without any shared-memory staging: ld.global.nc into registers, three chunks in flight per
+    // thread.  Measured at C2 (round 2): 4.82 / 4.83 / 4.67 ms with 1 / 2 / 3 chunks in flight against 4.42
+    // for variant 9 -- a global load costs the L1 pipe more than the TMA write + LDS it replaces.  Kept as a
+    // tested variant (the deepest one), not a default.
+    case 11: return a.term_tab != nullptr ? launch_t<P_U16G, false, 16, true, false, true, 3>(a, st) : launch_t<P_U16G, false, 16, true>(a, st);
     default:  // variant 0: TMA ring, bank swizzle, persistent CTAs with the fast epilogue
       return a.dumpJ != nullptr ? launch_persistent<true, false, true>(a, st) : launch_persistent<true, false>(a, st);
   }

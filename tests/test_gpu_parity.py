@@ -13,7 +13,7 @@ from orbslam2_nmi_b200.capi import Grid
 pytestmark = pytest.mark.gpu
 
 SCORE_RTOL = 1e-5  # north_star: "NMI scores must match within 1e-5 relative"
-HIST_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10]  # storage policy x TMA/LDG x 16/32 warps x swizzle; 0 = persistent CTAs + fast epilogue, 8 = one CTA per pair + warp-per-row epilogue, 9 = one CTA per pair + fast epilogue, 10 = 0 with the pixel ring staged through tensor memory (hist.cu)
+HIST_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]  # storage policy x TMA/LDG x 16/32 warps x swizzle; 0 = persistent CTAs + fast epilogue, 8 = one CTA per pair + warp-per-row epilogue, 9 = one CTA per pair + fast epilogue, 10 = 0 with the pixel ring staged through tensor memory, 11 = 9 with ld.global.nc into registers (three chunks in flight) instead of the TMA ring (hist.cu)
 
 
 @pytest.fixture(scope="module")

@@ -5,10 +5,11 @@
 //
 // Round-2 rewrite: round 1 seeded an LCG with threadIdx.x * constant, so the 32 lanes of a warp
 // walked an arithmetic progression -- its "random" case was close to conflict-free (12.3 lanes/clk
-// vs 12.8 for distinct banks).  Here every index is an independent hash of (thread, iteration)
-// (lowbias32), the hash cost alone is measured as a control, and the cases that matter for the
-// histogram kernel are separate: conflict-free, uniformly random words, the kernel's own
-// packed-u16 + swizzle + return-value pattern, and that pattern with the LDS.128 staging reads.
+// vs 12.8 for distinct banks).  Here every lane owns an independently seeded stream, address
+// generation costs one IMAD per index so that the ATOMS pipe and not the issue port bounds every
+// case, and the cases that matter for the histogram kernel are separate: conflict-free, 2-way /
+// 4-way conflicts, uniformly random words, the kernel's own packed-u16 + swizzle + return-value
+// pattern, and that pattern with the LDS.128 staging reads.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -18,7 +19,7 @@ constexpr int kWords = 32768;  // 128 KiB, the joint histogram of hist.cu
 constexpr int kIters = 4096;
 
 enum Mode { HASH_ONLY = 0, DISTINCT_BANKS, RANDOM, RANDOM_RET, SAME_ADDR, SAME_BANK_DIFF_ADDR, TWO_WAY, HALF_WARP_RANDOM,
-            HIST_PATTERN, HIST_PATTERN_LDS, RANDOM_RED, NMODES };
+            HIST_PATTERN, HIST_PATTERN_LDS, RANDOM_RED, FOUR_WAY, NMODES };
 const char* kNames[] = {"control: hash only, no atomics",
                         "distinct banks (lane = bank), random rows",
                         "uniformly random words (independent per lane)",
@@ -29,7 +30,8 @@ const char* kNames[] = {"control: hash only, no atomics",
                         "16 active lanes, random words",
                         "hist.cu pattern: packed u16 + XOR swizzle + return + OR-check",
                         "hist.cu pattern + 2 LDS.128 of staged pixels per 16 atomics",
-                        "uniformly random words, red.shared (no return)"};
+                        "uniformly random words, red.shared (no return)",
+                        "4-way: lanes l, l+8, l+16, l+24 same bank, different rows"};
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {  // lowbias32
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
@@ -87,9 +89,15 @@ __global__ void __launch_bounds__(1024, 1) k_atoms(uint32_t* out, long long* cyc
       if (orv & 0xF000F000u) acc++;
     }
   } else {
+    // One IMAD per index (a multiplicative-congruential stream per thread, seeds hashed independently per
+    // lane; the index is taken from the well-mixed high bits), so that the loop is bound by the ATOMS
+    // pipe and not by generating addresses: with a full hash per index (first version of this file)
+    // every mode but the serialised one sat at the issue limit the HASH_ONLY control shows.
+    uint32_t x = hash32(gtid) | 1u;
 #pragma unroll 8
     for (int it = 0; it < kIters; it++) {
-      const uint32_t r = hash32(gtid * 4099u + (uint32_t)it * 0x9E3779B9u);
+      x = x * 0x9E3779B1u + 0x7F4A7C15u;
+      const uint32_t r = MODE == HASH_ONLY ? hash32(x) : x;
       if (MODE == HASH_ONLY) {
         acc ^= r;
       } else if (MODE == DISTINCT_BANKS) {
@@ -101,11 +109,13 @@ __global__ void __launch_bounds__(1024, 1) k_atoms(uint32_t* out, long long* cyc
       } else if (MODE == RANDOM_RET) {
         acc |= atomicAdd(&h[r >> 17], 1u);
       } else if (MODE == SAME_ADDR) {
-        atomicAdd(&h[__shfl_sync(0xffffffffu, r, 0) >> 17], 1u);
+        atomicAdd(&h[(it * 37) & (kWords - 1)], 1u);   // warp-uniform address, no shuffle needed
       } else if (MODE == SAME_BANK_DIFF_ADDR) {
         atomicAdd(&h[(r >> 22) << 5], 1u);
       } else if (MODE == TWO_WAY) {
         atomicAdd(&h[((r >> 22) << 5) + (lane & 15u)], 1u);
+      } else if (MODE == FOUR_WAY) {
+        atomicAdd(&h[((r >> 22) << 5) + (lane & 7u)], 1u);
       } else if (MODE == HALF_WARP_RANDOM) {
         if (lane < 16) atomicAdd(&h[r >> 17], 1u);
       }
@@ -162,6 +172,7 @@ int main() {
   run<SAME_ADDR>(512, sms, d_out, d_cyc);
   run<SAME_BANK_DIFF_ADDR>(512, sms, d_out, d_cyc);
   run<TWO_WAY>(512, sms, d_out, d_cyc);
+  run<FOUR_WAY>(512, sms, d_out, d_cyc);
   run<HALF_WARP_RANDOM>(512, sms, d_out, d_cyc);
   run<HIST_PATTERN>(512, sms, d_out, d_cyc);
   run<HIST_PATTERN>(1024, sms, d_out, d_cyc);
