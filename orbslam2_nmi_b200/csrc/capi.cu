@@ -228,6 +228,7 @@ struct nmi_ctx {
   DevBuf<uint8_t> one_render, one_warp;
   DevBuf<uint32_t> winners, dumpJ, dumpH;
   DevBuf<float> one_score;
+  float* h_score = nullptr;  // pinned and device-visible: a single evaluation's kernel stores its score here, no copy call
   DevBuf<int2> zero_pair;  // device int2 {0,0}: the pair list of a single evaluation
 
   // last search
@@ -731,6 +732,7 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   CK(cudaEventCreateWithFlags(&c->ev_hot, cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_feedback, 8 * sizeof(uint32_t)));
   memset(c->h_feedback, 0, 8 * sizeof(uint32_t));
+  CK(cudaMallocHost(&c->h_score, 4 * sizeof(float)));
   CK(c->counter.reserve(1));
   CK(c->key.reserve(1));
   CK(c->one_score.reserve(1));
@@ -763,6 +765,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
     if (c->ev_frame[i]) cudaEventDestroy(c->ev_frame[i]);
   }
   if (c->h_params) cudaFreeHost(c->h_params);
+  if (c->h_score) cudaFreeHost(c->h_score);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->ev_params) cudaEventDestroy(c->ev_params);
   if (c->ev_feedback) cudaEventDestroy(c->ev_feedback);
@@ -1203,7 +1206,10 @@ static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped,
   a.bg = f->bg;
   a.mode = f->score_mode;
   a.variant = f->variant;
-  a.scores = c->one_score.p;
+  // with a host destination the kernel writes the score straight into pinned host memory (one store over PCIe
+  // instead of a copy call after the kernel: several microseconds of a 40 us call)
+  a.scores = score_host ? c->h_score : c->one_score.p;
+  a.force_batched = path == 1;  // path 1 = the persistent build a search launches, not the single-evaluation cluster kernel
   if (int rc = ensure_term_table(c, npix)) return rc;
   a.term_tab = c->term_tab.p;
   if (J || HA || HB) {
@@ -1215,22 +1221,25 @@ static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped,
   }
   if (path != 1 && (c->hist_skip != 0 || path == 2) && f->bins == 256 && f->bg && ((uintptr_t)render % 16) == 0 &&
       ((uintptr_t)warped % 16) == 0) {
-    // single evaluation: always the build with the side tables, the kernel decides
-    CK(c->img_mode.reserve(2));
-    CK(c->hot.reserve(2));
-    launch_image_modes(render, 0, 1, warped, 0, 1, npix, c->img_mode.p, c->hot.p, c->stream);
-    a.img_mode = c->img_mode.p;
-    a.sample_total = image_mode_sample_total(npix);
-    a.nrenders = 1;
     a.skip_mode = path == 2 ? 2 : c->hist_skip;
     a.skipcap = true;
+    a.nrenders = 1;
+    if (hist_uses_cluster(a)) {
+      a.sample_in_kernel = true;  // the cluster kernel samples the two dominant grey levels itself: one launch per call
+    } else {
+      // single evaluation: always the build with the side tables, the kernel decides
+      CK(c->img_mode.reserve(2));
+      CK(c->hot.reserve(2));
+      launch_image_modes(render, 0, 1, warped, 0, 1, npix, c->img_mode.p, c->hot.p, c->stream);
+      a.img_mode = c->img_mode.p;
+      a.sample_total = image_mode_sample_total(npix);
+    }
   }
   REQUIRE(launch_joint_hist_score(a, c->stream) >= 0, NMI_ERR_CUDA,
           "histogram kernel configuration failed");
   CK(cudaGetLastError());
-  if (score_host)
-    CK(cudaMemcpyAsync(score_host, c->one_score.p, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (score_host) *score_host = c->h_score[0];
   return NMI_OK;
 }
 

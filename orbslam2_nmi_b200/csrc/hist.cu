@@ -1227,6 +1227,384 @@ joint_hist_score_tmem_kernel(const HistArgs a) {
   asm volatile("bar.arrive 2, %0;" ::"n"(kConsumers + 32));  // lets the issuer warp free the TMEM columns
 }
 
+
+// ---- one evaluation on a CLUSTER of eight CTAs (the single-evaluation entry points) ------------------
+// CUDAF::NMIWithCuda_noMask scores ONE (render, warp) pair per call (kernel.cu:49-114); with one CTA per
+// evaluation that call used 1 of 148 SMs: 36 us for a 752x480 pair.  Here the pair is split over a
+// thread-block cluster: CTA r takes the chunks r, r + 8, ... into its own packed-u16 partial histogram
+// (the same TMA ring, hot loop, crossing / repay scheme and side tables as above), then the partials are
+// reduced through DISTRIBUTED SHARED MEMORY: CTA r owns render levels 32 r .. 32 r + 31, sums the eight
+// partial rows with ld.shared::cluster (uint4, sixteen threads per row), adds the repaid crossings and
+// the side tables, turns the 256 counts of a row into entropy terms and walks the reference's pairwise
+// tree (strides 128..16 between the sixteen threads of a row with shfl.xor, 8..1 inside a thread: pairing
+// b with b ^ stride at every level, in the reference's level order -- the swizzle only relabels the leaves
+// by an XOR, and fp32 addition is commutative, so the sums keep their bits).  CTA 0 finally collects the
+// 256 row sums and the marginals over DSMEM and forms the score.  Integers, terms, trees and score are
+// the ones every other build produces (same parity tests).
+constexpr int kClusterCtas = 8;
+#ifdef NMI_CLUSTER_TIMING  // experiment build: phase timestamps of cluster 0 / CTA 0 / thread 0 (globaltimer, ns)
+#define NMI_CT(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__)); ct__[i] = t__; } } while (0)
+#else
+#define NMI_CT(i) do { } while (0)
+#endif
+__device__ __forceinline__ void im_count16(uint32_t* h, const uint4 v, bool valid);  // defined with image_mode_kernel below
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldc_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ldc_f32(uint32_t addr) { return __uint_as_float(ldc_u32(addr)); }
+
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(16 * 32 + 32, 1)
+joint_hist_score_cluster_kernel(const HistArgs a) {
+  constexpr int NWARPS = 16;
+  constexpr int kConsumers = NWARPS * 32;
+  constexpr int kThreads = kConsumers + 32;
+  constexpr int PIX = kChunk / kConsumers;  // 16 pixels per thread and chunk
+  constexpr int NW = PIX / 4;
+  constexpr bool SWZ = true;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  SmemSkip& sk = *reinterpret_cast<SmemSkip*>(smem_raw + sizeof(Smem));
+  uint32_t* extra = reinterpret_cast<uint32_t*>(sm.rbuf);  // [32][256] u32 after the pixel loop: +4096 per repaid crossing
+  unsigned long long* rx = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(Smem) + sizeof(SmemSkip));  // reduce-add arrivals
+  constexpr uint32_t kSliceBytes = 32u * 128u * 4u;  // the 32 render levels one CTA owns: 16 KiB of packed words
+  static_assert(sizeof(sm.rbuf) >= 32 * 256 * sizeof(uint32_t), "the ring's render half holds the crossing table");
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+#ifdef NMI_CLUSTER_TIMING
+  unsigned long long ct__[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+  NMI_CT(0);
+  const uint32_t rank = cluster_rank();
+  const int pi = blockIdx.x / kClusterCtas;  // evaluation of this cluster
+  const int2 pr = a.pairs[pi];
+  const uint8_t* __restrict__ rimg = a.renders + (size_t)pr.x * a.render_pitch;
+  const uint8_t* __restrict__ wimg = a.warps + (size_t)pr.y * a.warp_pitch;
+  const uint32_t npix = a.npix;
+  const int nchunks = (int)((npix + kChunk - 1) / kChunk);
+  const int mine = nchunks > (int)rank ? (nchunks - (int)rank + kClusterCtas - 1) / kClusterCtas : 0;  // chunks of this CTA
+  const bool dump = a.dumpJ != nullptr && pi == a.dump_pair;
+
+  {
+    uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+    for (int i = tid; i < kHistWords / 4; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 256) sm.HB[tid] = 0;
+    for (int i = tid; i < 2 * kSkipCopies * 256; i += kThreads) (&sk.n1[0][0])[i] = 0;
+    if (tid == 0) sk.nboth = 0;
+    for (int i = tid; i < kTermTab && (uint32_t)i <= a.length; i += kThreads) sm.term_tab[i] = __ldg(a.term_tab + i);
+    if (tid == 0) {
+      sm.ev_count = 0;
+      for (int s = 0; s < kStages; s++) {
+        mbar_init(&sm.full[s], 1);
+        mbar_init(&sm.empty[s], NWARPS);
+      }
+      mbar_init(rx, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(rx, (kClusterCtas - 1) * kSliceBytes);  // seven partial slices will be added into this CTA's own
+    }
+  }
+  // hot-bin skipping: the sampled most frequent grey level of either image decides (CTA-uniform).  Either from
+  // image_mode_kernel (a.img_mode), or -- a single call must not pay two more launches for it -- sampled right
+  // here: every CTA takes the same 1/64 of the pixels image_mode_kernel takes (a few KB), into two 256-bin tables
+  // that live in sm.HA / sm.rowE until the reduce phase needs those arrays.
+  uint32_t skipT = 0xFFFFFFFFu;
+  if (a.img_mode != nullptr && a.bg && a.skip_mode != 0) {
+    const uint32_t ka = __ldg(a.img_mode + pr.x), kb = __ldg(a.img_mode + a.nrenders + pr.y);
+    if (a.skip_mode == 2 || ((unsigned long long)(ka >> 8) + (kb >> 8)) * 6ull >= a.sample_total)
+      skipT = ((ka & 0xFFu) << 8) | (kb & 0xFFu);
+  } else if (a.sample_in_kernel && a.bg && a.skip_mode != 0) {
+    uint32_t* hr = sm.HA;
+    uint32_t* hw = reinterpret_cast<uint32_t*>(sm.rowE);
+    uint32_t* best = reinterpret_cast<uint32_t*>(sm.sums);  // [0] render, [1] warp: count << 8 | 255 - level
+    if (tid < 256) hr[tid] = hw[tid] = 0;
+    if (tid < 2) best[tid] = 0;
+    __syncthreads();
+    const uint32_t ngroups = npix / 16, nsamp = (ngroups + 63) / 64;
+    const uint4* r4 = reinterpret_cast<const uint4*>(rimg);
+    const uint4* w4 = reinterpret_cast<const uint4*>(wimg);
+    for (uint32_t i0 = 0; i0 < nsamp; i0 += kThreads - 32) {  // warp-uniform trip count (im_count16 votes)
+      const uint32_t i = i0 + (uint32_t)tid;
+      const bool valid = tid < kConsumers && i < nsamp && (size_t)i * 64 < ngroups;
+      const uint4 vr = valid ? __ldg(r4 + (size_t)i * 64) : make_uint4(0, 0, 0, 0);
+      const uint4 vw = valid ? __ldg(w4 + (size_t)i * 64) : make_uint4(0, 0, 0, 0);
+      im_count16(hr, vr, valid);
+      im_count16(hw, vw, valid);
+    }
+    __syncthreads();
+    if (tid < 256) {
+      atomicMax(&best[0], (hr[tid] << 8) | (255u - (uint32_t)tid));  // largest count, lowest level among equals
+      atomicMax(&best[1], (hw[tid] << 8) | (255u - (uint32_t)tid));
+    }
+    __syncthreads();
+    const uint32_t ka = best[0], kb = best[1];
+    const uint32_t total = nsamp * 16u;  // == image_mode_sample_total(npix)
+    if (a.skip_mode == 2 || ((unsigned long long)(ka >> 8) + (kb >> 8)) * 6ull >= total)
+      skipT = ((255u - (ka & 0xFFu)) << 8) | (255u - (kb & 0xFFu));
+  }
+  const bool skip = skipT != 0xFFFFFFFFu;
+  const uint32_t a4 = ((skipT >> 8) & 0xFFu) * 0x01010101u, b4 = (skipT & 0xFFu) * 0x01010101u;
+  __syncthreads();
+  NMI_CT(1);  // init + mode sampling done
+
+  if (warp == NWARPS) {
+    // ===== producer warp: this CTA's chunks through the TMA ring =====
+    if (lane == 0) {
+      for (int kk = 0; kk < mine; kk++) {
+        const int st = kk % kStages;
+        if (kk >= kStages) mbar_wait(&sm.empty[st], ((kk / kStages) - 1) & 1);
+        const uint32_t off = (uint32_t)(rank + (uint32_t)kk * kClusterCtas) * kChunk;
+        uint32_t bytes = npix - off;
+        bytes = bytes > (uint32_t)kChunk ? (uint32_t)kChunk : ((bytes + 15u) & ~15u);
+        mbar_expect_tx(&sm.full[st], 2 * bytes);
+        tma_load_1d(sm.rbuf[st], rimg + off, bytes, &sm.full[st]);
+        tma_load_1d(sm.wbuf[st], wimg + off, bytes, &sm.full[st]);
+      }
+    }
+    __syncwarp();  // the cluster barriers below are warp-aligned
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (this warp zeroed part of the histogram)
+  } else {
+    // ===== consumers: the pixel loop of the persistent build over this CTA's chunks =====
+    uint32_t nboth = 0;
+    for (int kk = 0; kk < mine; kk++) {
+      const int st = kk % kStages;
+      const uint32_t off = (uint32_t)(rank + (uint32_t)kk * kClusterCtas) * kChunk + (uint32_t)tid * PIX;
+      uint32_t r[NW], w[NW];
+      mbar_wait(&sm.full[st], (kk / kStages) & 1);
+      load_words<NW>(r, sm.rbuf[st] + tid * PIX);
+      load_words<NW>(w, sm.wbuf[st] + tid * PIX);
+      const int nvalid = off >= npix ? 0 : (int)min((uint32_t)PIX, npix - off);
+      if (nvalid == PIX && a.bg) {
+        if (!skip) {
+          accum_fast<P_U16G, SWZ, NW>(sm, r, w, 0, warp);
+        } else {
+          uint32_t dr = 0, dw = 0;
+#pragma unroll
+          for (int j = 0; j < NW; j++) {
+            dr |= r[j] ^ a4;
+            dw |= w[j] ^ b4;
+          }
+          if (dr != 0u && dw != 0u) {
+            accum_fast<P_U16G, SWZ, NW>(sm, r, w, 0, warp);
+          } else if (dr == 0u && dw == 0u) {
+            nboth += PIX;
+          } else {
+            const uint32_t (&x)[NW] = dr == 0u ? w : r;
+            const uint32_t base = smem_u32(dr == 0u ? sk.n1[warp & (kSkipCopies - 1)] : sk.n2[warp & (kSkipCopies - 1)]);
+#pragma unroll
+            for (int i = 0; i < PIX; i++) {
+              const uint32_t v = __byte_perm(x[i >> 2], 0u, 0x4440 + (i & 3));
+              asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + v * 4u) : "memory");
+            }
+          }
+        }
+      } else if (nvalid > 0) {
+        accum_slow<P_U16G, SWZ, NW>(sm, r, w, nvalid, a.bg, 0, warp);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[st]);
+    }
+    if (skip) {  // fold the side tables into copy 0
+      if (nboth) atomicAdd(&sk.nboth, nboth);
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+      for (int i = tid; i < 512; i += kConsumers) {
+        uint32_t* t0 = i < 256 ? &sk.n1[0][i] : &sk.n2[0][i - 256];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int c = 0; c < kSkipCopies; c++) sum += t0[c * 256];
+        *t0 = sum;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's increments, before the bulk engine reads or adds to them
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // every increment of this CTA has landed, the ring is idle
+    for (int i = tid; i < 32 * 256; i += kConsumers) extra[i] = 0;
+    NMI_CT(2);  // pixel loop done
+  }
+  cluster_sync_all();  // C1: all eight partial histograms, event lists and side tables are complete
+
+  NMI_CT(3);  // cluster barrier 1 passed
+  if (warp < NWARPS) {
+    // ---- the partial histograms: CTA r ADDS its slice of rows 32 c .. 32 c + 31 into CTA c's own copy of that slice
+    //      with one bulk reduce per destination (cp.reduce.async.bulk .add.u32 through the cluster's shared-memory
+    //      network, completion counted in bytes on the destination's mbarrier).  Packed fields are < 4096 once every
+    //      crossing is repaid, so eight of them add without a carry into the neighbouring field, and the swizzle
+    //      depends on the row alone: word for word the same layout in all eight CTAs.
+    if (warp < kClusterCtas && (uint32_t)warp != rank && lane == 0) {
+      const uint32_t dst_cta = (uint32_t)warp;
+      const uint32_t src = smem_u32(sm.hist) + dst_cta * kSliceBytes;
+      asm volatile(
+          "cp.reduce.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes.add.u32 [%0], [%1], %2, [%3];" ::
+              "r"(map_to_cta(sm.hist, dst_cta) + dst_cta * kSliceBytes),
+          "r"(src), "r"(kSliceBytes), "r"(map_to_cta(rx, dst_cta))
+          : "memory");
+    }
+    // ---- what is not in the packed words, into extra[local row][b] (u32): +4096 per repaid crossing of a row this
+    //      CTA owns (all eight event lists), and the pixels the hot-bin side tables kept out of the histogram:
+    //      n1 -> row a*, n2 -> column b*, nboth -> (a*, b*), summed over the eight CTAs.  Rolled loops, few threads.
+    uint32_t nevs[kClusterCtas], nev_all = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < (uint32_t)kClusterCtas; c++) nevs[c] = ldc_u32(map_to_cta(&sm.ev_count, c));  // eight loads in flight
+#pragma unroll
+    for (uint32_t c = 0; c < (uint32_t)kClusterCtas; c++) {
+      nevs[c] = min(nevs[c], (uint32_t)kEvCap);
+      nev_all += nevs[c];
+    }
+    if (nev_all != 0u) {  // CTA-uniform; most pairs have no bin above 4095 counts per CTA
+#pragma unroll 1
+      for (uint32_t c = 0; c < (uint32_t)kClusterCtas; c++) {
+        const uint32_t evl = map_to_cta(sm.ev_list, c);
+        for (uint32_t e = tid; e < nevs[c]; e += kConsumers) {
+          const uint32_t word = ldc_u32(evl + (e >> 1) * 4u);  // two 16-bit entries per word
+          const uint32_t t = (e & 1u) ? (word >> 16) : (word & 0xFFFFu);
+          if ((t >> 13) == rank) atomicAdd(&extra[((t >> 8) & 31u) * 256u + (t & 0xFFu)], 4096u);
+        }
+      }
+    }
+    if (skip) {
+      const uint32_t astar = (skipT >> 8) & 0xFFu, bstar = skipT & 0xFFu;
+      if ((astar >> 5) == rank && tid < 256) {  // row a* lives here: its b-histogram of skipped pixels
+        uint32_t n1 = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < (uint32_t)kClusterCtas; q++) n1 += ldc_u32(map_to_cta(&sk.n1[0][tid], q));
+        if (n1) atomicAdd(&extra[(astar & 31u) * 256u + (uint32_t)tid], n1);
+      }
+      if (tid >= 256 && tid < 288) {  // column b* of this CTA's 32 rows
+        const uint32_t row = rank * 32u + (uint32_t)(tid - 256);
+        uint32_t n2 = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < (uint32_t)kClusterCtas; q++) n2 += ldc_u32(map_to_cta(&sk.n2[0][row], q));
+        if (row == astar) {
+#pragma unroll
+          for (uint32_t q = 0; q < (uint32_t)kClusterCtas; q++) n2 += ldc_u32(map_to_cta(&sk.nboth, q));
+        }
+        if (n2) atomicAdd(&extra[(row & 31u) * 256u + bstar], n2);
+      }
+    }
+    const bool use_extra = nev_all != 0u || skip;  // CTA-uniform
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
+    // ---- row = 32 rank + tid / 16; the thread sums physical words 8u .. 8u + 7 of that row over the CTAs ----
+    const uint32_t row = rank * 32u + ((uint32_t)tid >> 4), u = (uint32_t)tid & 15u;
+    const uint32_t cr = row & 0x7Fu;                      // swizzle: logical word m = physical ^ cr
+    const uint32_t pbase = ((row << 7) | (8u * u)) * 4u;  // byte offset of the thread's first physical word
+    uint32_t cnt[16];
+    mbar_wait(rx, 0);  // the seven other partial slices have been added into this CTA's own
+    {
+      const uint4* hp = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(sm.hist) + pbase);
+      const uint4 v0 = hp[0], v1 = hp[1];
+      const uint32_t wv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        cnt[2 * j] = wv[j] & 0xFFFFu;
+        cnt[2 * j + 1] = wv[j] >> 16;
+      }
+    }
+    uint32_t rs = 0;
+    float v[16];
+    const uint32_t* ex_row = extra + ((uint32_t)tid >> 4) * 256u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const uint32_t b = 2u * ((8u * u + (uint32_t)(i >> 1)) ^ cr) + (uint32_t)(i & 1);  // the camera level this register counts
+      uint32_t c = cnt[i];
+      if (use_extra) c += ex_row[b];
+      rs += c;
+      if (dump) a.dumpJ[row * 256u + b] = c;
+      v[i] = term_lut(sm.term_tab, a.term_tab, c);  // tables only (the dispatcher requires the per-size table)
+    }
+    // the reference's tree over the 256 terms of the row (NMI.cu:270-287): strides 128, 64, 32, 16 pair the
+    // sixteen threads of the row (bits 3..0 of the word group), 8, 4, 2, 1 pair registers (bits 3..1 of the word
+    // inside the group, then the two halves of a word)
+#pragma unroll
+    for (int d = 8; d >= 1; d /= 2)
+#pragma unroll
+      for (int i = 0; i < 16; i++) v[i] = __fadd_rn(v[i], __shfl_xor_sync(0xffffffffu, v[i], d));
+#pragma unroll
+    for (int h = 8; h >= 1; h /= 2)
+#pragma unroll
+      for (int i = 0; i < h; i++) v[i] = __fadd_rn(v[i], v[i + h]);
+#pragma unroll
+    for (int d = 8; d >= 1; d /= 2) rs += __shfl_xor_sync(0xffffffffu, rs, d);
+    if (u == 0u) {
+      sm.rowE[row] = v[0];
+      sm.HA[row] = rs;
+    }
+    {
+      // this CTA's share of the camera marginal: column sums over its 32 rows.  Thread -> logical word tid & 127
+      // (camera levels 2 m, 2 m + 1) of eight rows; consecutive lanes read consecutive (XOR-permuted) words.
+      const uint32_t m = (uint32_t)tid & 127u, g = (uint32_t)tid >> 7;
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 8u; k++) {
+        const uint32_t lr = 8u * g + k, r = rank * 32u + lr;
+        const uint32_t wv = sm.hist[(r << 7) | (m ^ (r & 0x7Fu))];
+        lo += wv & 0xFFFFu;
+        hi += wv >> 16;
+        if (use_extra) {
+          const uint2 e = *reinterpret_cast<const uint2*>(extra + lr * 256u + 2u * m);
+          lo += e.x;
+          hi += e.y;
+        }
+      }
+      atomicAdd(&sm.HB[2u * m], lo);
+      atomicAdd(&sm.HB[2u * m + 1u], hi);
+    }
+    NMI_CT(4);  // reduce + row trees done
+  }
+  cluster_sync_all();  // C2: every CTA's 32 row sums / render marginals and its share of the camera marginal are final
+
+  NMI_CT(5);  // cluster barrier 2 passed
+  if (rank == 0 && warp < 3) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t i = (uint32_t)lane + 32u * (uint32_t)k, owner = i >> 5;
+      if (warp == 0) {
+        v[k] = ldc_f32(map_to_cta(&sm.rowE[i], owner));
+      } else if (warp == 1) {
+        const uint32_t ha = ldc_u32(map_to_cta(&sm.HA[i], owner));
+        v[k] = term_lut(sm.term_tab, a.term_tab, ha);
+        if (dump) a.dumpHA[i] = ha;
+      } else {
+        uint32_t hb = 0;
+#pragma unroll
+        for (uint32_t c = 0; c < (uint32_t)kClusterCtas; c++) hb += ldc_u32(map_to_cta(&sm.HB[i], c));
+        v[k] = term_lut(sm.term_tab, a.term_tab, hb);
+        if (dump) a.dumpHB[i] = hb;
+      }
+    }
+    const float s = tree_lanes<8>(v);
+    if (lane == 0) sm.sums[warp] = s;
+  }
+  __syncthreads();
+  if (rank == 0 && tid == 0)
+    a.scores[a.out_index ? a.out_index[pi] : pi] = finish_score(sm.sums[1], sm.sums[2], sm.sums[0], a.mode);
+  NMI_CT(6);
+  cluster_sync_all();  // C3: nobody leaves while CTA 0 may still be reading its shared memory
+#ifdef NMI_CLUSTER_TIMING
+  NMI_CT(7);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    printf("[cluster ns] init+sample %llu | pixels %llu | C1 %llu | reduce %llu | C2 %llu | final %llu | C3 %llu | total %llu\n",
+           ct__[1] - ct__[0], ct__[2] - ct__[1], ct__[3] - ct__[2], ct__[4] - ct__[3], ct__[5] - ct__[4], ct__[6] - ct__[5],
+           ct__[7] - ct__[6], ct__[7] - ct__[0]);
+#endif
+}
+
 // e(c) for every count 0..length (counts cannot exceed the pixel count)
 __global__ void term_table_kernel(float* __restrict__ tab, uint32_t length) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1354,6 +1732,20 @@ int launch_tmem(const HistArgs& a, cudaStream_t st) {
   return 1;
 }
 
+int launch_cluster(const HistArgs& a, cudaStream_t st) {
+  auto kern = joint_hist_score_cluster_kernel;
+  constexpr size_t smem = sizeof(Smem) + sizeof(SmemSkip) + 16;  // + the mbarrier the partial slices arrive on
+  static bool configured[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  if (!configured[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured[dev] = true;
+  }
+  kern<<<a.npairs * kClusterCtas, 16 * 32 + 32, smem, st>>>(a);
+  return 1;
+}
+
 }  // namespace
 
 void launch_term_table(float* tab, uint32_t length, cudaStream_t st) {
@@ -1371,8 +1763,20 @@ int launch_image_modes(const uint8_t* renders, size_t rpitch, int nr, const uint
   return 1;
 }
 
+// a handful of evaluations (the per-pair drop-in, tiny grids): one 8-CTA cluster per evaluation instead of
+// one CTA -- $NMI_EVAL_CLUSTER=0 keeps the one-CTA builds (A/B switch)
+bool hist_uses_cluster(const HistArgs& a) {
+  static const bool use_cluster = [] {
+    const char* e = getenv("NMI_EVAL_CLUSTER");
+    return !(e && atoi(e) == 0);
+  }();
+  return use_cluster && !a.force_batched && a.bins == 256 && a.variant == 0 && a.npairs >= 1 &&
+         a.npairs * kClusterCtas <= 64 && a.term_tab != nullptr && a.npix >= (uint32_t)(2 * kChunk);
+}
+
 int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
   if (a.npairs <= 0) return 0;
+  if (hist_uses_cluster(a)) return launch_cluster(a, st);
   if (a.bins == 256 && a.skipcap && a.bg && a.img_mode != nullptr) {
     switch (a.variant) {  // the packed-u16 builds that carry the side tables
       case 0: case 8: case 9: return launch_t<P_U16G, true, 16, true, true>(a, st);

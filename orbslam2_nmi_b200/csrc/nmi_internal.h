@@ -69,7 +69,14 @@ struct HistArgs {
   uint32_t* dumpHA;
   uint32_t* dumpHB;
   int dump_pair;
+  // parity read-back of the batched build: do not route a single evaluation to the cluster kernel
+  bool force_batched;
+  // img_mode == nullptr: let the (cluster) kernel sample the two images' dominant grey levels itself
+  bool sample_in_kernel;
 };
+// true when launch_joint_hist_score will route `a` to the single-evaluation cluster kernel (which can do its
+// own mode sampling: no image_mode launch needed in front of it)
+bool hist_uses_cluster(const HistArgs& a);
 int launch_joint_hist_score(const HistArgs& a, cudaStream_t st);  // returns launches, <0 on error
 // sampled per-image modes for HistArgs::img_mode; hot[0] / hot[1] = largest sampled count over
 // the renders / the warps.  Returns launches.

@@ -195,11 +195,14 @@ class NmiSearcher:
         return int(p.value)
 
     def eval_pair(self, warped_dev: int, handle: int, flags: Flags | None = None) -> float:
-        flags = flags or self.flags()
-        s = np.zeros(1, dtype=np.float32)
+        if flags is None:
+            flags = self._default_flags = getattr(self, "_default_flags", None) or self.flags()
+        s = self._one_score = getattr(self, "_one_score", None)
+        if s is None:
+            s = self._one_score = C.c_float(0.0)
         check(self.lib.nmi_eval_pair(self.h, warped_dev, handle, self.cam.W, self.cam.H,
-                                     C.byref(flags), ptr(s)))
-        return float(s[0])
+                                     C.byref(flags), C.byref(s)))
+        return s.value
 
     def import_render(self, render_dev: int, pitch_bytes: int, bottom_up: bool = False) -> int:
         """Adopt a device image as the current render (kernel.cu:53-59's mapped GL texture)."""
