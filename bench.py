@@ -514,6 +514,44 @@ def config_c5(searcher, scene, key, rank, world, dist, frames):
     return res
 
 
+def config_c5_small_grid(searcher, scene, key, rank, world, dist, frames=60):
+    """The reference's own per-frame load (Tracking.cc:2088-2130 with the default kernel of
+    nmiSearchKernel.cpp:104-141): a 3^3 x 3^3 = 729-pose grid, up to three levels with the steps
+    halved, per frame.  Small grids are where fixed per-level costs (cull, warps, launches, the key
+    round trip) show; at N > 1 each level is sharded and combined by the 8-byte allreduce.  The
+    per-level host costs come from nmi_last_level_trace."""
+    import torch
+    from orbslam2_nmi_b200 import multigpu, synth
+    from orbslam2_nmi_b200.capi import Grid
+
+    searcher.set_frame(synth.frame_textured(scene.W, scene.H))
+    g = Grid.make((3, 3, 3), (3, 3, 3), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))
+    ms, traces, out = [], [], None
+    for k in range(frames):
+        T = scene.Twc.copy()
+        T[0, 3] += 0.01 * k
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = multigpu.relocalize_sharded(searcher, T, g, None, key, rank, world, threshold=0.0, max_iterations=3)
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms.append(float(t.item()))
+        traces.append(searcher.level_trace())
+    steady = ms[5:]
+    lv = [t for t in traces[5:] if len(t) == len(traces[-1])]
+    mean_trace = [{k2: float(np.mean([t[i][k2] for t in lv])) for k2 in lv[0][i]} for i in range(len(lv[0]))] if lv else []
+    return {"workload": f"C5 small grid: {frames} frames, coarse-to-fine 3^3 x 3^3 = 729 poses per level, 3 levels per frame, "
+                        "1920x1080 / 10M points",
+            "n_gpus": world, "scaling": "strong" if world > 1 else "n/a", "levels": int(out.iterations),
+            "evals_per_frame": int(out.n_evals), "ms_per_frame_mean": float(np.mean(steady)),
+            "ms_per_frame_median": float(np.median(steady)), "evals_per_s": out.n_evals / float(np.mean(steady)) * 1e3,
+            "per_level_rank0_us": mean_trace,
+            "timing": "wall clock around the synchronous driver call, max over ranks; per-level figures: this rank's host clock"}
+
+
 # ------------------------------------------------------------------------ GPU arm ----
 def run_gpu(args):
     import torch
@@ -627,10 +665,12 @@ def run_gpu(args):
         if world > 1:  # collectives inside: an exception on one rank must end the job, not hang the others
             configs["C4"] = config_c4(searcher, scene, key, rank, world, dist)
             configs["C5"] = config_c5(searcher, scene, key, rank, world, dist, args.frames)
+            configs["C5_small_grid"] = config_c5_small_grid(searcher, scene, key, rank, world, dist)
         else:
             for name, fn in (("C2_frames", lambda: config_c2_frames(searcher, scene, grid, flags)),
                              ("C4", lambda: config_c4(searcher, scene, key, rank, world, None)),
                              ("C5", lambda: config_c5(searcher, scene, key, rank, world, None, args.frames)),
+                             ("C5_small_grid", lambda: config_c5_small_grid(searcher, scene, key, rank, world, None)),
                              ("C1", lambda: config_c1(local)), ("C3", lambda: config_c3(local))):
                 try:
                     configs[name] = fn()

@@ -238,6 +238,12 @@ int nmi_relocalize_sharded(nmi_ctx *ctx, const float Twc[16], const nmi_grid *st
                            const nmi_flags *flags, const nmi_reloc_params *params,
                            int rank, int world, void *key_dev,
                            nmi_exchange_fn exchange, void *user, nmi_reloc_result *out);
+/* Host-side cost of level `level` (searches in launch order, retries included) of the calling
+ * thread's last nmi_relocalize_sharded, in microseconds: [0] enqueueing the level's kernels,
+ * [1] the exchange callback, [2] waiting for the 8-byte key, [3] this rank's device time.
+ * NMI_ERR_INVALID past the last level.  (No reference counterpart: Tracking.cc:2088-2130 runs
+ * its levels synchronously on one GPU.)                                               */
+int nmi_last_level_trace(int level, float out_us[4]);
 
 /* ---- stage-level entry points (the reference's own call granularity) ---- */
 /* Rendering::renderToTextureOnGPU(calculateTranslation(sx,sy,sz))

@@ -149,6 +149,7 @@ SYMBOLS = [
     ("nmi_score_pairs", C.c_int, [_P, _P, C.c_int, C.c_size_t, _P, C.c_int, C.c_size_t, C.c_int, C.c_int,
                                   C.POINTER(Flags), _P]),
     ("nmi_get_timings", C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    ("nmi_last_level_trace", C.c_int, [C.c_int, _P]),
 ]
 
 _lib = None

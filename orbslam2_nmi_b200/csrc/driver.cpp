@@ -135,6 +135,13 @@ int nmi_relocalize_with(nmi_level_search_fn search, void* user, const float Twc_
 
 namespace {
 
+// host-side cost of every level of this thread's last nmi_relocalize_sharded (nmi_last_level_trace)
+struct LevelTrace {
+  float enqueue_us, exchange_us, wait_us, device_ms;
+};
+thread_local LevelTrace g_trace[16];
+thread_local int g_trace_n = 0;
+
 struct SingleSearch {
   nmi_ctx* ctx;
   const nmi_flags* flags;
@@ -176,6 +183,8 @@ int sharded_level(void* user, const float Twc[16], const nmi_grid* grid, nmi_res
     const int rc = nmi_decode_key(grid, key, out);
     float ms[8];
     if (nmi_get_timings(s->ctx, ms, nullptr) == NMI_OK) out->gpu_ms = ms[6];  // this rank's device time
+    if (g_trace_n < 16)
+      g_trace[g_trace_n++] = LevelTrace{(float)us(t0, t1), (float)us(t1, t2), (float)us(t2, t3), out->gpu_ms};
     if (trace)
       fprintf(stderr, "[nmi level] rank %d/%d grid %dx%dx%d x %dx%dx%d: enqueue %ld us, exchange call %ld us, "
                       "wait %ld us, device %.3f ms (cull %.3f render %.3f hist %.3f)\n",
@@ -217,6 +226,7 @@ int nmi_relocalize_sharded(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid*
     return NMI_ERR_CUDA;
   }
   ShardedSearch s{ctx, flags, rank, world, key_dev, exchange, user};
+  g_trace_n = 0;
   const auto t0 = std::chrono::steady_clock::now();
   const int rc = nmi_relocalize_with(sharded_level, &s, Twc_in, start_grid, prm, out);
   if (getenv("NMI_TRACE_LEVELS"))
@@ -224,6 +234,15 @@ int nmi_relocalize_sharded(nmi_ctx* ctx, const float Twc_in[16], const nmi_grid*
             out->iterations,
             (long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count());
   return rc;
+}
+
+int nmi_last_level_trace(int level, float out_us[4]) {
+  if (level < 0 || level >= g_trace_n || !out_us) return NMI_ERR_INVALID;
+  out_us[0] = g_trace[level].enqueue_us;
+  out_us[1] = g_trace[level].exchange_us;
+  out_us[2] = g_trace[level].wait_us;
+  out_us[3] = g_trace[level].device_ms * 1e3f;
+  return NMI_OK;
 }
 
 }  // extern "C"

@@ -179,6 +179,14 @@ class NmiSearcher:
         check(rc)
         return out
 
+    def level_trace(self):
+        """Per level of this thread's last relocalize_sharded: host microseconds spent enqueueing the
+        level, in the exchange callback, waiting for the key, and this rank's device time."""
+        out, us = [], (C.c_float * 4)()
+        while self.lib.nmi_last_level_trace(len(out), us) == 0:
+            out.append({"enqueue_us": us[0], "exchange_us": us[1], "wait_us": us[2], "device_us": us[3]})
+        return out
+
     # -- stage-level API (reference call granularity) ------------------------------
     def render_cell(self, Twc, grid: Grid, sx, sy, sz) -> int:
         Twc = np.ascontiguousarray(Twc, dtype=np.float32).reshape(16)
