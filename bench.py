@@ -156,9 +156,9 @@ def roofline_block(pairs, P, hist_ms, mean_stage, hist_bytes, search_bytes, hbm_
                     "note": "algorithmic 2P bytes per evaluation / kernel time; real DRAM traffic is ~7 % of that "
                             "(inputs served from L2), so this fraction is L2 reuse, not an HBM limit"},
             "search_algorithmic_GBps": search_bytes / (mean_stage["total"] * 1e-3) / 1e9,
-            "note": "ncu: l1tex__data_pipe_lsu_wavefronts_mem_shared 91 % of peak, 3.77 wavefronts per warp-level "
-                    "ATOMS (32 random lanes over 32 banks: expected maximum multiplicity 3.5), issue slots 74 % busy "
-                    "(profiles/r01_hist_ncu_summary.txt, profiles/r02_ubench_shared_atomics.txt)"}
+            "note": "ncu: l1tex throughput 93 % of peak, 3.78 shared-memory wavefronts per warp-level ATOMS "
+                    "(32 random lanes over 32 banks: expected maximum multiplicity 3.5), 11.8 instructions per ATOMS, "
+                    "issue slots 64 % busy (profiles/r02_hist_ncu_summary.txt, profiles/r02_ubench_shared_atomics.txt)"}
 
 
 def ncu_traffic_bytes():
@@ -495,7 +495,9 @@ def config_c5(searcher, scene, key, rank, world, dist, frames):
                        "10M-point cloud, pageable frames uploaded every frame",
            "n_gpus": world, "scaling": "strong" if world > 1 else "n/a", "frames": frames,
            "ms_per_frame_mean": float(np.mean(steady)), "ms_per_frame_median": float(np.median(steady)),
-           "ms_per_frame_p99": float(np.percentile(steady, 99)), "frames_per_s": 1e3 / float(np.mean(steady)),
+           "ms_per_frame_p99": float(np.percentile(steady, 99)), "ms_per_frame_max": float(np.max(steady)),
+           "slowest_frames": [[int(i) + (3 if len(ms) > 6 else 0), float(steady[i])] for i in np.argsort(steady)[-3:][::-1]],
+           "frames_per_s": 1e3 / float(np.mean(steady)),
            "seconds_for_1000_frames": float(np.mean(steady)), "evals_per_s": g.n_pose / float(np.mean(steady)) * 1e3,
            "h2d_bytes_per_frame": int(scene.W * scene.H), "timing": "wall clock per frame (set_frame + search + key read-back), max over ranks",
            "parity": {"checker": "planted pose per frame", "frames_with_planted_winner": found,

@@ -31,10 +31,10 @@ void launch_scan_counts(uint32_t* block_counts, uint32_t nblocks, uint32_t* coun
 void launch_copy_rows(const uint8_t* src, size_t src_pitch, uint8_t* dst, int W, int H, bool flip, cudaStream_t st);
 void launch_bin_points(int mode, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
                        const float4* centres, int nviews, const ViewConst& vc, uint32_t* counts,
-                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, const BinLayout& bin_cap,
+                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t bin_cap,
                        uint32_t* overflow, cudaStream_t st);
 int tiles_per_view(int W, int H);
-void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, const BinLayout& bin_cap, const uint32_t* offsets, uint32_t* total, int nviews,
+void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, uint32_t bin_cap, const uint32_t* offsets, uint32_t* total, int nviews,
                          const ViewConst& vc, const uint8_t* val, bool packed, uint8_t* images,
                          size_t pitch, uint32_t* winners, size_t P, cudaStream_t st);
 
@@ -169,24 +169,23 @@ struct nmi_ctx {
   int tex_w = 0, tex_h = 0;  // > 0: per-fragment texture shading
 
   // feedback from the previous search, copied to pinned host memory asynchronously:
-  // [0] survivors, [1] records of the last view group, [2] overflow flag, [3] fullest class-0 sub-bin,
-  // [4] views of that group (host-written), [5..6] hot-bin sampling (below), [8..10] fullest sub-bins of
-  // the straddling classes 1..3
+  // [0] survivors, [1] records of the last view group, [2] overflow flag, [3] fullest bin,
+  // [4] views of that group (host-written)
   uint32_t* h_feedback = nullptr;
-  BinLayout bin_cap = {};  // cap_total > 0: this search bins in a single pass into sub-bins of these capacities
+  uint32_t bin_cap = 0;  // > 0: this search bins in a single pass into bins of that capacity
   cudaEvent_t ev_feedback = nullptr;
   bool feedback_pending = false;
   // fullest bins of the last searches: the single-pass bin capacity covers the fullest of them,
   // so a driver that alternates between coarse and fine levels (or a tracker whose pose jumps
   // back) does not overflow the bins sized by the one search before
   static constexpr int kFullestHist = 16;
-  uint32_t fullest_hist[kFullestHist][4] = {};  // per straddling class
+  uint32_t fullest_hist[kFullestHist] = {};
   int fullest_pos = 0;
   bool force_conservative = false;
   bool conservative_once = false;  // an enqueued search overflowed: size the next one exactly
   // binned tile renderer scratch (point clouds)
-  DevBuf<uint32_t> bin_offsets, bin_cursor;  // [views of a group * tiles * 4 classes]
-  DevBuf<uint32_t> bin_total;                // [0] records of the group, [1] overflow flag, [2] / [4..6] fullest sub-bins
+  DevBuf<uint32_t> bin_offsets, bin_cursor;  // [views of a group * tiles]
+  DevBuf<uint32_t> bin_total;                // [0] records of the group, [1] overflow flag
   DevBuf<uint4> records;
 
   DevBuf<uint8_t> frame;
@@ -286,58 +285,48 @@ int vc_point_size(const nmi_camera& cam) {
   return s < 1 ? 1 : s;
 }
 
-// Record buffer of the tile renderer: ONE 16-byte record per visible splat and view (filed under its
-// anchor's tile and straddling class, project.cu), so a group of views needs at most one record per
-// (point, view); the group shrinks until that fits 2 GiB.  The binning kernel never writes past the
-// buffer; an overflow (only the guessed sizes of steady state can) raises a flag that every
+// Record buffer of the tile renderer: one 16-byte record per (splat, tile).  A splat of
+// s <= 32 px touches at most 4 tiles but ~1.13 on average; the buffer is sized for
+// 1.5 records per (point, view) of a group and the group shrinks until that fits 2 GiB.
+// bin_scatter never writes past the buffer; an overflow raises a flag that every
 // synchronous entry point turns into an error (never a silently wrong render).
 int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   const size_t tiles = (size_t)tiles_per_view(c->cam.W, c->cam.H);
   const bool fb = c->h_feedback && !c->force_conservative && !c->conservative_once && c->feedback_pending &&
                   cudaEventQuery(c->ev_feedback) == cudaSuccess && c->h_feedback[4] > 0 &&
                   c->h_feedback[2] == 0;
-  CK(c->bin_total.reserve(8));
-  c->bin_cap = BinLayout{};
-  // (a) single pass: every sub-bin gets the capacity of the fullest sub-bin of its class in the
-  // previous searches (+25 %)
+  CK(c->bin_total.reserve(4));
+  c->bin_cap = 0;
+  // (a) single pass: every bin gets the capacity of the previous search's fullest bin (+25 %)
   if (!c->feedback_pending)  // new model / camera: the history belongs to the old one
-    for (auto& h : c->fullest_hist)
-      for (uint32_t& v : h) v = 0;
+    for (uint32_t& v : c->fullest_hist) v = 0;
   if (fb && c->h_feedback[3] > 0 && nviews <= kMaxViewsPerLaunch) {
-    uint32_t* now = c->fullest_hist[c->fullest_pos];
-    now[0] = c->h_feedback[3];
-    for (int k = 1; k < 4; k++) now[k] = c->h_feedback[7 + k];
+    c->fullest_hist[c->fullest_pos] = c->h_feedback[3];
     c->fullest_pos = (c->fullest_pos + 1) % nmi_ctx::kFullestHist;
-    BinLayout L{};
-    size_t total = 0;
-    for (int k = 0; k < 4; k++) {
-      uint32_t fullest = 0;
-      for (const auto& h : c->fullest_hist) fullest = h[k] > fullest ? h[k] : fullest;
-      size_t cap = (size_t)fullest + fullest / 4 + (k == 0 ? 32 : 16);
-      cap = (cap + 7) / 8 * 8;
-      L.cap[k] = (uint32_t)cap;
-      L.off[k] = (uint32_t)total;
-      total += cap;
-    }
-    L.cap_total = (uint32_t)total;
-    const size_t want = tiles * (size_t)nviews * total;
-    // (capacities and offsets travel as 16-bit fields inside the binning kernel)
-    if (total < 65536 && want <= (4ull << 30) / sizeof(uint4) && want < 0xFFFFFFFFull) {
+    uint32_t fullest = 0;
+    for (uint32_t v : c->fullest_hist) fullest = v > fullest ? v : fullest;
+    size_t cap = (size_t)fullest + fullest / 4 + 32;
+    cap = (cap + 7) / 8 * 8;
+    const size_t want = tiles * (size_t)nviews * cap;
+    if (want <= (4ull << 30) / sizeof(uint4) && want < 0xFFFFFFFFull) {
       if (want > c->records.cap) {
         CK(cudaStreamSynchronize(c->stream));
         CK(c->records.reserve(want));
       }
-      c->bin_cap = L;
+      c->bin_cap = (uint32_t)cap;
       *group = nviews;
-      CK(c->bin_cursor.reserve(4 * tiles * (size_t)nviews));
-      CK(cudaMemsetAsync(c->bin_total.p, 0, 8 * sizeof(uint32_t), c->stream));
+      CK(c->bin_cursor.reserve(tiles * (size_t)nviews));
+      CK(cudaMemsetAsync(c->bin_total.p, 0, 4 * sizeof(uint32_t), c->stream));
       return NMI_OK;
     }
   }
-  // (b) two-pass counting sort; record buffer sized for any pose (one record per point and
+  // (b) two-pass counting sort; record buffer sized for any pose (1.5 records per point and
   // view) or, in steady state, from what the previous search really produced (x1.5)
   const size_t cap_records = (2ull << 30) / sizeof(uint4);
-  size_t per_view = (size_t)c->n_pts + 65536;
+  // records per (point, view): a splat of s px touches (1 + (s-1)/32)^2 tiles on average, 4 at most
+  const double sps = (double)(vc_point_size(c->cam) - 1) / 32.0;
+  const double tiles_per_splat = std::min(4.0, (1.0 + sps) * (1.0 + sps)) * 1.35 + 0.15;  // 1.5 for s = 3
+  size_t per_view = (size_t)((double)c->n_pts * tiles_per_splat) + 65536;
   if (fb && c->h_feedback[1] > 0) {  // ([1] is only filled by a two-pass search)
     const size_t seen = (size_t)c->h_feedback[1] / c->h_feedback[4];
     const size_t guess = seen + seen / 2 + 65536;
@@ -348,7 +337,7 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   if (g > nviews) g = nviews;
   if (g > kMaxViewsPerLaunch) g = kMaxViewsPerLaunch;
   *group = g;
-  const size_t nbins = 4 * (size_t)g * tiles;  // sub-bins
+  const size_t nbins = (size_t)g * tiles;
   CK(c->bin_offsets.reserve(nbins));
   CK(c->bin_cursor.reserve(nbins));
   size_t want = per_view * (size_t)g;
@@ -357,7 +346,7 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
     CK(cudaStreamSynchronize(c->stream));
     CK(c->records.reserve(want));
   }
-  CK(cudaMemsetAsync(c->bin_total.p, 0, 8 * sizeof(uint32_t), c->stream));
+  CK(cudaMemsetAsync(c->bin_total.p, 0, 4 * sizeof(uint32_t), c->stream));
   return NMI_OK;
 }
 
@@ -444,9 +433,9 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
                uint32_t* winners) {
   if (!c->n_tris && vc.s <= 32) {
     // point cloud: binned tile renderer, no global z-buffer
-    const size_t nbins = 4 * (size_t)nviews * tiles_per_view(vc.W, vc.H);  // sub-bins: (view, tile, straddling class)
+    const size_t nbins = (size_t)nviews * tiles_per_view(vc.W, vc.H);
     CK(cudaMemsetAsync(c->bin_cursor.p, 0, nbins * sizeof(uint32_t), c->stream));
-    if (c->bin_cap.cap_total) {
+    if (c->bin_cap) {
       // steady state: the fullest bin of the previous search bounds every bin -> one pass
       launch_bin_points(2, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_cursor.p,
                         nullptr, c->records.p, (uint32_t)c->records.cap, c->bin_cap, c->bin_total.p + 1,
@@ -458,20 +447,18 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
     } else {
       CK(cudaMemsetAsync(c->bin_offsets.p, 0, nbins * sizeof(uint32_t), c->stream));
       launch_bin_points(0, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_offsets.p,
-                        nullptr, nullptr, 0, BinLayout{}, nullptr, c->stream);
+                        nullptr, nullptr, 0, 0, nullptr, c->stream);
       launch_scan_counts(c->bin_offsets.p, (uint32_t)nbins, c->bin_total.p, c->stream);
       launch_bin_points(1, c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->bin_cursor.p,
-                        c->bin_offsets.p, c->records.p, (uint32_t)c->records.cap, BinLayout{}, c->bin_total.p + 1,
+                        c->bin_offsets.p, c->records.p, (uint32_t)c->records.cap, 0, c->bin_total.p + 1,
                         c->stream);
-      launch_tile_resolve(c->records.p, (uint32_t)c->records.cap, BinLayout{}, c->bin_offsets.p, c->bin_total.p,
+      launch_tile_resolve(c->records.p, (uint32_t)c->records.cap, 0, c->bin_offsets.p, c->bin_total.p,
                           nviews, vc, c->val.p, c->packed_value, images, c->pitch, winners, c->P, c->stream);
       c->launches += 4;
     }
     if (c->h_feedback) {  // survivors / records / overflow of this group -> pinned host words
       CK(cudaMemcpyAsync(c->h_feedback, c->counter.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       CK(cudaMemcpyAsync(c->h_feedback + 1, c->bin_total.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                         c->stream));
-      CK(cudaMemcpyAsync(c->h_feedback + 8, c->bin_total.p + 4, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                          c->stream));
       c->h_feedback[4] = (uint32_t)nviews;
       CK(cudaEventRecord(c->ev_feedback, c->stream));
@@ -743,8 +730,8 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   CK(cudaEventCreateWithFlags(&c->ev_params, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_feedback, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_hot, cudaEventDisableTiming));
-  CK(cudaMallocHost(&c->h_feedback, 16 * sizeof(uint32_t)));
-  memset(c->h_feedback, 0, 16 * sizeof(uint32_t));
+  CK(cudaMallocHost(&c->h_feedback, 8 * sizeof(uint32_t)));
+  memset(c->h_feedback, 0, 8 * sizeof(uint32_t));
   CK(cudaMallocHost(&c->h_score, 4 * sizeof(float)));
   CK(c->counter.reserve(1));
   CK(c->key.reserve(1));

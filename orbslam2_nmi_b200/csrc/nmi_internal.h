@@ -18,13 +18,6 @@ struct ViewConst {
   int W, H, s;  // image size, integer point size
 };
 
-// Record layout of the tile renderer's fixed-capacity bins: every (view, tile) owns cap_total records,
-// class c (bit 0: the splat reaches into the tile to the right, bit 1: into the tile below) in
-// [off[c], off[c] + cap[c]).  cap_total == 0: counting-sort layout (offsets from a scan).
-struct BinLayout {
-  uint32_t cap[4], off[4], cap_total;
-};
-
 constexpr int kMaxViewsPerLaunch = 512;
 constexpr int kCullBlock = 1024;  // points per CTA of the cull kernels = points per load-time AABB
 constexpr size_t kImgAlign = 128;  // every render / warp image starts 128 B aligned

@@ -315,39 +315,6 @@ struct Splat {
   bool ok;
 };
 
-// IEEE quotient of two ordinary floats, two of them over one denominator.  div.rn.f32 compiles to
-// MUFU.RCP, a Newton step, the quotient and one residual correction, guarded by an FCHK and a branch
-// to a ~100-instruction slow path for operands whose exponents are extreme; when one lane of a warp
-// takes it all 32 wait.  Here the ranges are known -- the depth lies in [zn, zf], FAST says those are
-// within 2^-20 .. 2^20 -- so only the numerator is checked (zero, or 2^-60 .. 2^60 in magnitude: no
-// quotient can be denormal or overflow), and the fast path is restated instruction for instruction,
-// both quotients sharing the refined reciprocal: the same bits as __fdiv_rn.
-__device__ __forceinline__ bool numerator_ok(float a) {
-  const uint32_t e = __float_as_uint(a) & 0x7FFFFFFFu;
-  return e == 0u || (e - 0x21800000u) < 0x3C000000u;  // exponent field in [67, 187)
-}
-__device__ __forceinline__ void div2_rn(float a, float b, float d, bool fast, float& qa, float& qb) {
-  if (fast && numerator_ok(a) && numerator_ok(b)) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-    r = __fmaf_rn(r, __fmaf_rn(-d, r, 1.0f), r);
-    const float q0 = __fmaf_rn(a, r, 0.0f), q1 = __fmaf_rn(b, r, 0.0f);
-    qa = __fmaf_rn(r, __fmaf_rn(-d, q0, a), q0);
-    qb = __fmaf_rn(r, __fmaf_rn(-d, q1, b), q1);
-  } else {
-    qa = __fdiv_rn(a, d);
-    qb = __fdiv_rn(b, d);
-  }
-}
-// floor() of |x| < 2^22 as an int without the conversion unit (FRND / F2I are quarter rate): see warp.cu
-__device__ __forceinline__ int floor_to_int(float x) {
-  const float kMagic = 12582912.0f;  // 1.5 * 2^23
-  const float b = __fadd_rn(x, kMagic);  // = kMagic + rint(x), exact
-  const float r = __fsub_rn(b, kMagic);
-  return (int)(__float_as_uint(b) - 0x4B400000u) - (r > x ? 1 : 0);
-}
-
-template <bool FAST = false>  // FAST: zn, zf within 2^-20 .. 2^20 and W, H < 2^20 (checked by the launcher)
 __device__ __forceinline__ Splat project_splat_point(const float4& p, const float4& c, const ViewConst& vc,
                                                      float half) {
   Splat f;
@@ -359,41 +326,29 @@ __device__ __forceinline__ Splat project_splat_point(const float4& p, const floa
   if (!(Zc >= vc.zn && Zc <= vc.zf)) return f;
   const float Xc = __fmaf_rn(vc.r0[2], dz, __fmaf_rn(vc.r0[1], dy, __fmul_rn(vc.r0[0], dx)));
   const float Yc = __fmaf_rn(vc.r1[2], dz, __fmaf_rn(vc.r1[1], dy, __fmul_rn(vc.r1[0], dx)));
-  float nx, ny;
-  div2_rn(__fmul_rn(vc.kx, Xc), __fmul_rn(vc.ky, Yc), Zc, FAST, nx, ny);
+  const float nx = __fdiv_rn(__fmul_rn(vc.kx, Xc), Zc);
+  const float ny = __fdiv_rn(__fmul_rn(vc.ky, Yc), Zc);
   if (!(fabsf(nx) <= 1.0f && fabsf(ny) <= 1.0f)) return f;
   const float xw = __fmaf_rn(nx, vc.hw, vc.hw);
   const float yr = __fmaf_rn(ny, vc.hh, vc.hh);
-  if (FAST) {  // |xw - half| <= W + 16: far inside the range the biased floor is exact for
-    f.i0 = floor_to_int(__fsub_rn(xw, half));
-    f.j0 = floor_to_int(__fsub_rn(yr, half));
-  } else {
-    f.i0 = (int)floorf(__fsub_rn(xw, half));
-    f.j0 = (int)floorf(__fsub_rn(yr, half));
-  }
+  f.i0 = (int)floorf(__fsub_rn(xw, half));
+  f.j0 = (int)floorf(__fsub_rn(yr, half));
   f.zbits = __float_as_uint(Zc);
   // the splat must touch the image at all
   f.ok = f.i0 < vc.W && f.j0 < vc.H && f.i0 + vc.s > 0 && f.j0 + vc.s > 0;
   return f;
 }
 
-// ONE record per splat.  A splat of s <= 32 pixels touches at most 2 x 2 tiles; it is filed under the tile
-// of its anchor (clamped into the image), in one of four SUB-BINS by how it straddles: class bit 0 = it
-// reaches into the tile to the right, bit 1 = into the tile below.  tile_resolve reads, for its tile, the
-// four sub-bins of the tile itself plus the straddling classes of its left / upper / upper-left
-// neighbours: every record is still read once per tile it touches, but written once (was 1.13 times for
-// s = 3), and the binning loop has no divergent "second, third, fourth tile" code -- with 32 lanes some
-// lane almost always straddled, so the whole warp paid for those paths on nearly every view.
-// MODE 0: count records per sub-bin.  MODE 1: write them at offsets[sub-bin] + slot (second pass of
-// the counting sort).  MODE 2: single pass into fixed-capacity sub-bins (capacities per class known
-// from the previous searches; a sub-bin that fills up raises the overflow flag).
-template <int MODE, bool FAST>
+// MODE 0: count records per (view, tile).  MODE 1: write them at offsets[bin] + slot (second
+// pass of the counting sort).  MODE 2: single pass into fixed-capacity bins (capacity known
+// from the previous search; a bin that fills up raises the overflow flag).
+template <int MODE>
 __global__ void __launch_bounds__(256, NMI_BIN_CTAS)
 bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
            const uint32_t* __restrict__ counter, const float4* __restrict__ centres, int nviews,
            ViewConst vc, int ntx, int nt, uint32_t* __restrict__ counts,
            const uint32_t* __restrict__ offsets, uint4* __restrict__ rec, uint32_t rec_cap,
-           BinLayout L, uint32_t* __restrict__ overflow) {
+           uint32_t bin_cap, uint32_t* __restrict__ overflow) {
   constexpr bool SCATTER = MODE != 0;
   extern __shared__ float4 s_c[];
   for (int i = threadIdx.x; i < nviews; i += blockDim.x) s_c[i] = centres[i];
@@ -401,16 +356,41 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
   const uint32_t count = *counter;
   const float half = 0.5f * (float)(vc.s - 1);
   const int W = vc.W, H = vc.H, S = vc.s;
-  // Slot allocation.  The cloud is Morton-ordered, so the lanes of a warp fall into a handful of
-  // sub-bins: the lanes that share one (match.any) take their slots with ONE atomic, issued by the
-  // lowest of them, which adds their number -- an order of magnitude fewer L2 atomics than one per
-  // record.  U views are projected together and their
+  auto emit1 = [&](uint32_t bin, uint32_t ij, uint32_t zbits, uint32_t tag) {
+    const uint32_t slot = atomicAdd(&counts[bin], 1u);
+    if (MODE == 1) {
+      const uint32_t pos = offsets[bin] + slot;
+      if (pos < rec_cap)
+        rec[pos] = make_uint4(ij, zbits, tag, 0u);
+      else
+        *overflow = 1u;
+    } else if (MODE == 2) {
+      if (slot < bin_cap)
+        rec[(size_t)bin * bin_cap + slot] = make_uint4(ij, zbits, tag, 0u);
+      else
+        *overflow = 1u;
+    }
+  };
+  // a splat of s <= 32 pixels touches at most 2 x 2 tiles (usually one)
+  auto emit = [&](const Splat& f, int v, uint32_t tag) {
+    const int xa = max(f.i0, 0) >> 5, xb = min(f.i0 + S - 1, W - 1) >> 5;
+    const int ya = max(f.j0, 0) >> 5, yb = min(f.j0 + S - 1, H - 1) >> 5;
+    const uint32_t ij = (uint32_t)(f.i0 + 32768) | ((uint32_t)(f.j0 + 32768) << 16);
+    const uint32_t row_a = (uint32_t)v * nt + ya * ntx;
+    emit1(row_a + xa, ij, f.zbits, tag);
+    if (xb != xa) emit1(row_a + xb, ij, f.zbits, tag);
+    if (yb != ya) {
+      const uint32_t row_b = (uint32_t)v * nt + yb * ntx;
+      emit1(row_b + xa, ij, f.zbits, tag);
+      if (xb != xa) emit1(row_b + xb, ij, f.zbits, tag);
+    }
+  };
+  // Slot allocation.  The cloud is Morton-ordered, so neighbouring lanes usually fall into the
+  // same (view, tile) bin: each run of consecutive lanes with the same bin takes its slots with
+  // ONE atomic (issued by the run's first lane, which adds the run length), an order of
+  // magnitude fewer L2 atomics than one per record.  U views are projected together and their
   // atomics issued back to back (U round trips of ~700 cycles in flight per thread; see NMI_BIN_U).
   constexpr int U = NMI_BIN_U;
-  const unsigned long long cap16 = L.cap[0] | ((unsigned long long)L.cap[1] << 16) | ((unsigned long long)L.cap[2] << 32) |
-                                   ((unsigned long long)L.cap[3] << 48);
-  const unsigned long long off16 = L.off[0] | ((unsigned long long)L.off[1] << 16) | ((unsigned long long)L.off[2] << 32) |
-                                   ((unsigned long long)L.off[3] << 48);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); t0 < count; t0 += stride) {
@@ -418,54 +398,62 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
     const bool act = t < count;  // whole warps iterate together (shuffles below)
     const float4 p = act ? cpts[t] : make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t tag = (SCATTER && act) ? ctag[t] : 0u;
-    for (int v = 0; v < nviews; v += U) {
+    int v = 0;
+    for (; v + U <= nviews; v += U) {
       Splat f[U];
-      uint32_t sb[U], slot[U], leader[U], rank[U];
+      uint32_t bin0[U], slot[U], leader[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int vv = min(v + u, nviews - 1);
-        f[u] = project_splat_point<FAST>(p, s_c[vv], vc, half);
-        f[u].ok = f[u].ok && act && v + u < nviews;
+        f[u] = project_splat_point(p, s_c[v + u], vc, half);
+        f[u].ok = f[u].ok && act;
+        bin0[u] = (uint32_t)(v + u) * nt + (max(f[u].j0, 0) >> 5) * ntx + (max(f[u].i0, 0) >> 5);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t key = f[u].ok ? bin0[u] : 0xFFFFFFFFu;
+        const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, key, 1);
+        const uint32_t heads = __ballot_sync(0xFFFFFFFFu, lane == 0 || key != prev);
+        leader[u] = 31u - (uint32_t)__clz(heads & (0xFFFFFFFFu >> (31u - lane)));
+        const uint32_t above = heads & ~((2u << leader[u]) - 1u);
+        const uint32_t len = (above ? (uint32_t)__ffs(above) - 1u : 32u) - leader[u];
+        slot[u] = 0;
+        if (f[u].ok && lane == leader[u]) slot[u] = atomicAdd(&counts[bin0[u]], len);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        slot[u] = __shfl_sync(0xFFFFFFFFu, slot[u], leader[u]) + (lane - leader[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (!f[u].ok) continue;
+        const uint32_t ij = (uint32_t)(f[u].i0 + 32768) | ((uint32_t)(f[u].j0 + 32768) << 16);
+        if (MODE == 1) {
+          const uint32_t pos = offsets[bin0[u]] + slot[u];
+          if (pos < rec_cap)
+            rec[pos] = make_uint4(ij, f[u].zbits, tag, 0u);
+          else
+            *overflow = 1u;
+        } else if (MODE == 2) {
+          if (slot[u] < bin_cap)
+            rec[(size_t)bin0[u] * bin_cap + slot[u]] = make_uint4(ij, f[u].zbits, tag, 0u);
+          else
+            *overflow = 1u;
+        }
+        // the other (up to three) tiles of a splat that straddles a tile edge: ~12 % of splats
         const int xa = max(f[u].i0, 0) >> 5, xb = min(f[u].i0 + S - 1, W - 1) >> 5;
         const int ya = max(f[u].j0, 0) >> 5, yb = min(f[u].j0 + S - 1, H - 1) >> 5;
-        const uint32_t cls = (xb != xa ? 1u : 0u) | (yb != ya ? 2u : 0u);
-        sb[u] = (((uint32_t)vv * nt + ya * ntx + xa) << 2) | cls;
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const uint32_t key = f[u].ok ? sb[u] : 0xFFFFFFFFu;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);  // every lane of the warp with this sub-bin
-        leader[u] = (uint32_t)__ffs(peers) - 1u;
-        rank[u] = (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        slot[u] = 0;
-        if (f[u].ok && lane == leader[u]) slot[u] = atomicAdd(&counts[sb[u]], (uint32_t)__popc(peers));
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) slot[u] = __shfl_sync(0xFFFFFFFFu, slot[u], leader[u]) + rank[u];
-      if (SCATTER) {
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          if (!f[u].ok) continue;
-          const uint32_t ij = (uint32_t)(f[u].i0 + 32768) | ((uint32_t)(f[u].j0 + 32768) << 16);
-          if (MODE == 1) {
-            const uint32_t pos = offsets[sb[u]] + slot[u];
-            if (pos < rec_cap)
-              rec[pos] = make_uint4(ij, f[u].zbits, tag, 0u);
-            else
-              *overflow = 1u;
-          } else {
-            // capacity and offset of the class: 16-bit fields of two 64-bit words (one funnel shift each; an
-            // indexed read of the by-value struct would copy it to local memory, selects became branches)
-            const uint32_t sh = (sb[u] & 3u) * 16u;
-            const uint32_t ccap = (uint32_t)(cap16 >> sh) & 0xFFFFu, coff = (uint32_t)(off16 >> sh) & 0xFFFFu;
-            if (slot[u] < ccap)  // (record indices fit 32 bits: ensure_tile_buffers)
-              rec[(sb[u] >> 2) * L.cap_total + coff + slot[u]] = make_uint4(ij, f[u].zbits, tag, 0u);
-            else
-              *overflow = 1u;
-          }
+        if (xb != xa) emit1(bin0[u] + 1, ij, f[u].zbits, tag);
+        if (yb != ya) {
+          const uint32_t row_b = (uint32_t)(v + u) * nt + yb * ntx;
+          emit1(row_b + xa, ij, f[u].zbits, tag);
+          if (xb != xa) emit1(row_b + xb, ij, f[u].zbits, tag);
         }
       }
     }
+    if (act)
+      for (; v < nviews; v++) {
+        const Splat f0 = project_splat_point(p, s_c[v], vc, half);
+        if (f0.ok) emit(f0, v, tag);
+      }
   }
 }
 
@@ -476,11 +464,8 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
 // record and pass (9 for the reference's glPointSize(3): 18 atomics per record, 3 wavefronts each,
 // was 97 % of the L1 pipe).  Keys are compared as (depth bits, tag), the packed 64-bit order.
 template <bool PACKED, int ST>  // ST = 3: the reference's point size, filter in registers; 0: any S <= 32
-#ifndef NMI_TILE_CTAS
-#define NMI_TILE_CTAS 16  // 32 registers: sixteen tiles in flight per SM hide the record loads
-#endif
-__global__ void __launch_bounds__(kTileThreads, NMI_TILE_CTAS)
-tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, BinLayout L,
+__global__ void __launch_bounds__(kTileThreads)
+tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bin_cap,
                     const uint32_t* __restrict__ offsets, uint32_t* __restrict__ total, int ntx, int nt,
                     int W, int H, int S,
                     const uint8_t* __restrict__ val, uint8_t* __restrict__ images, size_t pitch,
@@ -495,46 +480,18 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, BinLayout L
   const int ty = tile / ntx, tx = tile - ty * ntx;
   const int x0 = tx * kTile, y0 = ty * kTile;
   const int tid = threadIdx.x;
-  // Records of sub-bin (b, cls).  Fixed-capacity sub-bins (L.cap_total > 0): `offsets` holds the fill
-  // counts; else the counting sort's offsets.  Clamped to the record buffer: after an overflow (flagged
-  // by the binning kernel, the search is then redone) the offsets may point past it.
-  const uint32_t nsub = gridDim.x * 4u;
-  auto segment = [&](uint32_t b, uint32_t cls, uint32_t& start, uint32_t& n) {
-    const uint32_t sb = b * 4u + cls;
-    if (L.cap_total) {
-      start = b * L.cap_total + (cls == 0u ? L.off[0] : cls == 1u ? L.off[1] : cls == 2u ? L.off[2] : L.off[3]);
-      n = min(offsets[sb], cls == 0u ? L.cap[0] : cls == 1u ? L.cap[1] : cls == 2u ? L.cap[2] : L.cap[3]);
-    } else {
-      start = min(offsets[sb], rec_cap);
-      n = min(sb + 1 < nsub ? offsets[sb + 1] : *total, rec_cap) - start;
-    }
-  };
-  // The tile's own non-straddling splats (class 0, the bulk) are spread over all threads; the eight
-  // straddler segments -- its own classes 1..3 and the neighbours' splats that reach into it -- are
-  // short (6 % of a bin for an edge, 0.4 % for a corner at s = 3): warp w walks one edge segment and
-  // one corner segment with its 32 lanes (warp-uniform bounds, no table in shared memory).
-  const uint32_t warp = (uint32_t)tid >> 5, lane = (uint32_t)tid & 31u;
-  uint32_t sst[2] = {0, 0}, sn[2] = {0, 0};
-  {
-    //            warp 0             1              2                   3
-    // edge:   own right (1)    own down (2)   left's right (1)    upper's down (2)
-    // corner: own (3)          left's (3)     upper's (3)         upper-left's (3)
-    const bool left = tx > 0, up = ty > 0;
-    const uint32_t be = warp == 2u ? bin - 1u : warp == 3u ? bin - (uint32_t)ntx : bin;
-    const bool have_e = warp == 2u ? left : warp == 3u ? up : true;
-    if (have_e) segment(be, (warp & 1u) ? 2u : 1u, sst[0], sn[0]);
-    const uint32_t bc = warp == 0u ? bin : warp == 1u ? bin - 1u : warp == 2u ? bin - (uint32_t)ntx : bin - (uint32_t)ntx - 1u;
-    const bool have_c = warp == 0u ? true : warp == 1u ? left : warp == 2u ? up : left && up;
-    if (have_c) segment(bc, 3u, sst[1], sn[1]);
-    // feedback: fullest sub-bin of classes 1..3.  (Read first: 130 K CTAs hammering the words of one
-    // sector with atomics serialise in L2; the maximum settles after a few CTAs and the rest only load.)
-    if (lane == 0u && warp < 2u && sn[0] > __ldcg(total + 4 + warp)) atomicMax(total + 4 + warp, sn[0]);
-    if (tid == 0 && sn[1] > __ldcg(total + 6)) atomicMax(total + 6, sn[1]);
+  // clamp to the record buffer: after an overflow (flagged by bin_scatter, the search is then
+  // redone) the offsets may point past it
+  // bin_cap > 0: fixed-capacity bins, `offsets` holds the fill counts; else counting-sort offsets
+  size_t start, end;
+  if (bin_cap) {
+    start = (size_t)bin * bin_cap;
+    end = start + min(offsets[bin], bin_cap);
+  } else {
+    start = min(offsets[bin], rec_cap);
+    end = min(bin + 1 < gridDim.x ? offsets[bin + 1] : *total, rec_cap);
   }
-  uint32_t start, n0;
-  segment(bin, 0, start, n0);
-  const uint32_t end = start + n0;  // (record indices fit 32 bits: ensure_tile_buffers)
-  if (tid == 0 && n0 > __ldcg(total + 2)) atomicMax(total + 2, n0);  // feedback: fullest class-0 sub-bin
+  if (tid == 0) atomicMax(total + 2, (uint32_t)(end - start));  // feedback: fullest bin
   {
     uint4* s4 = reinterpret_cast<uint4*>(s_dyn);  // 2 * E * E words, rounded up to whole uint4s (the buffer is padded)
     for (int q = tid; q < (2 * E * E + 3) / 4; q += kTileThreads) s4[q] = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -545,56 +502,35 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, BinLayout L
   // for pass 2 (the average bin holds ~4 per thread), the rest are read again (L2).
   constexpr int kKeep = 4;
   uint4 keep[kKeep];
+  int ckeep[kKeep];
 #pragma unroll
   for (int k = 0; k < kKeep; k++) {
-    const uint32_t r = start + tid + k * kTileThreads;
-    keep[k].x = 0u;  // anchor (-32768, -32768): outside every tile
-    if (r < end) keep[k] = rec[r];
+    const size_t r = start + tid + (size_t)k * kTileThreads;
+    ckeep[k] = -1;
+    if (r < end) {
+      keep[k] = rec[r];
+      const int u = (int)(keep[k].x & 0xFFFFu) - ox, w = (int)(keep[k].x >> 16) - oy;
+      if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E) {
+        ckeep[k] = w * E + u;
+        atomicMin(&s_depth[ckeep[k]], keep[k].y);
+      }
+    }
   }
-#pragma unroll
-  for (int k = 0; k < kKeep; k++) {
-    const int u = (int)(keep[k].x & 0xFFFFu) - ox, w = (int)(keep[k].x >> 16) - oy;
-    if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E) atomicMin(&s_depth[w * E + u], keep[k].y);
-  }
-#pragma unroll 1
-  for (uint32_t r = start + tid + kKeep * kTileThreads; r < end; r += kTileThreads) {
+  for (size_t r = start + tid + (size_t)kKeep * kTileThreads; r < end; r += kTileThreads) {
     const uint4 e = rec[r];
     const int u = (int)(e.x & 0xFFFFu) - ox, w = (int)(e.x >> 16) - oy;
     if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E) atomicMin(&s_depth[w * E + u], e.y);
   }
-#pragma unroll
-  for (int h = 0; h < 2; h++) {  // (read again in pass 2: L2 hits, about one record per lane)
-#pragma unroll 1
-    for (uint32_t q = lane; q < sn[h]; q += 32u) {
-      const uint4 e = rec[sst[h] + q];
-      const int u = (int)(e.x & 0xFFFFu) - ox, w = (int)(e.x >> 16) - oy;
-      if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E) atomicMin(&s_depth[w * E + u], e.y);
-    }
-  }
   __syncthreads();
   // pass 2: lowest tie-break word among the records at the minimum depth of their cell
 #pragma unroll
-  for (int k = 0; k < kKeep; k++) {
-    const int u = (int)(keep[k].x & 0xFFFFu) - ox, w = (int)(keep[k].x >> 16) - oy;
-    if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E && s_depth[w * E + u] == keep[k].y)
-      atomicMin(&s_tag[w * E + u], keep[k].z);
-  }
-#pragma unroll 1
-  for (uint32_t r = start + tid + kKeep * kTileThreads; r < end; r += kTileThreads) {
+  for (int k = 0; k < kKeep; k++)
+    if (ckeep[k] >= 0 && s_depth[ckeep[k]] == keep[k].y) atomicMin(&s_tag[ckeep[k]], keep[k].z);
+  for (size_t r = start + tid + (size_t)kKeep * kTileThreads; r < end; r += kTileThreads) {
     const uint4 e = rec[r];
     const int u = (int)(e.x & 0xFFFFu) - ox, w = (int)(e.x >> 16) - oy;
     if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E && s_depth[w * E + u] == e.y)
       atomicMin(&s_tag[w * E + u], e.z);
-  }
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-#pragma unroll 1
-    for (uint32_t q = lane; q < sn[h]; q += 32u) {
-      const uint4 e = rec[sst[h] + q];
-      const int u = (int)(e.x & 0xFFFFu) - ox, w = (int)(e.x >> 16) - oy;
-      if ((unsigned)u < (unsigned)E && (unsigned)w < (unsigned)E && s_depth[w * E + u] == e.y)
-        atomicMin(&s_tag[w * E + u], e.z);
-    }
   }
   __syncthreads();
   // S x S min filter; the CTA owns the tile: plain stores of the finished pixels (8 per thread, one
@@ -746,30 +682,27 @@ void launch_project_splat(const float4* cpts, const uint32_t* cidx, const uint32
 }
 
 // mode 0 = count, 1 = scatter at offsets (two-pass counting sort), 2 = single pass into
-// fixed-capacity sub-bins.  counts / offsets: [nviews * tiles * 4]; rec: rec_cap records.
+// fixed-capacity bins.  counts / offsets: [nviews * tiles]; rec: rec_cap records.
 void launch_bin_points(int mode, const float4* cpts, const uint32_t* ctag, const uint32_t* counter,
                        const float4* centres, int nviews, const ViewConst& vc, uint32_t* counts,
-                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, const BinLayout& bin_cap,
+                       const uint32_t* offsets, uint4* rec, uint32_t rec_cap, uint32_t bin_cap,
                        uint32_t* overflow, cudaStream_t st) {
   if (nviews == 0) return;
   const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
   const dim3 grid(sm_count() * 16), block(256);
   const size_t smem = sizeof(float4) * nviews;
-  // the binning kernel's fast arithmetic (div2_rn / floor_to_int) needs ordinary ranges; anything else takes
-  // the generic build
-  const bool fast = vc.zn >= 9.5367431640625e-07f && vc.zf <= 1048576.0f && vc.W < (1 << 20) && vc.H < (1 << 20);
-#define NMI_BIN(M, F)                                                                                             \
-  prefer_max_shared((const void*)bin_kernel<M, F>);                                                               \
-  bin_kernel<M, F><<<grid, block, smem, st>>>(cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts,  \
-                                              offsets, rec, rec_cap, bin_cap, overflow)
-  if (mode == 0) {
-    if (fast) { NMI_BIN(0, true); } else { NMI_BIN(0, false); }
-  } else if (mode == 1) {
-    if (fast) { NMI_BIN(1, true); } else { NMI_BIN(1, false); }
-  } else {
-    if (fast) { NMI_BIN(2, true); } else { NMI_BIN(2, false); }
-  }
-#undef NMI_BIN
+  prefer_max_shared((const void*)bin_kernel<0>);
+  prefer_max_shared((const void*)bin_kernel<1>);
+  prefer_max_shared((const void*)bin_kernel<2>);
+  if (mode == 0)
+    bin_kernel<0><<<grid, block, smem, st>>>(cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts,
+                                             offsets, rec, rec_cap, bin_cap, overflow);
+  else if (mode == 1)
+    bin_kernel<1><<<grid, block, smem, st>>>(cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts,
+                                             offsets, rec, rec_cap, bin_cap, overflow);
+  else
+    bin_kernel<2><<<grid, block, smem, st>>>(cpts, ctag, counter, centres, nviews, vc, ntx, ntx * nty, counts,
+                                             offsets, rec, rec_cap, bin_cap, overflow);
 }
 
 void launch_copy_rows(const uint8_t* src, size_t src_pitch, uint8_t* dst, int W, int H, bool flip, cudaStream_t st) {
@@ -779,7 +712,7 @@ void launch_copy_rows(const uint8_t* src, size_t src_pitch, uint8_t* dst, int W,
 
 int tiles_per_view(int W, int H) { return ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile); }
 
-void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, const BinLayout& bin_cap, const uint32_t* offsets, uint32_t* total, int nviews,
+void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, uint32_t bin_cap, const uint32_t* offsets, uint32_t* total, int nviews,
                          const ViewConst& vc, const uint8_t* val, bool packed, uint8_t* images,
                          size_t pitch, uint32_t* winners, size_t P, cudaStream_t st) {
   if (nviews == 0) return;

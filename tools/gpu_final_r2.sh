@@ -29,3 +29,8 @@ d = json.load(open(f"gpurun_out/bench_frame_{sys.argv[1]}.json"))
 print("frame", sys.argv[1], round(d["value"]), "evals/s", {k: round(x, 3) for k, x in d["stage_ms"].items()})
 PY
 done
+# single evaluation (config 1): launch list and a full capture of the cluster kernel
+python tools/exp_c1_launches.py > gpurun_out/c1_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/c1_launches.csv python tools/exp_c1_launches.py > /dev/null 2>&1
+ncu --set full --import-source on --clock-control none -k regex:"joint_hist_score_cluster" -s 2 -c 1 -f -o gpurun_out/prof_cluster python tools/exp_c1_launches.py > gpurun_out/prof_ncu_cluster.log 2>&1
+tail -1 gpurun_out/prof_ncu_cluster.log
