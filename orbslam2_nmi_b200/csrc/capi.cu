@@ -182,6 +182,7 @@ struct nmi_ctx {
   uint32_t fullest_hist[kFullestHist] = {};
   int fullest_pos = 0;
   bool force_conservative = false;
+  uint32_t retry_fullest = 0;  // > 0: redo of a search whose bins overflowed; the fullest bin it wanted
   bool conservative_once = false;  // an enqueued search overflowed: size the next one exactly
   // binned tile renderer scratch (point clouds)
   DevBuf<uint32_t> bin_offsets, bin_cursor;  // [views of a group * tiles]
@@ -300,8 +301,9 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   // (a) single pass: every bin gets the capacity of the previous search's fullest bin (+25 %)
   if (!c->feedback_pending)  // new model / camera: the history belongs to the old one
     for (uint32_t& v : c->fullest_hist) v = 0;
-  if (fb && c->h_feedback[3] > 0 && nviews <= kMaxViewsPerLaunch) {
-    c->fullest_hist[c->fullest_pos] = c->h_feedback[3];
+  const bool retry = c->retry_fullest != 0 && !c->force_conservative;
+  if (((fb && c->h_feedback[3] > 0) || retry) && nviews <= kMaxViewsPerLaunch) {
+    c->fullest_hist[c->fullest_pos] = retry ? c->retry_fullest : c->h_feedback[3];
     c->fullest_pos = (c->fullest_pos + 1) % nmi_ctx::kFullestHist;
     uint32_t fullest = 0;
     for (uint32_t v : c->fullest_hist) fullest = v > fullest ? v : fullest;
@@ -1048,7 +1050,7 @@ int nmi_search(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fla
   REQUIRE(out, NMI_ERR_INVALID, "null result");
   if (int rc = search_impl(c, Twc, g, f, 0, 1, nullptr, nullptr)) return rc;
   unsigned long long key = 0;
-  uint32_t tile_state[2] = {0, 0};
+  uint32_t tile_state[3] = {0, 0, 0};
   CK(cudaMemcpyAsync(&key, c->key.p, sizeof key, cudaMemcpyDeviceToHost, c->stream));
   if (c->bin_total.p)
     CK(cudaMemcpyAsync(tile_state, c->bin_total.p, sizeof tile_state, cudaMemcpyDeviceToHost, c->stream));
@@ -1059,8 +1061,15 @@ int nmi_search(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fla
   }
   CK(cudaStreamSynchronize(c->stream));
   if (tile_state[1] != 0 && !c->force_conservative) {
-    // the record-buffer guess from the previous search was too small for this pose: redo the
-    // search with the pose-independent sizing
+    // the bin capacity guessed from the previous searches was too small for this pose.  The resolve kernel
+    // has reported the fullest bin this search wanted: redo it in a single pass with bins of that size ...
+    if (c->retry_fullest == 0 && tile_state[2] > 0 && c->bin_cap != 0) {  // (the two-pass layout reports clamped counts)
+      c->retry_fullest = tile_state[2];
+      const int rc2 = nmi_search(c, Twc, g, f, out, scores_host);
+      c->retry_fullest = 0;
+      return rc2;
+    }
+    // ... and only if that fails too (it cannot, unless the buffer limit is hit) with the pose-independent sizing
     c->force_conservative = true;
     const int rc2 = nmi_search(c, Twc, g, f, out, scores_host);
     c->force_conservative = false;

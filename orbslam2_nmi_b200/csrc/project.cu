@@ -491,7 +491,9 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bi
     start = min(offsets[bin], rec_cap);
     end = min(bin + 1 < gridDim.x ? offsets[bin + 1] : *total, rec_cap);
   }
-  if (tid == 0) atomicMax(total + 2, (uint32_t)(end - start));  // feedback: fullest bin
+  // feedback: fullest bin -- the number of records the binning kernel WANTED to file here, also when that
+  // exceeded the capacity (the retry then sizes its bins from it)
+  if (tid == 0) atomicMax(total + 2, bin_cap ? offsets[bin] : (uint32_t)(end - start));
   {
     uint4* s4 = reinterpret_cast<uint4*>(s_dyn);  // 2 * E * E words, rounded up to whole uint4s (the buffer is padded)
     for (int q = tid; q < (2 * E * E + 3) / 4; q += kTileThreads) s4[q] = make_uint4(~0u, ~0u, ~0u, ~0u);
