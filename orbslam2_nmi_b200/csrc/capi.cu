@@ -43,13 +43,15 @@ void launch_mesh_values(const float4* verts, const uint3* tris, const uint32_t* 
                         uint32_t nt, cudaStream_t st);
 void launch_mesh_cull(const float4* verts, const uint3* tris, uint32_t nt, const ViewConst& vc,
                       const float c0[3], const float margin[3], uint32_t* slots, uint32_t* counter,
-                      uint32_t* block_counts, cudaStream_t st);
-void launch_mesh_raster(const float4* verts, const uint3* tris, const uint32_t* tri_orig,
-                        const uint32_t* slots, const uint32_t* counter, const float4* centres, int nviews,
+                      uint32_t* block_counts, uint8_t* vflag, uint32_t nv, cudaStream_t st);
+void launch_mesh_vertices(const float4* verts, const uint8_t* vflag, uint32_t nv, const float4* centres, int nviews,
+                          const ViewConst& vc, int4* tv, cudaStream_t st);
+void launch_mesh_raster(const int4* tv, const uint3* tris, const uint32_t* tri_orig,
+                        const uint32_t* slots, const uint32_t* counter, int nviews,
                         const ViewConst& vc, unsigned long long* zbuf, size_t P, cudaStream_t st);
 void launch_mesh_luma(const uint8_t* tex, float* luma, size_t n, cudaStream_t st);
-void launch_mesh_shade(unsigned long long* zbuf, const float4* verts, const uint3* tris_orig, const float* corner_uv,
-                       const float* luma, int tw, int th, const float4* centres, int nviews, const ViewConst& vc,
+void launch_mesh_shade(unsigned long long* zbuf, const int4* tv, const uint4* tris_orig, const float4* corner_uv,
+                       const float* luma, int tw, int th, int nviews, const ViewConst& vc,
                        size_t P, uint8_t* images, size_t pitch, uint32_t* winners, cudaStream_t st);
 
 static thread_local std::string g_err;
@@ -164,8 +166,14 @@ struct nmi_ctx {
   size_t n_tris = 0;  // > 0: the model is a mesh, else a point cloud
   // textured mesh (Rendering<1> as the reference runs it): triangles in ORIGINAL order (what the
   // z-buffer key names), un-indexed corner UVs, the texture's luma in 0..255 units
-  DevBuf<uint3> mtris_o;
-  DevBuf<float> muv, mluma;
+  DevBuf<uint4> mtris_o;   // {v0, v1, v2, -}
+  DevBuf<float4> muv;      // two per triangle: {u0, v0, u1, v1}, {u2, v2, -, -}
+  DevBuf<float> mluma;
+  // per-view vertex table of the current view group ([vertex][view], mesh.cu) + the vertices the
+  // cull flagged (corners of surviving triangles)
+  DevBuf<int4> mtv;
+  DevBuf<uint8_t> mvflag;
+  size_t n_verts = 0;
   int tex_w = 0, tex_h = 0;  // > 0: per-fragment texture shading
 
   // feedback from the previous search, copied to pinned host memory asynchronously:
@@ -419,7 +427,7 @@ int cull_model(nmi_ctx* c, const ViewConst& vc, const float Twc[16], const float
   const float c0[3] = {Twc[3], Twc[7], Twc[11]};
   if (c->n_tris) {
     launch_mesh_cull(c->mverts.p, c->mtris.p, (uint32_t)c->n_tris, vc, c0, margin, c->mslots.p,
-                     c->counter.p, c->block_counts.p, c->stream);
+                     c->counter.p, c->block_counts.p, c->mvflag.p, (uint32_t)c->n_verts, c->stream);
   } else {
     launch_cull_compact(c->pts.p, c->tag.p, (uint32_t)c->n_pts, c->use_block_cull ? c->aabb.p : nullptr, vc, c0, margin,
                         c->cpts.p, c->cidx.p,
@@ -470,15 +478,18 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
     return NMI_OK;
   }
   if (c->n_tris) {
-    launch_mesh_raster(c->mverts.p, c->mtris.p, c->mtri_orig.p, c->mslots.p, c->counter.p, d_centres,
-                       nviews, vc, c->zbuf.p, c->P, c->stream);
+    CK(c->mtv.reserve(c->n_verts * (size_t)nviews));
+    launch_mesh_vertices(c->mverts.p, c->mvflag.p, (uint32_t)c->n_verts, d_centres, nviews, vc, c->mtv.p, c->stream);
+    launch_mesh_raster(c->mtv.p, c->mtris.p, c->mtri_orig.p, c->mslots.p, c->counter.p, nviews, vc, c->zbuf.p, c->P,
+                       c->stream);
+    c->launches++;
   } else {
     launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->zbuf.p, c->P,
                          (uint32_t)c->n_pts, c->stream);
   }
   if (c->n_tris && c->tex_w > 0)
-    launch_mesh_shade(c->zbuf.p, c->mverts.p, c->mtris_o.p, c->muv.p, c->mluma.p, c->tex_w, c->tex_h, d_centres, nviews, vc,
-                      c->P, images, c->pitch, winners, c->stream);
+    launch_mesh_shade(c->zbuf.p, c->mtv.p, c->mtris_o.p, c->muv.p, c->mluma.p, c->tex_w, c->tex_h, nviews, vc, c->P,
+                      images, c->pitch, winners, c->stream);
   else
     launch_resolve(c->zbuf.p, c->val.p, nviews, c->P, images, c->pitch, winners, c->packed_value,
                    c->stream);
@@ -653,6 +664,8 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   if (c->n_tris) {  // the mesh rasteriser gives every view of a group a lane: power-of-two groups
     int p2 = 1;
     while (p2 * 2 <= group && p2 < 32) p2 *= 2;
+    // ... and a 16-byte entry of the vertex table per (vertex, view of the group): at most 4 GiB
+    while (p2 > 1 && c->n_verts * (size_t)p2 * sizeof(int4) > (4ull << 30)) p2 /= 2;
     group = p2;
   }
   const bool tiled = !c->n_tris && vc_point_size(c->cam) <= 32;
@@ -756,7 +769,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->pts.release(); c->aabb.release(); c->orig.release(); c->tag.release(); c->val.release(); c->mverts.release(); c->mtris.release();
-  c->mtri_orig.release(); c->mslots.release(); c->mtris_o.release(); c->muv.release(); c->mluma.release(); c->bin_offsets.release(); c->bin_cursor.release();
+  c->mtri_orig.release(); c->mslots.release(); c->mtris_o.release(); c->muv.release(); c->mtv.release(); c->mvflag.release(); c->mluma.release(); c->bin_offsets.release(); c->bin_cursor.release();
   c->bin_total.release(); c->records.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
@@ -956,6 +969,7 @@ int nmi_set_mesh(nmi_ctx* c, const float* verts, size_t nv, const uint32_t* tris
   CK(c->mtris.reserve(nt));
   CK(c->mtri_orig.reserve(nt));
   CK(c->mslots.reserve(nt));
+  CK(c->mvflag.reserve(nv));
   CK(c->val.reserve(nt));
   CK(c->block_counts.reserve((nt + 255) / 256 + 1));
   CK(cudaMemcpyAsync(c->mverts.p, verts, nv * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -965,6 +979,7 @@ int nmi_set_mesh(nmi_ctx* c, const float* verts, size_t nv, const uint32_t* tris
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   c->n_tris = nt;
+  c->n_verts = nv;
   c->packed_value = false;  // mesh keys carry the plain triangle index
   c->n_pts = 0;
   c->tex_w = c->tex_h = 0;  // flat grey of the first vertex until nmi_set_mesh_textured says otherwise
@@ -979,12 +994,22 @@ int nmi_set_mesh_textured(nmi_ctx* c, const float* verts, size_t nv, const uint3
   if (int rc = nmi_set_mesh(c, verts, nv, tris, nt)) return rc;
   const size_t ntex = (size_t)tex_w * tex_h;
   CK(c->mtris_o.reserve(nt));
-  CK(c->muv.reserve(6 * nt));
+  CK(c->muv.reserve(2 * nt));
   CK(c->mluma.reserve(ntex));
   DevBuf<uint8_t> raw;
   CK(raw.reserve(3 * ntex));
-  CK(cudaMemcpyAsync(c->mtris_o.p, tris, nt * sizeof(uint3), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->muv.p, corner_uv, 6 * nt * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  // padded to 16-byte entries: the shading kernel fetches a triangle's corners / UVs with one / two loads
+  std::vector<uint4> tri4(nt);
+  std::vector<float4> uv4(2 * nt);
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < (long long)nt; i++) {
+    tri4[i] = make_uint4(tris[3 * i], tris[3 * i + 1], tris[3 * i + 2], 0u);
+    const float* q = corner_uv + 6 * (size_t)i;
+    uv4[2 * i] = make_float4(q[0], q[1], q[2], q[3]);
+    uv4[2 * i + 1] = make_float4(q[4], q[5], 0.0f, 0.0f);
+  }
+  CK(cudaMemcpyAsync(c->mtris_o.p, tri4.data(), nt * sizeof(uint4), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->muv.p, uv4.data(), 2 * nt * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(raw.p, texture, 3 * ntex, cudaMemcpyHostToDevice, c->stream));
   launch_mesh_luma(raw.p, c->mluma.p, ntex, c->stream);
   CK(cudaGetLastError());
