@@ -137,6 +137,11 @@ struct nmi_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // the frame warps run here, concurrently with the render stage
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // mesh models: the view groups of a search alternate between `stream` and `stream3` (each with its own
+  // half of the z-buffer and of the vertex table), so that the issue-bound raster kernel of one group runs
+  // under the latency-bound shading kernel of the other
+  cudaStream_t stream3 = nullptr;
+  cudaEvent_t ev_fork3 = nullptr, ev_join3 = nullptr;
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_params = nullptr;  // completion of the last H2D from h_params
   bool params_in_flight = false;
@@ -440,7 +445,7 @@ int cull_model(nmi_ctx* c, const ViewConst& vc, const float Twc[16], const float
 
 // z-buffer the culled model into `nviews` views (z-buffer views [0, nviews)) and resolve them.
 int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nviews, uint8_t* images,
-               uint32_t* winners) {
+               uint32_t* winners, int half = 0, size_t half_views = 0) {
   if (!c->n_tris && vc.s <= 32) {
     // point cloud: binned tile renderer, no global z-buffer
     const size_t nbins = (size_t)nviews * tiles_per_view(vc.W, vc.H);
@@ -477,22 +482,28 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
     CK(cudaGetLastError());
     return NMI_OK;
   }
+  // half 1 (mesh view groups only): second stream, second half of the z-buffer and of the vertex table
+  cudaStream_t st = half ? c->stream3 : c->stream;
+  unsigned long long* zb = c->zbuf.p + (size_t)half * half_views * c->P;
   if (c->n_tris) {
-    CK(c->mtv.reserve(c->n_verts * (size_t)nviews));
-    launch_mesh_vertices(c->mverts.p, c->mvflag.p, (uint32_t)c->n_verts, d_centres, nviews, vc, c->mtv.p, c->stream);
-    launch_mesh_raster(c->mtv.p, c->mtris.p, c->mtri_orig.p, c->mslots.p, c->counter.p, nviews, vc, c->zbuf.p, c->P,
-                       c->stream);
+    CK(c->mtv.reserve(c->n_verts * (half_views ? 2 * half_views : (size_t)nviews)));
+    int4* tv = c->mtv.p + (size_t)half * half_views * c->n_verts;
+    launch_mesh_vertices(c->mverts.p, c->mvflag.p, (uint32_t)c->n_verts, d_centres, nviews, vc, tv, st);
+    launch_mesh_raster(tv, c->mtris.p, c->mtri_orig.p, c->mslots.p, c->counter.p, nviews, vc, zb, c->P, st);
     c->launches++;
+    if (c->tex_w > 0)
+      launch_mesh_shade(zb, tv, c->mtris_o.p, c->muv.p, c->mluma.p, c->tex_w, c->tex_h, nviews, vc, c->P, images,
+                        c->pitch, winners, st);
+    else
+      launch_resolve(zb, c->val.p, nviews, c->P, images, c->pitch, winners, c->packed_value, st);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    return NMI_OK;
   } else {
     launch_project_splat(c->cpts.p, c->cidx.p, c->counter.p, d_centres, nviews, vc, c->zbuf.p, c->P,
                          (uint32_t)c->n_pts, c->stream);
   }
-  if (c->n_tris && c->tex_w > 0)
-    launch_mesh_shade(c->zbuf.p, c->mtv.p, c->mtris_o.p, c->muv.p, c->mluma.p, c->tex_w, c->tex_h, nviews, vc, c->P,
-                      images, c->pitch, winners, c->stream);
-  else
-    launch_resolve(c->zbuf.p, c->val.p, nviews, c->P, images, c->pitch, winners, c->packed_value,
-                   c->stream);
+  launch_resolve(c->zbuf.p, c->val.p, nviews, c->P, images, c->pitch, winners, c->packed_value, c->stream);
   c->launches += 2;
   CK(cudaGetLastError());
   return NMI_OK;
@@ -657,7 +668,13 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
     const char* e = getenv("NMI_ZBUF_MB");
     return (size_t)(e && atoi(e) > 0 ? atoi(e) : 64) << 20;
   }();
-  int group = (int)(zb_budget / (zb_view ? zb_view : 1));
+  static const bool mesh_two_streams = [] {
+    const char* e = getenv("NMI_MESH_STREAMS");
+    return !(e && atoi(e) == 1);
+  }();
+  // mesh: two groups are in flight (one per stream), each with half of the budget
+  const bool pingpong = c->n_tris && mesh_two_streams && (size_t)nvl * zb_view > zb_budget / 2 && nvl >= 4;
+  int group = (int)(zb_budget / (pingpong ? 2 : 1) / (zb_view ? zb_view : 1));
   if (group < 1) group = 1;
   if (group > nvl) group = nvl;
   if (group > kMaxViewsPerLaunch) group = kMaxViewsPerLaunch;
@@ -665,14 +682,14 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
     int p2 = 1;
     while (p2 * 2 <= group && p2 < 32) p2 *= 2;
     // ... and a 16-byte entry of the vertex table per (vertex, view of the group): at most 4 GiB
-    while (p2 > 1 && c->n_verts * (size_t)p2 * sizeof(int4) > (4ull << 30)) p2 /= 2;
+    while (p2 > 1 && c->n_verts * (size_t)p2 * sizeof(int4) * (pingpong ? 2 : 1) > (4ull << 30)) p2 /= 2;
     group = p2;
   }
   const bool tiled = !c->n_tris && vc_point_size(c->cam) <= 32;
   if (tiled) {
     if (int rc = ensure_tile_buffers(c, nvl, &group)) return rc;
   } else {
-    if (int rc = ensure_zbuf(c, (size_t)group * c->P)) return rc;
+    if (int rc = ensure_zbuf(c, (size_t)group * c->P * (pingpong ? 2 : 1))) return rc;
   }
 
   c->launches = 0;
@@ -696,10 +713,19 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   CK(cudaEventRecord(c->ev_join, c->stream2));
   if (int rc = cull_model(c, vc, Twc, margin)) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
-  for (int v0 = 0; v0 < nvl; v0 += group) {
+  if (pingpong) {  // both streams start behind the cull
+    CK(cudaEventRecord(c->ev_fork3, c->stream));
+    CK(cudaStreamWaitEvent(c->stream3, c->ev_fork3, 0));
+  }
+  for (int v0 = 0, gi = 0; v0 < nvl; v0 += group, gi++) {
     const int nv = nvl - v0 < group ? nvl - v0 : group;
-    if (int rc = draw_views(c, vc, d_centres + v0, nv, c->renders.p + (size_t)v0 * c->pitch, nullptr))
+    if (int rc = draw_views(c, vc, d_centres + v0, nv, c->renders.p + (size_t)v0 * c->pitch, nullptr,
+                            pingpong ? (gi & 1) : 0, pingpong ? (size_t)group : 0))
       return rc;
+  }
+  if (pingpong) {
+    CK(cudaEventRecord(c->ev_join3, c->stream3));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join3, 0));
   }
   // stage events: [1] = project + resolve of all view groups (interleaved), [2] = 0
   if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
@@ -739,6 +765,9 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   c->device = device;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto& e : c->ev) CK(cudaEventCreate(&e));
@@ -791,6 +820,9 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_fork3) cudaEventDestroy(c->ev_fork3);
+  if (c->ev_join3) cudaEventDestroy(c->ev_join3);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
