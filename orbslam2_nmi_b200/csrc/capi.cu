@@ -19,7 +19,7 @@
 namespace nmi {
 
 // project.cu (not in the header: only capi uses them)
-void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const float* aabb, const ViewConst& vc,
+int launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const float* aabb, const ViewConst& vc,
                          const float c0[3], const float margin[3], float4* out_pts,
                          uint32_t* out_idx, uint32_t* counter, uint32_t* block_counts,
                          cudaStream_t st);
@@ -433,12 +433,12 @@ int cull_model(nmi_ctx* c, const ViewConst& vc, const float Twc[16], const float
   if (c->n_tris) {
     launch_mesh_cull(c->mverts.p, c->mtris.p, (uint32_t)c->n_tris, vc, c0, margin, c->mslots.p,
                      c->counter.p, c->block_counts.p, c->mvflag.p, (uint32_t)c->n_verts, c->stream);
+    c->launches += 3;
   } else {
-    launch_cull_compact(c->pts.p, c->tag.p, (uint32_t)c->n_pts, c->use_block_cull ? c->aabb.p : nullptr, vc, c0, margin,
+    c->launches += launch_cull_compact(c->pts.p, c->tag.p, (uint32_t)c->n_pts, c->use_block_cull ? c->aabb.p : nullptr, vc, c0, margin,
                         c->cpts.p, c->cidx.p,
                         c->counter.p, c->block_counts.p, c->stream);
   }
-  c->launches += 3;
   CK(cudaGetLastError());
   return NMI_OK;
 }
@@ -763,8 +763,17 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   CK(cudaSetDevice(device));
   nmi_ctx* c = new nmi_ctx();
   c->device = device;
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  // the main stream outranks the warp stream: the small, latency-bound cull launches get their CTAs
+  // placed as soon as SM resources free up instead of queueing behind the (issue-bound) warp kernel
+  // that was launched first ($NMI_STREAM_PRIO=0: equal priorities)
+  {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const char* e = getenv("NMI_STREAM_PRIO");
+    const bool prio = !(e && atoi(e) == 0);
+    CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio ? hi : lo));
+    CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, lo));
+  }
   CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));

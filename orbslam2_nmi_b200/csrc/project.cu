@@ -19,6 +19,8 @@
 // the global z-buffer path above serves the mesh model's resolve and splats wider than a tile.
 #include <climits>
 
+#include <cstdlib>
+
 #include "nmi_internal.h"
 
 namespace nmi {
@@ -219,6 +221,58 @@ cull_scatter_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__
   }
   __syncthreads();
   uint32_t before = block_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kCullPer; k++) {
+    uint32_t off = before;
+    for (int w = 0; w < warp; w++) off += s_warp[k][w];
+    if (keep[k]) {
+      const uint32_t o = off + __popc(m[k] & ((1u << lane) - 1u));
+      out_pts[o] = p[k];
+      out_idx[o] = tag[base + k * kCullThreads + threadIdx.x];  // the z-buffer key's tie-break word
+    }
+    for (int w = 0; w < kCullThreads / 32; w++) before += s_warp[k][w];
+  }
+}
+
+// One-pass compaction: a CTA that survives the block test counts its survivors, takes its output range
+// with ONE atomic on the running total and writes them in order.  The survivors of a block stay in Morton
+// order and the blocks arrive roughly in launch order, which is all the locality the binning pass needs
+// (the z-buffer minimum does not depend on the order of its candidates); one launch instead of
+// count -> scan -> scatter, and the cloud is read once.  `counter` must be zero at launch.
+__global__ void __launch_bounds__(kCullThreads)
+cull_compact_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ tag, uint32_t n,
+                    ViewConst vc, CullConst cc, const float* __restrict__ aabb,
+                    uint32_t* __restrict__ counter, float4* __restrict__ out_pts, uint32_t* __restrict__ out_idx) {
+  __shared__ uint32_t s_warp[kCullPer][kCullThreads / 32];
+  __shared__ uint32_t s_base;
+  const uint32_t base = blockIdx.x * kCullBlock;
+  if (!block_may_survive(aabb, blockIdx.x, vc, cc)) return;  // CTA-uniform
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 p[kCullPer];
+  unsigned m[kCullPer];
+  bool keep[kCullPer];
+#pragma unroll
+  for (int k = 0; k < kCullPer; k++) {  // sub-block k holds points base + k*256 .. +255 (in order)
+    const uint32_t i = base + k * kCullThreads + threadIdx.x;
+    keep[k] = false;
+    p[k] = make_float4(0, 0, 0, 0);
+    if (i < n) {
+      p[k] = ldg_stream(pts + i);
+      keep[k] = cull_keep(p[k], vc, cc);
+    }
+    m[k] = __ballot_sync(0xffffffffu, keep[k]);
+    if (lane == 0) s_warp[k][warp] = (uint32_t)__popc(m[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < kCullPer; k++)
+      for (int w = 0; w < kCullThreads / 32; w++) t += s_warp[k][w];
+    s_base = t ? atomicAdd(counter, t) : 0u;
+  }
+  __syncthreads();
+  uint32_t before = s_base;
 #pragma unroll
   for (int k = 0; k < kCullPer; k++) {
     uint32_t off = before;
@@ -651,17 +705,28 @@ void launch_intensity_u8(const float4* pts, const uint32_t* orig, uint8_t* val, 
   intensity_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pts, orig, val, tag, packed, n);
 }
 
-void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const float* aabb, const ViewConst& vc,
+int launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, const float* aabb, const ViewConst& vc,
                          const float c0[3], const float margin[3], float4* out_pts,
                          uint32_t* out_idx, uint32_t* counter, uint32_t* block_counts,
                          cudaStream_t st) {
-  if (n == 0) return;
+  if (n == 0) return 0;
   CullConst cc;
   for (int i = 0; i < 3; i++) cc.c0[i] = c0[i];
   cc.mx = margin[0];
   cc.my = margin[1];
   cc.mz = margin[2];
   const uint32_t nblocks = (n + kCullBlock - 1) / kCullBlock;
+  // $NMI_CULL_PASSES=3: the stable three-kernel compaction (A/B switch)
+  static const bool one_pass = [] {
+    const char* e = getenv("NMI_CULL_PASSES");
+    return !(e && atoi(e) == 3);
+  }();
+  if (one_pass) {
+    prefer_max_shared((const void*)cull_compact_kernel);
+    cudaMemsetAsync(counter, 0, sizeof(uint32_t), st);
+    cull_compact_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, orig, n, vc, cc, aabb, counter, out_pts, out_idx);
+    return 1;
+  }
   prefer_max_shared((const void*)cull_count_kernel);
   prefer_max_shared((const void*)cull_scan_kernel);
   prefer_max_shared((const void*)cull_scatter_kernel);
@@ -669,6 +734,7 @@ void launch_cull_compact(const float4* pts, const uint32_t* orig, uint32_t n, co
   cull_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, counter);
   cull_scatter_kernel<<<nblocks, kCullThreads, 0, st>>>(pts, orig, n, vc, cc, aabb, block_counts, out_pts,
                                                         out_idx);
+  return 3;
 }
 
 void launch_scan_counts(uint32_t* block_counts, uint32_t nblocks, uint32_t* counter, cudaStream_t st) {
