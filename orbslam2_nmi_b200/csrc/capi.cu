@@ -664,7 +664,7 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   // together (~64 MB of the 126 MB): the z-buffer is written, resolved and reset without
   // ever being streamed through HBM, and only `group` views of it exist.
   const size_t zb_view = c->P * sizeof(unsigned long long);
-  static const size_t zb_budget = [] {  // bytes of z-buffer kept in flight (L2 is 126 MB)
+  const size_t zb_budget = [] {  // bytes of z-buffer kept in flight (L2 is 126 MB); read per search (tests shrink it)
     const char* e = getenv("NMI_ZBUF_MB");
     return (size_t)(e && atoi(e) > 0 ? atoi(e) : 64) << 20;
   }();

@@ -571,6 +571,34 @@ def test_textured_mesh_search_matches_oracle(searcher, oracle, bins, height):
     assert_scores_close(r2.scores, s2)
 
 
+@pytest.mark.parametrize("n,height", [(12, 8.0), (40, 15.0), (40, 8.0), (400, 15.0)])
+def test_mesh_triangle_size_paths(searcher, oracle, n, height, monkeypatch):
+    """mesh_raster has three code paths by triangle size: at most 8 x 8 pixel centres (coverage mask,
+    32-bit edge functions), up to 64 px (32-bit, direct loop), larger (64-bit).  Coarse, medium and fine
+    terrains put the whole render on each of them in turn; winners and textured renders stay bit-exact,
+    with more views than one group holds so that the two-stream ping-pong over view groups is on."""
+    sc = synth.make_scene("small", n_points=10)
+    verts, tris = synth.make_mesh(n, n, extent=24.0)
+    uv = synth.make_mesh_uv(verts, tris, extent=24.0, repeats=2.0)
+    tex = synth.make_texture(96, 64)
+    Twc = synth.prior_pose(height_above=height)
+    px = 48.0 / n / (height - 2.0) * sc.fx  # projected edge length of a terrain cell, roughly
+    assert (px > 64) if n == 12 else (8 < px < 64) if n == 40 else (px < 8)
+    g = Grid.make((3, 2, 1), (1, 1, 1), (0.3, 0.2, 0.5), (0.02, 0.02, 0.05))
+    searcher.set_camera(sc.W, sc.H, sc.fx, sc.fy, sc.cx, sc.cy, sc.zn, sc.zf, sc.point_size)
+    searcher.set_mesh_textured(verts, tris, uv, tex)
+    searcher.set_frame(synth.frame_textured(sc.W, sc.H, seed=8))
+    monkeypatch.setenv("NMI_ZBUF_MB", "2")  # 0.5 MB of z-buffer per view: three groups of two views, two streams
+    searcher.search(Twc, g)
+    assert searcher.timings()[1] >= 1 + 3 + 3 * 3 + 2  # warp, cull, 3 groups x (vertices, raster, shade), histogram, argmax
+    for s in range(g.n_synth):
+        t = oracle.cell_translation(Twc, g, s % 3, s // 3, 0)
+        win, img = oracle.render_mesh_tex(sc, Twc, t, verts, tris, uv, tex)
+        assert (win != oracle.EMPTY).mean() > 0.9
+        assert np.array_equal(searcher.get_winners(s), win), f"winners differ, view {s}"
+        assert np.array_equal(searcher.get_render(s), img), f"render differs, view {s}"
+
+
 def test_large_cloud_uses_gather_path(searcher, oracle):
     """>= 2^24 points: the key cannot carry the value, resolve gathers it (both paths exact)."""
     sc = synth.make_scene("tiny", n_points=(1 << 24) + 1000)
