@@ -329,6 +329,14 @@ def config_c2_frames(searcher, scene, grid, flags):
 
     ms, st = time_frame(synth.frame_uniform(scene.W, scene.H))
     out["uniform"] = {"search_ms": ms, "evals_per_s": grid.n_pose / ms * 1e3, "hist_ms": st["hist_score"]}
+    # flat image content (hot-bin skipping through the image marginals, hist.cu): a frame whose top 35 % is a
+    # saturated sky, and a constant frame; the winner is checked against the side-table build of the same kernel
+    for name, fr in (("sky", synth.frame_sky(scene.W, scene.H)), ("constant", synth.frame_constant(scene.W, scene.H))):
+        ms, st = time_frame(fr)
+        r = searcher.search(scene.Twc, grid, flags)
+        out[name] = {"search_ms": ms, "evals_per_s": grid.n_pose / ms * 1e3, "hist_ms": st["hist_score"],
+                     "hist_path": searcher.last_hist_path(),
+                     "winner": {"index": int(r.best_index), "score": r.best_score}}
     # planted: translation cell (2, 1, 3), rotation cell (1, 1, 1) = the cell whose evaluated angles
     # are 0 for n = 4 (image.cpp:77: start = -trunc((n-1)/2) * step)
     cell_s, cell_w = (2, 1, 3), (1, 1, 1)

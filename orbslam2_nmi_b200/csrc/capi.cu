@@ -198,6 +198,7 @@ struct nmi_ctx {
   uint32_t retry_fullest = 0;  // > 0: redo of a search whose bins overflowed; the fullest bin it wanted
   bool conservative_once = false;  // an enqueued search overflowed: size the next one exactly
   // binned tile renderer scratch (point clouds)
+  DevBuf<uint32_t> img_hist;  // exact 256-bin histogram of every render / warp of the current search (hot-bin skipping)
   DevBuf<uint32_t> bin_offsets, bin_cursor;  // [views of a group * tiles]
   DevBuf<uint32_t> bin_total;                // [0] records of the group, [1] overflow flag
   DevBuf<uint4> records;
@@ -580,6 +581,18 @@ int score_pairs_launch(nmi_ctx* c, const nmi_flags* f, int nvl, int nwl, const i
     a.nrenders = nvl;
     a.skip_mode = c->hist_skip;
     a.skipcap = skipcap;
+    // the build with the skip code is about to run: give it the images' exact marginals, so that the
+    // skipped pixels cost nothing at all ($NMI_HIST_MARGINALS=0: count them into side tables instead)
+    static const bool marginals = [] {
+      const char* e = getenv("NMI_HIST_MARGINALS");
+      return !(e && atoi(e) == 0);
+    }();
+    if (skipcap && marginals && (f->variant == 0 || f->variant == 8 || f->variant == 9 || f->variant == 4 || f->variant == 5)) {
+      CK(c->img_hist.reserve((size_t)(nvl + nwl) * 256));
+      c->launches += launch_image_hists(c->renders.p, c->pitch, nvl, c->warps.p, c->pitch, nwl, (uint32_t)c->P,
+                                        c->img_hist.p, c->stream);
+      a.img_hist = c->img_hist.p;
+    }
   }
   c->last_skipcap = use_skip && skipcap;
   const int nl = launch_joint_hist_score(a, c->stream);
@@ -811,7 +824,7 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   c->bin_total.release(); c->records.release(); c->cpts.release(); c->cidx.release(); c->counter.release(); c->block_counts.release();
   c->frame.release(); c->zbuf.release(); c->renders.release(); c->warps.release();
   c->scores.release(); c->key.release(); c->params.release(); c->one_render.release();
-  c->img_mode.release(); c->hot.release(); c->term_tab.release(); c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
+  c->img_mode.release(); c->img_hist.release(); c->hot.release(); c->term_tab.release(); c->one_warp.release(); c->winners.release(); c->dumpJ.release(); c->dumpH.release();
   c->one_score.release(); c->zero_pair.release();
   for (int i = 0; i < 2; i++) {
     if (c->h_frame[i]) cudaFreeHost(c->h_frame[i]);
@@ -1308,6 +1321,12 @@ static int eval_images(nmi_ctx* c, const uint8_t* render, const uint8_t* warped,
       launch_image_modes(render, 0, 1, warped, 0, 1, npix, c->img_mode.p, c->hot.p, c->stream);
       a.img_mode = c->img_mode.p;
       a.sample_total = image_mode_sample_total(npix);
+      const char* e = getenv("NMI_HIST_MARGINALS");
+      if (!(e && atoi(e) == 0)) {  // as in a batched search: skipped pixels come back through the marginals
+        CK(c->img_hist.reserve(512));
+        launch_image_hists(render, 0, 1, warped, 0, 1, npix, c->img_hist.p, c->stream);
+        a.img_hist = c->img_hist.p;
+      }
     }
   }
   REQUIRE(launch_joint_hist_score(a, c->stream) >= 0, NMI_ERR_CUDA,

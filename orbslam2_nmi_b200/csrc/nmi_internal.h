@@ -59,6 +59,10 @@ struct HistArgs {
   // image; skip_mode 0 never, 1 when a pair's two levels cover >= 1/6 of the samples,
   // 2 always; skipcap = launch the build that carries the side tables.
   const uint32_t* img_mode;
+  // optional (SKIPCAP builds): full 256-bin histogram of every render, then of every warp
+  // (launch_image_hists).  Then a skipped pixel is not counted at all: row a* / column b* of the joint
+  // histogram are reconstructed from these marginals (hist.cu, marginal_side_counts).
+  const uint32_t* img_hist;
   uint32_t sample_total;
   int nrenders;
   int skip_mode;
@@ -83,6 +87,9 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st);  // returns lau
 int launch_image_modes(const uint8_t* renders, size_t rpitch, int nr, const uint8_t* warps, size_t wpitch,
                        int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st);
 uint32_t image_mode_sample_total(uint32_t npix);
+// img_hist[(nr + nw) * 256]: exact histograms of all npix pixels of every image.  Returns launches.
+int launch_image_hists(const uint8_t* renders, size_t rpitch, int nr, const uint8_t* warps, size_t wpitch,
+                       int nw, uint32_t npix, uint32_t* img_hist, cudaStream_t st);
 void launch_term_table(float* tab, uint32_t length, cudaStream_t st);
 
 // --- argmax.cu -------------------------------------------------------------
