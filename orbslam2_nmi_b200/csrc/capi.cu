@@ -197,6 +197,11 @@ struct nmi_ctx {
   bool force_conservative = false;
   uint32_t retry_fullest = 0;  // > 0: redo of a search whose bins overflowed; the fullest bin it wanted
   bool conservative_once = false;  // an enqueued search overflowed: size the next one exactly
+  // an enqueued (sharded) search overflowed its fixed-capacity bins: the fullest bin it wanted, for ONE redo in a
+  // single pass with bins of that size (what nmi_search does through retry_fullest); was_sized_retry: the search
+  // that just ran was such a redo, so another overflow falls back to the pose-independent sizing
+  uint32_t retry_fullest_once = 0;
+  bool was_sized_retry = false;
   // binned tile renderer scratch (point clouds)
   DevBuf<uint32_t> img_hist;  // exact 256-bin histogram of every render / warp of the current search (hot-bin skipping)
   DevBuf<uint32_t> bin_offsets, bin_cursor;  // [views of a group * tiles]
@@ -315,9 +320,10 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   // (a) single pass: every bin gets the capacity of the previous search's fullest bin (+25 %)
   if (!c->feedback_pending)  // new model / camera: the history belongs to the old one
     for (uint32_t& v : c->fullest_hist) v = 0;
-  const bool retry = c->retry_fullest != 0 && !c->force_conservative;
+  const uint32_t retry_size = c->retry_fullest ? c->retry_fullest : c->retry_fullest_once;
+  const bool retry = retry_size != 0 && !c->force_conservative && !c->conservative_once;
   if (((fb && c->h_feedback[3] > 0) || retry) && nviews <= kMaxViewsPerLaunch) {
-    c->fullest_hist[c->fullest_pos] = retry ? c->retry_fullest : c->h_feedback[3];
+    c->fullest_hist[c->fullest_pos] = retry ? retry_size : c->h_feedback[3];
     c->fullest_pos = (c->fullest_pos + 1) % nmi_ctx::kFullestHist;
     uint32_t fullest = 0;
     for (uint32_t v : c->fullest_hist) fullest = v > fullest ? v : fullest;
@@ -747,6 +753,8 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   if (int rc = score_pairs_launch(c, f, nvl, nwl, d_pairs, d_index, npl, nP, key_dev, scores_dev, tiled)) return rc;
 
   c->conservative_once = false;
+  c->was_sized_retry = c->retry_fullest_once != 0;
+  c->retry_fullest_once = 0;
   c->has_search = true;
   c->grid = *g;
   c->nvl = nvl;
@@ -849,6 +857,17 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   delete c;
 }
 
+// An enqueued search overflowed its bins (pinned feedback words of that search are complete: the stream has
+// been synchronised).  The resolve kernel has reported the fullest bin the search WANTED: the redo runs in a
+// single pass with bins of that size; only a redo that overflows again gets the two-pass sizing.
+static void arm_enqueued_retry(nmi_ctx* c) {
+  if (c->bin_cap != 0 && c->h_feedback[3] > 0 && !c->was_sized_retry)
+    c->retry_fullest_once = c->h_feedback[3];
+  else
+    c->conservative_once = true;
+  c->h_feedback[2] = 0;
+}
+
 void* nmi_ctx_stream(nmi_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int nmi_ctx_set_hist_skip(nmi_ctx* c, int mode) {
@@ -861,10 +880,9 @@ int nmi_ctx_sync(nmi_ctx* c) {
   REQUIRE(c, NMI_ERR_INVALID, "null ctx");
   CK(cudaStreamSynchronize(c->stream));
   if (c->feedback_pending && c->h_feedback && c->h_feedback[2] != 0) {
-    c->conservative_once = true;  // the next search uses the pose-independent sizing
+    arm_enqueued_retry(c);  // the next search gets bins of the size this one wanted
     set_error("tile renderer record buffer overflow in an enqueued search: its renders are incomplete; "
               "re-enqueue it");
-    c->h_feedback[2] = 0;
     return NMI_ERR_CUDA;
   }
   return NMI_OK;
@@ -1174,10 +1192,7 @@ int nmi_read_key(nmi_ctx* c, const void* key_dev, uint64_t* key) {
   CK(cudaMemcpyAsync(key, key_dev, sizeof *key, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   // a local overflow is also visible in the pinned feedback words: size the next search exactly
-  if (c->feedback_pending && c->h_feedback && c->h_feedback[2] != 0) {
-    c->conservative_once = true;
-    c->h_feedback[2] = 0;
-  }
+  if (c->feedback_pending && c->h_feedback && c->h_feedback[2] != 0) arm_enqueued_retry(c);
   return NMI_OK;
 }
 
