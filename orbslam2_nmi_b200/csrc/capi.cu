@@ -46,11 +46,11 @@ void launch_mesh_cull(const float4* verts, const uint3* tris, uint32_t nt, const
                       uint32_t* block_counts, uint8_t* vflag, uint32_t nv, cudaStream_t st);
 void launch_mesh_vertices(const float4* verts, const uint8_t* vflag, uint32_t nv, const float4* centres, int nviews,
                           const ViewConst& vc, int4* tv, cudaStream_t st);
-void launch_mesh_raster(const int4* tv, const uint3* tris, const uint32_t* tri_orig,
+void launch_mesh_raster(const int4* tv, uint32_t nv, const uint3* tris, const uint32_t* tri_orig,
                         const uint32_t* slots, const uint32_t* counter, int nviews,
                         const ViewConst& vc, unsigned long long* zbuf, size_t P, cudaStream_t st);
 void launch_mesh_luma(const uint8_t* tex, float* luma, size_t n, cudaStream_t st);
-void launch_mesh_shade(unsigned long long* zbuf, const int4* tv, const uint4* tris_orig, const float4* corner_uv,
+void launch_mesh_shade(unsigned long long* zbuf, const int4* tv, uint32_t nv, const uint4* tris_orig, const float4* corner_uv,
                        const float* luma, int tw, int th, int nviews, const ViewConst& vc,
                        size_t P, uint8_t* images, size_t pitch, uint32_t* winners, cudaStream_t st);
 
@@ -496,10 +496,10 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
     CK(c->mtv.reserve(c->n_verts * (half_views ? 2 * half_views : (size_t)nviews)));
     int4* tv = c->mtv.p + (size_t)half * half_views * c->n_verts;
     launch_mesh_vertices(c->mverts.p, c->mvflag.p, (uint32_t)c->n_verts, d_centres, nviews, vc, tv, st);
-    launch_mesh_raster(tv, c->mtris.p, c->mtri_orig.p, c->mslots.p, c->counter.p, nviews, vc, zb, c->P, st);
+    launch_mesh_raster(tv, (uint32_t)c->n_verts, c->mtris.p, c->mtri_orig.p, c->mslots.p, c->counter.p, nviews, vc, zb, c->P, st);
     c->launches++;
     if (c->tex_w > 0)
-      launch_mesh_shade(zb, tv, c->mtris_o.p, c->muv.p, c->mluma.p, c->tex_w, c->tex_h, nviews, vc, c->P, images,
+      launch_mesh_shade(zb, tv, (uint32_t)c->n_verts, c->mtris_o.p, c->muv.p, c->mluma.p, c->tex_w, c->tex_h, nviews, vc, c->P, images,
                         c->pitch, winners, st);
     else
       launch_resolve(zb, c->val.p, nviews, c->P, images, c->pitch, winners, c->packed_value, st);

@@ -1,3 +1,4 @@
 #!/bin/bash
-python tools/exp_c3_profile.py 6 2>&1 | tail -2 | head -1
-for m in 5 6 8; do echo "raster minb $m"; NMI_B200_LIB=orbslam2_nmi_b200/_lib/variants/rast$m.so python tools/exp_c3_profile.py 6 2>&1 | tail -2 | head -1; done
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x -k "mesh or Mesh or textured or compat" > gpurun_out/pytest_mesh.log 2>&1; tail -2 gpurun_out/pytest_mesh.log
+for l in 1 0; do echo "tv layout $l"; NMI_MESH_TV_LAYOUT=$l python tools/exp_c3_profile.py 6 2>&1 | tail -2 | head -1; done
