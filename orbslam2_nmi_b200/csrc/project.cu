@@ -511,6 +511,13 @@ bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
   }
 }
 
+// total[2] = fullest bin: the number of records the binning kernel WANTED to file in this CTA's bin, also when that
+// exceeded the capacity (the retry sizes its bins from it).  Not inlined: written inside tile_resolve_kernel the same
+// statement costs eight registers (40 instead of 32) and a quarter of the kernel's occupancy.
+__device__ __noinline__ void report_wanted_fill(uint32_t* __restrict__ total, const uint32_t* __restrict__ offsets) {
+  atomicMax(total + 2, offsets[blockIdx.x]);
+}
+
 // A splat covers the S x S pixels whose top-left corner is its ANCHOR (i0, j0), so
 //   zbuf(x, y) = min over anchors in [x-S+1, x] x [y-S+1, y] of  min key of the splats anchored there
 // (min is associative): ONE shared-memory atomic per record and pass into an anchor buffer of
@@ -537,6 +544,9 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bi
   // clamp to the record buffer: after an overflow (flagged by bin_scatter, the search is then
   // redone) the offsets may point past it
   // bin_cap > 0: fixed-capacity bins, `offsets` holds the fill counts; else counting-sort offsets
+  // feedback (total[2]): fullest bin -- the number of records the binning kernel WANTED to file here, also when
+  // that exceeded the capacity (the retry then sizes its bins from it)
+  // (fixed-capacity bins report at the end of the kernel, report_wanted_fill)
   size_t start, end;
   if (bin_cap) {
     start = (size_t)bin * bin_cap;
@@ -544,10 +554,8 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bi
   } else {
     start = min(offsets[bin], rec_cap);
     end = min(bin + 1 < gridDim.x ? offsets[bin + 1] : *total, rec_cap);
+    if (tid == 0) atomicMax(total + 2, (uint32_t)(end - start));
   }
-  // feedback: fullest bin -- the number of records the binning kernel WANTED to file here, also when that
-  // exceeded the capacity (the retry then sizes its bins from it)
-  if (tid == 0) atomicMax(total + 2, bin_cap ? offsets[bin] : (uint32_t)(end - start));
   {
     uint4* s4 = reinterpret_cast<uint4*>(s_dyn);  // 2 * E * E words, rounded up to whole uint4s (the buffer is padded)
     for (int q = tid; q < (2 * E * E + 3) / 4; q += kTileThreads) s4[q] = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -654,6 +662,10 @@ tile_resolve_kernel(const uint4* __restrict__ rec, uint32_t rec_cap, uint32_t bi
     } else {
       for (int k = 0; k < 8 && x0 + col + k < W; k++) img[o + k] = (uint8_t)(packed >> (8 * k));
     }
+  }
+  if (bin_cap && tid == 0) {
+    if (ST == 3) report_wanted_fill(total, offsets);
+    else atomicMax(total + 2, offsets[blockIdx.x]);
   }
 }
 
