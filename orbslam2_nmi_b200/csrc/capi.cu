@@ -310,6 +310,18 @@ int vc_point_size(const nmi_camera& cam) {
 // 1.5 records per (point, view) of a group and the group shrinks until that fits 2 GiB.
 // bin_scatter never writes past the buffer; an overflow raises a flag that every
 // synchronous entry point turns into an error (never a silently wrong render).
+// Growing the record buffer is a cudaFree + cudaMalloc of gigabytes (~0.5 s, seen as one slow frame in a
+// sequence): once a request passes 1 GiB the buffer goes straight to the 4 GiB that the single-pass layout
+// may ever ask for, so a sequence pays for it once, in its first search.
+int grow_records(nmi_ctx* c, size_t want) {
+  if (want <= c->records.cap) return NMI_OK;
+  const size_t limit = (4ull << 30) / sizeof(uint4);
+  if (want * sizeof(uint4) > (1ull << 30) && want < limit) want = limit;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(c->records.reserve(want));
+  return NMI_OK;
+}
+
 int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   const size_t tiles = (size_t)tiles_per_view(c->cam.W, c->cam.H);
   const bool fb = c->h_feedback && !c->force_conservative && !c->conservative_once && c->feedback_pending &&
@@ -331,10 +343,7 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
     cap = (cap + 7) / 8 * 8;
     const size_t want = tiles * (size_t)nviews * cap;
     if (want <= (4ull << 30) / sizeof(uint4) && want < 0xFFFFFFFFull) {
-      if (want > c->records.cap) {
-        CK(cudaStreamSynchronize(c->stream));
-        CK(c->records.reserve(want));
-      }
+      if (int rc = grow_records(c, want)) return rc;
       c->bin_cap = (uint32_t)cap;
       *group = nviews;
       CK(c->bin_cursor.reserve(tiles * (size_t)nviews));
@@ -364,10 +373,7 @@ int ensure_tile_buffers(nmi_ctx* c, int nviews, int* group) {
   CK(c->bin_cursor.reserve(nbins));
   size_t want = per_view * (size_t)g;
   if (want > cap_records) want = cap_records;
-  if (want > c->records.cap) {
-    CK(cudaStreamSynchronize(c->stream));
-    CK(c->records.reserve(want));
-  }
+  if (int rc = grow_records(c, want)) return rc;
   CK(cudaMemsetAsync(c->bin_total.p, 0, 4 * sizeof(uint32_t), c->stream));
   return NMI_OK;
 }
