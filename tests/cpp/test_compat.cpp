@@ -68,6 +68,18 @@ static int output_checks(const char* dir) {
   nmi_grid g{{3, 3, 3}, {3, 3, 3}, {0.2f, 0.2f, 0.5f}, {0.02f, 0.02f, 0.05f}};
   const int32_t bs[3] = {0, 1, 2}, bw[3] = {2, 1, 0};
   std::printf("NAME %s\n", overlay_name("res", 12, g, 0.25f, bs, bw).c_str());
+  std::printf("JNAME %s\n", overlay_name("res", 12, g, 0.25f, bs, bw, ".jpg").c_str());
+  {  // the same overlay as a JPEG (what cv::imwrite gives the reference's .jpg names): 83 x 37, not a multiple of 8
+    const int JW = 83, JH = 37;
+    std::vector<uint8_t> ji(JW * JH), js(JW * JH);
+    for (int y = 0; y < JH; y++)
+      for (int x = 0; x < JW; x++) {
+        ji[y * JW + x] = (uint8_t)(128 + 100 * std::sin(x / 9.0) * std::cos(y / 7.0));
+        js[y * JW + x] = (uint8_t)((x * 3 + y * 5) % 256 > 200 ? 255 : 40 + (x + 2 * y) % 150);
+      }
+    EXPECT(saveOverlayJPG((std::string(dir) + "/overlay.jpg").c_str(), ji.data(), js.data(), JW, JH));
+    EXPECT(saveOverlayBMP((std::string(dir) + "/overlay_ref.bmp").c_str(), ji.data(), js.data(), JW, JH));
+  }
   std::printf("OUTPUTS OK\n");
   return 0;
 }

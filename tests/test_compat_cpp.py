@@ -136,6 +136,19 @@ def test_compat_output_files(exe, tmp_path):
     assert bmp[54 + 32:54 + 35] == bytes([0, 100, 10])  # top row stored last
     name = [l for l in res.stdout.splitlines() if l.startswith("NAME ")][0][5:]
     assert name == "res/0012_NMI_[0.25]_WzyxSzyx_[0,1,2,2,1,0]_grid_[3x3x3_3x3x3].bmp"
+    jname = [l for l in res.stdout.splitlines() if l.startswith("JNAME ")][0][6:]
+    assert jname == name[:-4] + ".jpg"
+    # the JPEG writer (cv::imwrite's container for the reference's .jpg overlays): any decoder reads it, and the
+    # picture is the BMP's within quantisation error at quality 95
+    jpg = (tmp_path / "overlay.jpg").read_bytes()
+    assert jpg[:4] == b"\xff\xd8\xff\xe0" and jpg[6:11] == b"JFIF\0" and jpg[-2:] == b"\xff\xd9"
+    cv2 = pytest.importorskip("cv2")
+    got = cv2.imread(str(tmp_path / "overlay.jpg"), cv2.IMREAD_COLOR)
+    want = cv2.imread(str(tmp_path / "overlay_ref.bmp"), cv2.IMREAD_COLOR)
+    assert got is not None and got.shape == want.shape == (37, 83, 3)
+    err = got.astype(np.float64) - want.astype(np.float64)
+    psnr = 10 * np.log10(255.0 ** 2 / np.mean(err ** 2))
+    assert psnr > 32.0 and np.abs(err).max() < 60, (psnr, np.abs(err).max())
 
 
 def _loaded_cloud(d):
