@@ -221,6 +221,12 @@ struct nmi_ctx {
   unsigned char* h_frame[2] = {nullptr, nullptr};
   size_t h_frame_cap[2] = {0, 0};
   cudaEvent_t ev_frame[2] = {nullptr, nullptr};  // "the H2D out of staging buffer i is done"
+  // The frame is uploaded on stream2 -- the only stream that reads it during a search (texture refresh + warp
+  // kernel) -- so the cull / render stage on the main stream does not queue behind 2 MB crossing PCIe.
+  // ev_frame_order: main-stream work enqueued before the upload (it may still read the old frame);
+  // ev_frame_up: the upload; main-stream readers of the frame (nmi_warp_cells) and nmi_ctx_sync wait for it.
+  cudaEvent_t ev_frame_order = nullptr, ev_frame_up = nullptr;
+  bool frame_up_pending = false;
   int frame_slot = 0;
 
   DevBuf<unsigned long long> zbuf;
@@ -803,6 +809,8 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
   }
   CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_frame_order, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_frame_up, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -857,6 +865,8 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->ev_fork3) cudaEventDestroy(c->ev_fork3);
+  if (c->ev_frame_order) cudaEventDestroy(c->ev_frame_order);
+  if (c->ev_frame_up) cudaEventDestroy(c->ev_frame_up);
   if (c->ev_join3) cudaEventDestroy(c->ev_join3);
   if (c->stream3) cudaStreamDestroy(c->stream3);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -885,6 +895,10 @@ int nmi_ctx_set_hist_skip(nmi_ctx* c, int mode) {
 int nmi_ctx_sync(nmi_ctx* c) {
   REQUIRE(c, NMI_ERR_INVALID, "null ctx");
   CK(cudaStreamSynchronize(c->stream));
+  if (c->frame_up_pending) {  // a frame upload without a search behind it: the caller's pinned buffer is free after this
+    CK(cudaEventSynchronize(c->ev_frame_up));
+    c->frame_up_pending = false;
+  }
   if (c->feedback_pending && c->h_feedback && c->h_feedback[2] != 0) {
     arm_enqueued_retry(c);  // the next search gets bins of the size this one wanted
     set_error("tile renderer record buffer overflow in an enqueued search: its renders are incomplete; "
@@ -1117,9 +1131,12 @@ int nmi_set_frame(nmi_ctx* c, const uint8_t* gray, int W, int H) {
   const bool pinned = cudaPointerGetAttributes(&attr, gray) == cudaSuccess &&
                       attr.type == cudaMemoryTypeHost;
   cudaGetLastError();  // pageable pointers may leave a sticky-free error behind
+  // the upload runs on stream2, behind everything already enqueued on the main stream
+  CK(cudaEventRecord(c->ev_frame_order, c->stream));
+  CK(cudaStreamWaitEvent(c->stream2, c->ev_frame_order, 0));
   if (pinned) {
     // caller's buffer is page-locked: DMA straight from it (caller keeps it alive until sync)
-    CK(cudaMemcpyAsync(c->frame.p, gray, c->P, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->frame.p, gray, c->P, cudaMemcpyHostToDevice, c->stream2));
   } else {
     // pageable -> pinned staging so the H2D copy is a true async DMA on our stream
     const int slot = c->frame_slot;
@@ -1128,9 +1145,11 @@ int nmi_set_frame(nmi_ctx* c, const uint8_t* gray, int W, int H) {
     CK(cudaEventSynchronize(c->ev_frame[slot]));  // the upload that last used this buffer is done
     if (int rc = ensure_pinned(&c->h_frame[slot], &c->h_frame_cap[slot], c->P)) return rc;
     memcpy(c->h_frame[slot], gray, c->P);
-    CK(cudaMemcpyAsync(c->frame.p, c->h_frame[slot], c->P, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaEventRecord(c->ev_frame[slot], c->stream));
+    CK(cudaMemcpyAsync(c->frame.p, c->h_frame[slot], c->P, cudaMemcpyHostToDevice, c->stream2));
+    CK(cudaEventRecord(c->ev_frame[slot], c->stream2));
   }
+  CK(cudaEventRecord(c->ev_frame_up, c->stream2));
+  c->frame_up_pending = true;
   c->frame_tex_dirty = true;
   c->has_frame = true;
   return NMI_OK;
@@ -1142,6 +1161,7 @@ int nmi_set_frame_device(nmi_ctx* c, const void* gray_dev, int W, int H) {
   REQUIRE(W == c->cam.W && H == c->cam.H, NMI_ERR_INVALID, "frame size != camera size");
   CK(cudaSetDevice(c->device));
   CK(c->frame.reserve(c->pitch));
+  if (c->frame_up_pending) CK(cudaStreamWaitEvent(c->stream, c->ev_frame_up, 0));  // an earlier host upload lands first
   CK(cudaMemcpyAsync(c->frame.p, gray_dev, c->P, cudaMemcpyDeviceToDevice, c->stream));
   c->frame_tex_dirty = true;
   c->has_frame = true;
@@ -1274,6 +1294,7 @@ int nmi_warp_cells(nmi_ctx* c, const nmi_grid* g) {
     nmi_cell_homography_inv(&c->cam, g, wx, wy, wz, hm + 9 * (size_t)w);
   }
   CK(cudaMemcpyAsync(c->params.p, c->h_params, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (c->frame_up_pending) CK(cudaStreamWaitEvent(c->stream, c->ev_frame_up, 0));  // the frame is uploaded on stream2
   cudaTextureObject_t frame_tex = 0;
   if (int rc = ensure_frame_texture(c, c->stream, &frame_tex)) return rc;
   launch_warp(c->frame.p, frame_tex, c->cam.W, c->cam.H, reinterpret_cast<const float*>(c->params.p), nW,
