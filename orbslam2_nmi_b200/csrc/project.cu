@@ -6,11 +6,14 @@
 // Arithmetic follows SURVEY.md Appendix A.2/A.3 and is written with explicit
 // round-to-nearest intrinsics so it is bit-identical to oracle/nmi_oracle.c.
 //
-// Three kernels:
-//   cull_*         two passes over the float4 cloud (coalesced 16 B loads): drop the
-//                  points outside the union of all view frusta (conservative) and
-//                  compact the survivors {xyz, original index} IN ORDER (count, scan,
-//                  scatter), so the Morton order of the cloud survives;
+// Kernels:
+//   cull_compact   one pass over the float4 cloud (coalesced 16 B loads; whole 1 024-point blocks
+//                  are rejected by their load-time box without a load): drop the points outside
+//                  the union of all view frusta (conservative) and compact the survivors
+//                  {xyz, tie-break word}; blocks keep their Morton order inside, their order among
+//                  each other is that of one atomic per block (cull_count / cull_scan /
+//                  cull_scatter: the stable three-pass variant, $NMI_CULL_PASSES=3, and the scan
+//                  the mesh cull and the two-pass binning share);
 //   project_splat  survivors x the views of a group: fp32 projection, s x s splat, packed
 //                  (depth bits << 32 | tie-break word) atomicMin into the per-view
 //                  z-buffer, with a plain-load early-z test in front;
@@ -18,7 +21,6 @@
 // Point clouds go through the binned TILE renderer further down (bin_kernel / tile_resolve);
 // the global z-buffer path above serves the mesh model's resolve and splats wider than a tile.
 #include <climits>
-
 #include <cstdlib>
 
 #include "nmi_internal.h"
@@ -85,7 +87,8 @@ __device__ __forceinline__ bool cull_keep(const float4& p, const ViewConst& vc, 
 
 // Order-preserving (stable) compaction in three small kernels, so that the survivors keep
 // the Morton order of the cloud and a run of consecutive survivors stays a compact image
-// patch:  count per CTA -> exclusive scan of the CTA counts -> scatter.
+// patch:  count per CTA -> exclusive scan of the CTA counts -> scatter.  (The default is the one-pass
+// cull_compact_kernel below; this variant remains as $NMI_CULL_PASSES=3.)
 constexpr int kCullThreads = 256;
 constexpr int kCullPer = 4;                              // points per thread
 static_assert(kCullThreads * kCullPer == kCullBlock, "one CTA per AABB block");
