@@ -1028,6 +1028,7 @@ joint_hist_score_persistent_kernel(const HistArgs a) {
         skipT = ((ka & 0xFFu) << 8) | (kb & 0xFFu);
     }
     const bool skip = SKIPCAP && skipT != 0xFFFFFFFFu;
+    const bool marg = skip && a.img_hist != nullptr;  // skipped pixels come back through the image marginals
     const uint32_t a4 = ((skipT >> 8) & 0xFFu) * 0x01010101u, b4 = (skipT & 0xFFu) * 0x01010101u;
     uint32_t nboth = 0;
 
@@ -1051,6 +1052,8 @@ joint_hist_score_persistent_kernel(const HistArgs a) {
           }
           if (dr != 0u && dw != 0u) {
             accum_fast<P_U16G, SWZ, NW>(sm, r, w, 0, warp);
+          } else if (marg) {
+            // not counted at all: marginal_side_counts() reconstructs row a* and column b*
           } else if (dr == 0u && dw == 0u) {
             nboth += PIX;
           } else {
@@ -1070,7 +1073,10 @@ joint_hist_score_persistent_kernel(const HistArgs a) {
       if (lane == 0) mbar_arrive(&sm.empty[st]);
     }
 
-    if (skip) {  // fold the side tables into copy 0
+    if (SKIPCAP && marg) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));  // every increment of this pair has landed
+      if constexpr (SKIPCAP) marginal_side_counts<SWZ, NWARPS>(sm, sk, a, pr, skipT, warp, lane);
+    } else if (skip) {  // fold the side tables into copy 0
       if (nboth) atomicAdd(&sk.nboth, nboth);
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumers));
       for (int i = tid; i < 512; i += kConsumers) {
@@ -1911,6 +1917,14 @@ int launch_joint_hist_score(const HistArgs& a, cudaStream_t st) {
   if (a.npairs <= 0) return 0;
   if (hist_uses_cluster(a)) return launch_cluster(a, st);
   if (a.bins == 256 && a.skipcap && a.bg && a.img_mode != nullptr) {
+    // with the image marginals the skipped pixels cost nothing and the pairs of a search differ less in cost than
+    // with the side tables: the persistent CTAs' static schedule does ($NMI_SKIP_PERSISTENT=0: one CTA per pair)
+    static const bool skip_persistent = [] {
+      const char* e = getenv("NMI_SKIP_PERSISTENT");
+      return !(e && atoi(e) == 0);
+    }();
+    if (a.variant == 0 && a.img_hist != nullptr && a.dumpJ == nullptr && skip_persistent)
+      return launch_persistent<true, true>(a, st);
     switch (a.variant) {  // the packed-u16 builds that carry the side tables
       case 0: case 8: case 9: return launch_t<P_U16G, true, 16, true, true>(a, st);
       case 4: return launch_t<P_U16G, true, 32, false, true>(a, st);

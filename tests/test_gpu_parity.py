@@ -223,6 +223,32 @@ def test_hot_bin_skipping_is_exact(searcher, oracle, mode, frame_kind, n_points,
         searcher.set_hist_skip(1)
 
 
+@pytest.mark.parametrize("frame_kind", ["sky", "constant"])
+def test_hot_bin_skipping_persistent_ctas(searcher, oracle, frame_kind):
+    """More pairs than SMs with hot-bin skipping forced on: the persistent build (several pairs per CTA, the
+    skipped pixels reconstructed from the image marginals pair after pair) scores what the oracle scores --
+    bit for bit -- and what the build without skipping scores."""
+    sc = synth.make_scene("tiny", n_points=3000)
+    g = Grid.make((3, 3, 2), (3, 3, 2), (0.2, 0.2, 0.5), (0.02, 0.02, 0.05))  # 324 pairs on 148 SMs
+    frame = {"sky": synth.frame_sky, "constant": synth.frame_constant}[frame_kind](sc.W, sc.H)
+    searcher.set_scene(sc)
+    searcher.set_frame(frame)
+    scores, _, _ = oracle.search_points(sc, sc.Twc, g, sc.xyzi, frame)
+    try:
+        got = {}
+        for mode in (2, 0):
+            searcher.set_hist_skip(mode)
+            for _ in range(2):
+                res = searcher.search(sc.Twc, g, want_scores=True)
+            assert searcher.last_hist_path() == (2 if mode == 2 else 1)
+            got[mode] = res.scores.copy()
+            assert np.array_equal(res.scores.view(np.uint32), scores.view(np.uint32)), f"skip mode {mode}"
+            assert res.best_index == oracle.argmax(scores)[0]
+        assert np.array_equal(got[2].view(np.uint32), got[0].view(np.uint32))
+    finally:
+        searcher.set_hist_skip(1)
+
+
 @pytest.mark.parametrize("case", range(14))
 def test_randomized_parity(searcher, oracle, case):
     """Seeded random scenes / grids / flags / kernel options against the oracle: renders
