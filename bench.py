@@ -603,10 +603,12 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def step_device():
-        with torch.cuda.stream(stream):
-            searcher.search_enqueue(scene.Twc, grid, flags, rank, world, key.data_ptr())
-            if world > 1:
+        if world > 1:
+            with torch.cuda.stream(stream):
+                searcher.search_enqueue(scene.Twc, grid, flags, rank, world, key.data_ptr())
                 dist.all_reduce(key, op=dist.ReduceOp.MAX)
+        else:  # the library enqueues on its own stream; torch's current stream only matters for the collective
+            searcher.search_enqueue(scene.Twc, grid, flags, rank, world, key.data_ptr())
         searcher.sync()  # stream sync + surfaces a record-buffer overflow of the enqueued search
 
     def step_e2e():
