@@ -558,7 +558,7 @@ void fill_pair_schedule(int2* hp, uint32_t* hi, int nvl, int nwl, int nS_total, 
 // grid search (Tracking.cc:1886-1905).  Records ev[4..6].
 int score_pairs_launch(nmi_ctx* c, const nmi_flags* f, int nvl, int nwl, const int2* d_pairs,
                        const uint32_t* d_index, size_t npl, size_t nP, unsigned long long* key_dev,
-                       float* scores_dev, bool tiled) {
+                       float* scores_dev, bool tiled, bool modes_sampled = false) {
   if (c->timed) CK(cudaEventRecord(c->ev[4], c->stream));
   // hot-bin skipping: sample every image's dominant grey level (decides per pair inside the
   // kernel); the build with the side tables is launched when the previous search saw levels
@@ -568,10 +568,12 @@ int score_pairs_launch(nmi_ctx* c, const nmi_flags* f, int nvl, int nwl, const i
   if (use_skip) {
     if (c->hist_skip == 1 && c->hot_pending && cudaEventQuery(c->ev_hot) == cudaSuccess)
       skipcap = ((unsigned long long)c->h_feedback[5] + c->h_feedback[6]) * 6ull >= c->hot_total;
-    CK(c->img_mode.reserve((size_t)(nvl + nwl)));
-    CK(c->hot.reserve(2));
-    c->launches += launch_image_modes(c->renders.p, c->pitch, nvl, c->warps.p, c->pitch, nwl, (uint32_t)c->P,
-                                      c->img_mode.p, c->hot.p, c->stream);
+    if (!modes_sampled) {  // (a search has done it already: renders and warps each behind their own kernels)
+      CK(c->img_mode.reserve((size_t)(nvl + nwl)));
+      CK(c->hot.reserve(2));
+      c->launches += launch_image_modes(c->renders.p, c->pitch, nvl, c->warps.p, c->pitch, nwl, (uint32_t)c->P,
+                                        c->img_mode.p, c->hot.p, c->stream);
+    }
     CK(cudaMemcpyAsync(c->h_feedback + 5, c->hot.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaEventRecord(c->ev_hot, c->stream));
     c->hot_pending = true;
@@ -735,12 +737,23 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   memcpy(c->Twc, Twc, sizeof(float) * 16);
   // fork: the warps of the camera frame (issue-bound) overlap the render stage (atomic- and
   // latency-bound) on a second stream; both only need the uploaded parameters
+  // hot-bin skipping samples every image's dominant grey level (score_pairs_launch): the warps right behind the
+  // warp kernel on stream2, the renders behind the render stage -- neither sits between the join and the histogram
+  const bool sample_modes = c->hist_skip != 0 && f->bins == 256 && f->bg;
+  if (sample_modes) {
+    CK(c->img_mode.reserve((size_t)(nvl + nwl)));
+    CK(c->hot.reserve(2));
+    CK(cudaMemsetAsync(c->hot.p, 0, 2 * sizeof(uint32_t), c->stream));
+  }
   CK(cudaEventRecord(c->ev_fork, c->stream));
   CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
   cudaTextureObject_t frame_tex = 0;
   if (int rc = ensure_frame_texture(c, c->stream2, &frame_tex)) return rc;
   launch_warp(c->frame.p, frame_tex, c->cam.W, c->cam.H, d_minv, nwl, c->warps.p, c->pitch, c->stream2);
   c->launches++;
+  if (sample_modes)
+    c->launches += launch_image_modes(nullptr, 0, 0, c->warps.p, c->pitch, nwl, (uint32_t)c->P, c->img_mode.p + nvl,
+                                      c->hot.p, c->stream2, false);
   CK(cudaEventRecord(c->ev_join, c->stream2));
   if (int rc = cull_model(c, vc, Twc, margin)) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
@@ -758,11 +771,15 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
     CK(cudaEventRecord(c->ev_join3, c->stream3));
     CK(cudaStreamWaitEvent(c->stream, c->ev_join3, 0));
   }
+  if (sample_modes)
+    c->launches += launch_image_modes(c->renders.p, c->pitch, nvl, nullptr, 0, 0, (uint32_t)c->P, c->img_mode.p, c->hot.p,
+                                      c->stream, false);
   // stage events: [1] = project + resolve of all view groups (interleaved), [2] = 0
   if (c->timed) CK(cudaEventRecord(c->ev[2], c->stream));
   if (c->timed) CK(cudaEventRecord(c->ev[3], c->stream));
   CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join: the warps are done
-  if (int rc = score_pairs_launch(c, f, nvl, nwl, d_pairs, d_index, npl, nP, key_dev, scores_dev, tiled)) return rc;
+  if (int rc = score_pairs_launch(c, f, nvl, nwl, d_pairs, d_index, npl, nP, key_dev, scores_dev, tiled, sample_modes))
+    return rc;
 
   c->conservative_once = false;
   c->was_sized_retry = c->retry_fullest_once != 0;

@@ -1884,9 +1884,9 @@ void launch_term_table(float* tab, uint32_t length, cudaStream_t st) {
 uint32_t image_mode_sample_total(uint32_t npix) { return ((npix / 16 + 63) / 64) * 16; }
 
 int launch_image_modes(const uint8_t* renders, size_t rpitch, int nr, const uint8_t* warps, size_t wpitch,
-                       int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st) {
+                       int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st, bool clear_hot) {
   if (nr + nw == 0) return 0;
-  cudaMemsetAsync(hot, 0, 2 * sizeof(uint32_t), st);
+  if (clear_hot) cudaMemsetAsync(hot, 0, 2 * sizeof(uint32_t), st);
   prefer_max_shared((const void*)image_mode_kernel);
   image_mode_kernel<<<nr + nw, kImThreads, 0, st>>>(renders, rpitch, nr, warps, wpitch, npix, img_mode, hot);
   return 1;

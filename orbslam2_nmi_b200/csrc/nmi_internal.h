@@ -84,8 +84,10 @@ bool hist_uses_cluster(const HistArgs& a);
 int launch_joint_hist_score(const HistArgs& a, cudaStream_t st);  // returns launches, <0 on error
 // sampled per-image modes for HistArgs::img_mode; hot[0] / hot[1] = largest sampled count over
 // the renders / the warps.  Returns launches.
+// clear_hot = false: hot[] was zeroed by the caller (a search samples its renders and its warps in two launches,
+// each on the stream that produced them)
 int launch_image_modes(const uint8_t* renders, size_t rpitch, int nr, const uint8_t* warps, size_t wpitch,
-                       int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st);
+                       int nw, uint32_t npix, uint32_t* img_mode, uint32_t* hot, cudaStream_t st, bool clear_hot = true);
 uint32_t image_mode_sample_total(uint32_t npix);
 // img_hist[(nr + nw) * 256]: exact histograms of all npix pixels of every image.  Returns launches.
 int launch_image_hists(const uint8_t* renders, size_t rpitch, int nr, const uint8_t* warps, size_t wpitch,
