@@ -611,13 +611,17 @@ def run_gpu(args):
             searcher.search_enqueue(scene.Twc, grid, flags, rank, world, key.data_ptr())
         searcher.sync()  # stream sync + surfaces a record-buffer overflow of the enqueued search
 
+    h_frame_np = h_frame.numpy()
+
     def step_e2e():
         # public API with HOST buffers: frame H2D + search + winner key D2H, every step
-        searcher.set_frame(h_frame.numpy())
+        searcher.set_frame(h_frame_np)
+        if world == 1:  # the C ABI alone: enqueue, then nmi_read_key (8-byte D2H + stream sync)
+            searcher.search_enqueue(scene.Twc, grid, flags, rank, world, key.data_ptr())
+            return searcher.read_key(key.data_ptr())
         with torch.cuda.stream(stream):
             searcher.search_enqueue(scene.Twc, grid, flags, rank, world, key.data_ptr())
-            if world > 1:
-                dist.all_reduce(key, op=dist.ReduceOp.MAX)
+            dist.all_reduce(key, op=dist.ReduceOp.MAX)
             h_key.copy_(key, non_blocking=True)
         searcher.sync()
         return int(h_key.item())
@@ -662,10 +666,12 @@ def run_gpu(args):
 
     def step_e2e_pageable():
         searcher.set_frame(pageable)
+        if world == 1:
+            searcher.search_enqueue(scene.Twc, grid, flags, rank, world, key.data_ptr())
+            return searcher.read_key(key.data_ptr())
         with torch.cuda.stream(stream):
             searcher.search_enqueue(scene.Twc, grid, flags, rank, world, key.data_ptr())
-            if world > 1:
-                dist.all_reduce(key, op=dist.ReduceOp.MAX)
+            dist.all_reduce(key, op=dist.ReduceOp.MAX)
             h_key.copy_(key, non_blocking=True)
         searcher.sync()
 
