@@ -363,6 +363,9 @@ project_splat_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict
 #ifndef NMI_BIN_CTAS
 #define NMI_BIN_CTAS 8   // resident CTAs per SM the register budget is cut for
 #endif
+#ifndef NMI_BIN_THREADS
+#define NMI_BIN_THREADS 256  // threads per CTA (128 / 512 measured: no difference)
+#endif
 constexpr int kTile = 32;  // (bin_kernel shifts by 5)
 constexpr int kTileThreads = 128;
 
@@ -400,7 +403,7 @@ __device__ __forceinline__ Splat project_splat_point(const float4& p, const floa
 // pass of the counting sort).  MODE 2: single pass into fixed-capacity bins (capacity known
 // from the previous search; a bin that fills up raises the overflow flag).
 template <int MODE>
-__global__ void __launch_bounds__(256, NMI_BIN_CTAS)
+__global__ void __launch_bounds__(NMI_BIN_THREADS, NMI_BIN_CTAS * 256 / NMI_BIN_THREADS)
 bin_kernel(const float4* __restrict__ cpts, const uint32_t* __restrict__ ctag,
            const uint32_t* __restrict__ counter, const float4* __restrict__ centres, int nviews,
            ViewConst vc, int ntx, int nt, uint32_t* __restrict__ counts,
@@ -772,7 +775,7 @@ void launch_bin_points(int mode, const float4* cpts, const uint32_t* ctag, const
                        uint32_t* overflow, cudaStream_t st) {
   if (nviews == 0) return;
   const int ntx = (vc.W + kTile - 1) / kTile, nty = (vc.H + kTile - 1) / kTile;
-  const dim3 grid(sm_count() * 16), block(256);
+  const dim3 grid(sm_count() * 16 * 256 / NMI_BIN_THREADS), block(NMI_BIN_THREADS);
   const size_t smem = sizeof(float4) * nviews;
   prefer_max_shared((const void*)bin_kernel<0>);
   prefer_max_shared((const void*)bin_kernel<1>);
