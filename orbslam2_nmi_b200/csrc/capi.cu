@@ -697,10 +697,14 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   // together (~64 MB of the 126 MB): the z-buffer is written, resolved and reset without
   // ever being streamed through HBM, and only `group` views of it exist.
   const size_t zb_view = c->P * sizeof(unsigned long long);
-  const size_t zb_budget = [] {  // bytes of z-buffer kept in flight (L2 is 126 MB); read per search (tests shrink it)
+  const size_t zb_env = [] {  // bytes of z-buffer kept in flight (L2 is 126 MB); read per search (tests shrink it)
     const char* e = getenv("NMI_ZBUF_MB");
     return (size_t)(e && atoi(e) > 0 ? atoi(e) : 64) << 20;
   }();
+  // A mesh search keeps, per view in flight, its z-buffer AND its slice of the vertex table in L2, next to the
+  // triangle / UV / texture data the shading pass gathers from: half the budget (C3, render stage: groups of
+  // 2 / 4 / 8 / 16 views per stream 1.42 / 1.27 / 1.47 / 1.79 ms)
+  const size_t zb_budget = c->n_tris ? zb_env / 2 : zb_env;
   static const bool mesh_two_streams = [] {
     const char* e = getenv("NMI_MESH_STREAMS");
     return !(e && atoi(e) == 1);

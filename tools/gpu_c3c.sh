@@ -1,2 +1,2 @@
 #!/bin/bash
-for v in 1 2 3 4; do echo "shade variant $v"; NMI_SHADE_V=$v python tools/exp_c3_profile.py 6 2>&1 | tail -2 | head -1; done
+for z in 8 16 32 48; do echo "zbuf MB $z"; NMI_ZBUF_MB=$z python tools/exp_c3_profile.py 6 2>&1 | tail -2 | head -1; done
