@@ -137,11 +137,12 @@ struct nmi_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // the frame warps run here, concurrently with the render stage
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  // mesh models: the view groups of a search alternate between `stream` and `stream3` (each with its own
-  // half of the z-buffer and of the vertex table), so that the issue-bound raster kernel of one group runs
-  // under the latency-bound shading kernel of the other
-  cudaStream_t stream3 = nullptr;
-  cudaEvent_t ev_fork3 = nullptr, ev_join3 = nullptr;
+  // mesh models: the view groups of a search take turns on `stream` and up to three more streams (each with
+  // its own slot of the z-buffer and of the vertex table), so that the issue-bound raster kernel of one group
+  // runs under the latency-bound shading kernel of another
+  static constexpr int kMeshStreams = 4;  // slot 0 = `stream`, slots 1.. = mesh_stream[]
+  cudaStream_t mesh_stream[kMeshStreams - 1] = {};
+  cudaEvent_t ev_fork3 = nullptr, ev_join3[kMeshStreams - 1] = {};
   cudaEvent_t ev[8] = {};
   cudaEvent_t ev_params = nullptr;  // completion of the last H2D from h_params
   bool params_in_flight = false;
@@ -176,6 +177,7 @@ struct nmi_ctx {
   DevBuf<float> mluma;
   // per-view vertex table of the current view group ([vertex][view], mesh.cu) + the vertices the
   // cull flagged (corners of surviving triangles)
+  int mesh_slots = 1;  // view groups in flight in the current mesh search (stream slots of z-buffer / vertex table)
   DevBuf<int4> mtv;
   DevBuf<uint8_t> mvflag;
   size_t n_verts = 0;
@@ -502,10 +504,10 @@ int draw_views(nmi_ctx* c, const ViewConst& vc, const float4* d_centres, int nvi
     return NMI_OK;
   }
   // half 1 (mesh view groups only): second stream, second half of the z-buffer and of the vertex table
-  cudaStream_t st = half ? c->stream3 : c->stream;
+  cudaStream_t st = half ? c->mesh_stream[half - 1] : c->stream;
   unsigned long long* zb = c->zbuf.p + (size_t)half * half_views * c->P;
   if (c->n_tris) {
-    CK(c->mtv.reserve(c->n_verts * (half_views ? 2 * half_views : (size_t)nviews)));
+    CK(c->mtv.reserve(c->n_verts * (half_views ? (size_t)c->mesh_slots * half_views : (size_t)nviews)));
     int4* tv = c->mtv.p + (size_t)half * half_views * c->n_verts;
     launch_mesh_vertices(c->mverts.p, c->mvflag.p, (uint32_t)c->n_verts, d_centres, nviews, vc, tv, st);
     launch_mesh_raster(tv, (uint32_t)c->n_verts, c->mtris.p, c->mtri_orig.p, c->mslots.p, c->counter.p, nviews, vc, zb, c->P, st);
@@ -705,13 +707,16 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   // triangle / UV / texture data the shading pass gathers from: half the budget (C3, render stage: groups of
   // 2 / 4 / 8 / 16 views per stream 1.42 / 1.27 / 1.47 / 1.79 ms)
   const size_t zb_budget = c->n_tris ? zb_env / 2 : zb_env;
-  static const bool mesh_two_streams = [] {
+  static const int mesh_streams = [] {  // view groups of a mesh search in flight, one stream each (1..4)
     const char* e = getenv("NMI_MESH_STREAMS");
-    return !(e && atoi(e) == 1);
+    const int k = e ? atoi(e) : 4;  // C3 render stage with 1 / 2 / 3 / 4 streams: 1.44 / 1.28 / 1.26 / 1.25 ms
+    return k < 1 ? 1 : (k > nmi_ctx::kMeshStreams ? nmi_ctx::kMeshStreams : k);
   }();
   // mesh: two groups are in flight (one per stream), each with half of the budget
-  const bool pingpong = c->n_tris && mesh_two_streams && (size_t)nvl * zb_view > zb_budget / 2 && nvl >= 4;
-  int group = (int)(zb_budget / (pingpong ? 2 : 1) / (zb_view ? zb_view : 1));
+  const bool pingpong = c->n_tris && mesh_streams > 1 && (size_t)nvl * zb_view > zb_budget / 2 && nvl >= 4;
+  const int slots = pingpong ? mesh_streams : 1;
+  c->mesh_slots = slots;
+  int group = (int)(zb_budget / (size_t)slots / (zb_view ? zb_view : 1));
   if (group < 1) group = 1;
   if (group > nvl) group = nvl;
   if (group > kMaxViewsPerLaunch) group = kMaxViewsPerLaunch;
@@ -719,14 +724,14 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
     int p2 = 1;
     while (p2 * 2 <= group && p2 < 32) p2 *= 2;
     // ... and a 16-byte entry of the vertex table per (vertex, view of the group): at most 4 GiB
-    while (p2 > 1 && c->n_verts * (size_t)p2 * sizeof(int4) * (pingpong ? 2 : 1) > (4ull << 30)) p2 /= 2;
+    while (p2 > 1 && c->n_verts * (size_t)p2 * sizeof(int4) * (size_t)slots > (4ull << 30)) p2 /= 2;
     group = p2;
   }
   const bool tiled = !c->n_tris && vc_point_size(c->cam) <= 32;
   if (tiled) {
     if (int rc = ensure_tile_buffers(c, nvl, &group)) return rc;
   } else {
-    if (int rc = ensure_zbuf(c, (size_t)group * c->P * (pingpong ? 2 : 1))) return rc;
+    if (int rc = ensure_zbuf(c, (size_t)group * c->P * (size_t)slots)) return rc;
   }
 
   c->launches = 0;
@@ -761,20 +766,21 @@ int search_impl(nmi_ctx* c, const float Twc[16], const nmi_grid* g, const nmi_fl
   CK(cudaEventRecord(c->ev_join, c->stream2));
   if (int rc = cull_model(c, vc, Twc, margin)) return rc;
   if (c->timed) CK(cudaEventRecord(c->ev[1], c->stream));
-  if (pingpong) {  // both streams start behind the cull
+  if (pingpong) {  // all streams start behind the cull
     CK(cudaEventRecord(c->ev_fork3, c->stream));
-    CK(cudaStreamWaitEvent(c->stream3, c->ev_fork3, 0));
+    for (int k = 1; k < slots; k++) CK(cudaStreamWaitEvent(c->mesh_stream[k - 1], c->ev_fork3, 0));
   }
   for (int v0 = 0, gi = 0; v0 < nvl; v0 += group, gi++) {
     const int nv = nvl - v0 < group ? nvl - v0 : group;
     if (int rc = draw_views(c, vc, d_centres + v0, nv, c->renders.p + (size_t)v0 * c->pitch, nullptr,
-                            pingpong ? (gi & 1) : 0, pingpong ? (size_t)group : 0))
+                            pingpong ? gi % slots : 0, pingpong ? (size_t)group : 0))
       return rc;
   }
-  if (pingpong) {
-    CK(cudaEventRecord(c->ev_join3, c->stream3));
-    CK(cudaStreamWaitEvent(c->stream, c->ev_join3, 0));
-  }
+  if (pingpong)
+    for (int k = 1; k < slots; k++) {
+      CK(cudaEventRecord(c->ev_join3[k - 1], c->mesh_stream[k - 1]));
+      CK(cudaStreamWaitEvent(c->stream, c->ev_join3[k - 1], 0));
+    }
   if (sample_modes)
     c->launches += launch_image_modes(c->renders.p, c->pitch, nvl, nullptr, 0, 0, (uint32_t)c->P, c->img_mode.p, c->hot.p,
                                       c->stream, false);
@@ -828,11 +834,11 @@ int nmi_ctx_create(int device, nmi_ctx** out) {
     CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio ? hi : lo));
     CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, lo));
   }
-  CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  for (auto& st : c->mesh_stream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_frame_order, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_frame_up, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming));
+  for (auto& ev : c->ev_join3) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (auto& e : c->ev) CK(cudaEventCreate(&e));
@@ -888,8 +894,10 @@ void nmi_ctx_destroy(nmi_ctx* c) {
   if (c->ev_fork3) cudaEventDestroy(c->ev_fork3);
   if (c->ev_frame_order) cudaEventDestroy(c->ev_frame_order);
   if (c->ev_frame_up) cudaEventDestroy(c->ev_frame_up);
-  if (c->ev_join3) cudaEventDestroy(c->ev_join3);
-  if (c->stream3) cudaStreamDestroy(c->stream3);
+  for (auto ev : c->ev_join3)
+    if (ev) cudaEventDestroy(ev);
+  for (auto st : c->mesh_stream)
+    if (st) cudaStreamDestroy(st);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
