@@ -41,7 +41,7 @@ void launch_tile_resolve(const uint4* rec, uint32_t rec_cap, uint32_t bin_cap, c
 // mesh.cu
 void launch_mesh_values(const float4* verts, const uint3* tris, const uint32_t* tri_orig, uint8_t* val,
                         uint32_t nt, cudaStream_t st);
-void launch_mesh_cull(const float4* verts, const uint3* tris, uint32_t nt, const ViewConst& vc,
+int launch_mesh_cull(const float4* verts, const uint3* tris, uint32_t nt, const ViewConst& vc,
                       const float c0[3], const float margin[3], uint32_t* slots, uint32_t* counter,
                       uint32_t* block_counts, uint8_t* vflag, uint32_t nv, cudaStream_t st);
 void launch_mesh_vertices(const float4* verts, const uint8_t* vflag, uint32_t nv, const float4* centres, int nviews,
@@ -452,9 +452,8 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int cull_model(nmi_ctx* c, const ViewConst& vc, const float Twc[16], const float margin[3]) {
   const float c0[3] = {Twc[3], Twc[7], Twc[11]};
   if (c->n_tris) {
-    launch_mesh_cull(c->mverts.p, c->mtris.p, (uint32_t)c->n_tris, vc, c0, margin, c->mslots.p,
-                     c->counter.p, c->block_counts.p, c->mvflag.p, (uint32_t)c->n_verts, c->stream);
-    c->launches += 3;
+    c->launches += launch_mesh_cull(c->mverts.p, c->mtris.p, (uint32_t)c->n_tris, vc, c0, margin, c->mslots.p,
+                                    c->counter.p, c->block_counts.p, c->mvflag.p, (uint32_t)c->n_verts, c->stream);
   } else {
     c->launches += launch_cull_compact(c->pts.p, c->tag.p, (uint32_t)c->n_pts, c->use_block_cull ? c->aabb.p : nullptr, vc, c0, margin,
                         c->cpts.p, c->cidx.p,

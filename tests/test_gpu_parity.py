@@ -616,7 +616,7 @@ def test_mesh_triangle_size_paths(searcher, oracle, n, height, monkeypatch):
     searcher.set_frame(synth.frame_textured(sc.W, sc.H, seed=8))
     monkeypatch.setenv("NMI_ZBUF_MB", "4")  # 0.5 MB of z-buffer per view, half of the budget for a mesh: three groups of two views, two streams
     searcher.search(Twc, g)
-    assert searcher.timings()[1] >= 1 + 3 + 3 * 3 + 2  # warp, cull, 3 groups x (vertices, raster, shade), histogram, argmax
+    assert searcher.timings()[1] >= 1 + 1 + 3 * 3 + 2  # warp, cull, >= 3 groups x (vertices, raster, shade), histogram, argmax
     for s in range(g.n_synth):
         t = oracle.cell_translation(Twc, g, s % 3, s // 3, 0)
         win, img = oracle.render_mesh_tex(sc, Twc, t, verts, tris, uv, tex)
