@@ -210,6 +210,14 @@ __device__ __forceinline__ void u16g_repay_if_crossed(Smem& sm, uint32_t t, uint
   }
 }
 
+// 64-bin policy: word of bin (a >> 2, b >> 2) inside a 64 x 64 sub-histogram, t = a << 8 | b.  Row-major with the
+// low five bits of the column XORed with the row: the bank of a bin then mixes both images (as the packed-u16
+// swizzle does), instead of being the warp image's value alone -- a smooth camera frame put the 32 lanes of an
+// atomic on a handful of banks.
+__device__ __forceinline__ uint32_t b64_word(uint32_t t) {
+  return (((t >> 4) & 0xFC0u) | ((t >> 2) & 0x3Fu)) ^ ((t >> 10) & 0x1Fu);
+}
+
 // generic (branchy) per-pixel path: partial chunks and BG == false
 template <int POLICY, bool SWZ>
 __device__ __forceinline__ void accum_one(Smem& sm, uint32_t t, int pass, int warp) {
@@ -220,8 +228,7 @@ __device__ __forceinline__ void accum_one(Smem& sm, uint32_t t, int pass, int wa
   } else if (POLICY == P_U32X2) {
     if ((int)(t >> 15) == pass) atomicAdd(sm.hist + (t & 0x7FFFu), 1u);
   } else {
-    const uint32_t idx = ((t >> 4) & 0xFC0u) | ((t >> 2) & 0x3Fu);
-    atomicAdd(sm.hist + (warp & (kB64Copies - 1)) * 4096 + idx, 1u);
+    atomicAdd(sm.hist + (warp & (kB64Copies - 1)) * 4096 + b64_word(t), 1u);
   }
 }
 
@@ -298,7 +305,7 @@ __device__ __forceinline__ void accum_fast(Smem& sm, const uint32_t (&rw)[NW], c
 #pragma unroll
     for (int i = 0; i < N; i++) {
       const uint32_t t = __byte_perm(ww[i >> 2], rw[i >> 2], 0x4440 + (i & 3) * 0x11);
-      atomicAdd(h + (((t >> 4) & 0xFC0u) | ((t >> 2) & 0x3Fu)), 1u);
+      atomicAdd(h + b64_word(t), 1u);
     }
   }
 }
@@ -435,7 +442,7 @@ __device__ __forceinline__ void rows_epilogue(Smem& sm, int pass, float L, const
       uint32_t rs = 0;
 #pragma unroll
       for (int k = 0; k < 2; k++) {
-        const uint32_t c = sm.hist[row * 64 + lane + 32 * k];
+        const uint32_t c = sm.hist[row * 64 + ((lane + 32 * k) ^ (row & 31))];  // b64_word's swizzle undone
         rs += c;
         col[k] += c;
         v[k] = term_t(sm.term_tab, a.term_tab, c, L);
