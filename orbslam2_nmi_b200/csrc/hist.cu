@@ -76,7 +76,10 @@ constexpr int kEvCap = 2048;       // >= npix / 4096 drain events (npix <= 8.3M)
 constexpr uint32_t kFlagMask = 0xF000F000u;  // a field >= 4096 has one of these bits set
 constexpr uint32_t kCross = 0x0FFFu;         // low 12 bits of a field: 0 right after a crossing
 constexpr int kHistWords = 32768;  // 128 KiB
-constexpr int kB64Copies = 8;
+#ifndef NMI_B64_COPIES
+#define NMI_B64_COPIES 8
+#endif
+constexpr int kB64Copies = NMI_B64_COPIES;  // replicated 64 x 64 sub-histograms (one per pair of consumer warps)
 constexpr int kTermTab = 1024;     // counts below this take their entropy term from a table
 
 enum Policy { P_U16G = 0, P_U32X2 = 2, P_B64 = 3 };
